@@ -1,0 +1,217 @@
+/* psc_b200 -- C ABI of the B200-native (sm_100a) implementation of PSC's per-timestep
+ * particle-in-cell hot path.  This is the drop-in boundary: the C++ wrapper types in
+ * include/psc_b200/psc_config_b200.hxx (MparticlesB200, MfieldsStateB200,
+ * PushParticlesB200, SortB200, BndParticlesB200, BndB200, BndFieldsB200,
+ * PushFieldsB200, MarderB200, ChecksB200 -> PscConfig1vbecB200<Dim>) are thin
+ * shells over these entry points, and so are the Python test/bench bindings.
+ *
+ * Conventions
+ *   - one opaque context per process/GPU ("rank"); not thread-safe per context
+ *   - every call returns 0 on success, non-zero on error; psc_b200_last_error()
+ *     gives the text.  No exceptions cross the boundary.  (PSC itself aborts on
+ *     error: libpsc/bits.hxx:35-40, cuda/cuda_bits.h:32-40.)
+ *   - all device memory is owned by the context; host pointers are borrowed for
+ *     the duration of the call only
+ *   - calls are stream-ordered on the context's stream; calls that return data to
+ *     the host synchronise, everything else is asynchronous until psc_b200_sync
+ *   - there is NO CPU fallback: every operator launches CUDA kernels and fails
+ *     with an error if no device is present
+ *
+ * Data layouts are PSC's (so a deck's data moves with plain copies):
+ *   fields    float [p][m][iz][iy][ix], ix fastest; dims ldims + 2*ibn, lower bound
+ *             -ibn (src/include/fields3d.hxx:29-32,284-291); m = JXI..HZ
+ *             (src/include/psc.h:26-38)
+ *   particles 32-byte records {float x[3]; float u[3]; int kind; float qni_wni}
+ *             = ParticleSimple<float> (src/include/particle_simple.hxx:10-42),
+ *             x patch-relative in physical units, patch p = [off[p], off[p+1])
+ *   patches   "bydim" order p = (pz*npy + py)*npx + px
+ *             (src/libmrc/src/mrc_domain_lib.c:21-35); a rank owns a contiguous
+ *             range of that list (src/libmrc/src/mrc_domain_multi.c:162-193)
+ */
+#ifndef PSC_B200_H
+#define PSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSC_B200_MAX_KINDS 10 /* push_particles_1vb.hxx:11 */
+#define PSC_B200_NR_FIELDS 9
+
+/* field components, src/include/psc.h:26-38 */
+enum
+{
+  PSC_B200_JXI,
+  PSC_B200_JYI,
+  PSC_B200_JZI,
+  PSC_B200_EX,
+  PSC_B200_EY,
+  PSC_B200_EZ,
+  PSC_B200_HX,
+  PSC_B200_HY,
+  PSC_B200_HZ
+};
+
+/* src/include/grid/BC.h:8-24 */
+enum
+{
+  PSC_B200_BND_FLD_OPEN,
+  PSC_B200_BND_FLD_PERIODIC,
+  PSC_B200_BND_FLD_CONDUCTING_WALL,
+  PSC_B200_BND_FLD_ABSORBING
+};
+enum
+{
+  PSC_B200_BND_PRT_REFLECTING,
+  PSC_B200_BND_PRT_PERIODIC,
+  PSC_B200_BND_PRT_ABSORBING,
+  PSC_B200_BND_PRT_OPEN
+};
+
+/* which 1vb deposit: src/psc_config.hxx:47-72 picks VAR1 for dim_yz and SPLIT for
+ * dim_xyz in production; PSC's tests use SPLIT for yz too. */
+enum
+{
+  PSC_B200_DEPOSIT_DEFAULT = -1,
+  PSC_B200_DEPOSIT_VAR1 = 0,
+  PSC_B200_DEPOSIT_SPLIT = 1
+};
+
+typedef struct psc_b200_ctx psc_b200_ctx;
+
+/* Grid_t as far as the hot path reads it (src/include/grid.hxx:68-101,141-160;
+ * grid/domain.hxx:25-47; grid.hxx:265-293 Normalization).  All reals are double
+ * here and narrowed inside exactly where PSC narrows them. */
+typedef struct
+{
+  int gdims[3];     /* global cells; gdims[d] == 1 marks an invariant direction */
+  int np[3];        /* patches per direction */
+  double length[3]; /* domain size */
+  double corner[3]; /* lower corner */
+  double dt;
+  double fnqs; /* grid.norm.fnqs */
+  double eta;  /* grid.norm.eta  */
+  int n_kinds;
+  double q[PSC_B200_MAX_KINDS];
+  double m[PSC_B200_MAX_KINDS];
+  int bc_fld_lo[3], bc_fld_hi[3];
+  int bc_prt_lo[3], bc_prt_hi[3];
+  int deposit; /* PSC_B200_DEPOSIT_* */
+  /* decomposition: global patch range owned by each rank; n_patches_by_rank may be
+   * NULL = uniform split like mrc_domain_multi.c:181-189 */
+  int rank, n_ranks;
+  const int* n_patches_by_rank;
+  int device;           /* CUDA device ordinal, -1 = current device */
+  uint64_t max_n_prts;  /* particle capacity of this rank, 0 = grow on demand */
+} psc_b200_grid_desc;
+
+const char* psc_b200_last_error(void);
+const char* psc_b200_version(void);
+
+/* Grid_t ctor + Mparticles(grid) + MfieldsState(grid)  (psc_bubble_yz.cxx:117-147,290-291) */
+int psc_b200_create(const psc_b200_grid_desc* desc, psc_b200_ctx** ctx);
+void psc_b200_destroy(psc_b200_ctx* ctx);
+int psc_b200_sync(psc_b200_ctx* ctx);
+
+int psc_b200_n_patches(const psc_b200_ctx* ctx);   /* local */
+int psc_b200_patch_begin(const psc_b200_ctx* ctx); /* global index of local patch 0 */
+int psc_b200_get_ldims(const psc_b200_ctx* ctx, int ldims[3], int ibn[3]);
+
+/* ---- Mparticles (src/include/particles_simple.hxx:123-247, injector_simple.hxx) ---- */
+/* replace all particles: n_by_patch[n_patches], records patch after patch */
+int psc_b200_mprts_set(psc_b200_ctx* ctx, const void* prts_aos32,
+                       const uint32_t* n_by_patch);
+/* append per patch (InjectorSimple::Patch::operator(), injector_simple.hxx:24-43,
+ * already converted to patch-relative float records) */
+int psc_b200_mprts_inject(psc_b200_ctx* ctx, const void* prts_aos32,
+                          const uint32_t* n_by_patch);
+int psc_b200_mprts_size(psc_b200_ctx* ctx, uint64_t* n_total);
+int psc_b200_mprts_size_by_patch(psc_b200_ctx* ctx, uint32_t* n_by_patch);
+/* MparticlesBase::get_as<MparticlesSingle> (src/include/particles.hxx:35-54) */
+int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts_aos32, uint32_t* off);
+/* synthetic loader on the device (uniform-in-cell thermal plasma):
+ * ppc particles per cell for each kind, u ~ N(0, vth[kind]), w = 1, sorted by cell */
+int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth,
+                                 uint64_t seed);
+
+/* ---- MfieldsState / Mfields (src/include/fields3d.hxx:321-464) ---- */
+/* field 0 is the 9-component state; further scratch fields via _create */
+int psc_b200_mflds_create(psc_b200_ctx* ctx, int n_comps, int* field_id);
+int psc_b200_mflds_upload(psc_b200_ctx* ctx, int field_id, int mb, int me,
+                          const float* host);
+int psc_b200_mflds_download(psc_b200_ctx* ctx, int field_id, int mb, int me,
+                            float* host);
+int psc_b200_mflds_zero(psc_b200_ctx* ctx, int field_id, int mb, int me);
+/* uniform value everywhere incl. ghosts (setupFields with a constant lambda) */
+int psc_b200_mflds_fill(psc_b200_ctx* ctx, int field_id, int m, float value);
+
+/* ---- PushParticles::push_mprts (push_particles_1vb.hxx:27-84) ---- */
+int psc_b200_push_mprts(psc_b200_ctx* ctx);
+/* ---- Sort::operator() = SortCountsort2 (psc_sort_impl.hxx:65-124) ---- */
+int psc_b200_sort(psc_b200_ctx* ctx);
+/* ---- BndParticles::operator() (bnd_particles_impl.hxx:234-247, ddc_particles.hxx:283-478) ---- */
+int psc_b200_bnd_particles(psc_b200_ctx* ctx);
+/* ---- Bnd::add_ghosts / fill_ghosts (psc_bnd_impl.hxx:105-158) ---- */
+int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int field_id, int mb, int me);
+int psc_b200_bnd_fill_ghosts(psc_b200_ctx* ctx, int field_id, int mb, int me);
+/* ---- BndFields (psc_bnd_fields_impl.hxx:27-188) ---- */
+int psc_b200_bndf_fill_ghosts_E(psc_b200_ctx* ctx);
+int psc_b200_bndf_fill_ghosts_H(psc_b200_ctx* ctx);
+int psc_b200_bndf_add_ghosts_J(psc_b200_ctx* ctx);
+/* ---- PushFields::push_E / push_H (psc_push_fields_impl.hxx:134-178) ---- */
+int psc_b200_push_E(psc_b200_ctx* ctx, double dt_fac);
+int psc_b200_push_H(psc_b200_ctx* ctx, double dt_fac);
+/* ---- Marder::correct_gauss (marder_impl.hxx:197-264) ---- */
+int psc_b200_marder(psc_b200_ctx* ctx, double diffusion, int loop);
+/* ---- Moment_rho_1st_nc incl. ghost add (psc/moment.hxx:149-171) into comp 0 of field_id ---- */
+int psc_b200_moment_rho_1st_nc(psc_b200_ctx* ctx, int field_id);
+/* ---- Checks (checks_impl.hxx:33-215) ---- */
+int psc_b200_check_continuity_begin(psc_b200_ctx* ctx);
+int psc_b200_check_continuity_end(psc_b200_ctx* ctx, double* max_err);
+int psc_b200_check_gauss(psc_b200_ctx* ctx, double* max_err);
+/* ---- DiagEnergies (DiagEnergiesField.h:19-42, DiagEnergiesParticle.h:15-40):
+ * out[0..5] = EX2 EY2 EZ2 HX2 HY2 HZ2 ; out[6] = E_electron (q<0), out[7] = E_ion ---- */
+int psc_b200_energies(psc_b200_ctx* ctx, double out[8]);
+
+/* ---- Psc::step (src/include/psc.hxx:321-486): the whole sequence on the stream ---- */
+typedef struct
+{
+  int sort;             /* run Sort this step (PscParams::sort_interval hit) */
+  int marder_loop;      /* > 0: Marder correction with this many relaxation loops */
+  double marder_diffusion;
+  int push_fields;      /* 0 = particle part only (push + exchange + sort) */
+  int checks;           /* continuity + gauss checks (results via _last_checks) */
+} psc_b200_step_params;
+int psc_b200_step(psc_b200_ctx* ctx, const psc_b200_step_params* prm);
+int psc_b200_last_checks(psc_b200_ctx* ctx, double* continuity, double* gauss);
+
+/* ---- multi-GPU: NCCL over NVLink (replaces every MPI site of SURVEY.md 2.3) ---- */
+int psc_b200_nccl_unique_id(void* id128);
+int psc_b200_nccl_init(psc_b200_ctx* ctx, const void* id128);
+/* Balance::operator() (psc_balance_impl.hxx:770-1026): redistribute patches by load */
+int psc_b200_balance(psc_b200_ctx* ctx, double factor_fields, int* changed);
+/* best_mapping (psc_balance_impl.hxx:99-160): pure function, exposed for tests */
+int psc_b200_best_mapping(int n_ranks, const double* capability, int n_patches,
+                          const double* loads, int* n_patches_by_rank);
+
+/* ---- options, measurement ---- */
+/* "keep_sorted" (0/1), "tile" (cells per tile edge), "warp_reduce" (0/1),
+ * "threads" (CTA size of the push kernel), "profile" (0/1) */
+int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value);
+int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value);
+/* CUDA-event timer on the context's stream */
+int psc_b200_timer_start(psc_b200_ctx* ctx);
+int psc_b200_timer_stop(psc_b200_ctx* ctx, float* ms);
+/* per-kernel accumulators (when option "profile" = 1): writes up to max entries,
+ * returns the number of kernels; names are static strings */
+int psc_b200_prof_get(psc_b200_ctx* ctx, int max, const char** names, float* ms,
+                      uint64_t* launches);
+int psc_b200_prof_reset(psc_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

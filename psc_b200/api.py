@@ -1,0 +1,421 @@
+"""Host-side mirror of PSC's PscConfig plugin surface over the psc_b200 C ABI.
+
+Same type names, argument meaning and call order as the reference's types
+(SURVEY.md 8b): Grid ~ Grid_t, Mparticles, MfieldsState, PushParticles, Sort,
+BndParticles, Bnd, BndFields, PushFields, Marder, Checks, and Psc whose step()
+follows Psc::step (src/include/psc.hxx:321-486).  Every method is one C-ABI call
+into the CUDA library; nothing is computed here.  Errors raise PscB200Error
+(the reference aborts: libpsc/bits.hxx:35-40)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import GridDesc, StepParams, PscB200Error, load, check, i3, d3, MAX_KINDS
+
+JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS = range(10)
+BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING = range(4)
+BND_PRT_REFLECTING, BND_PRT_PERIODIC, BND_PRT_ABSORBING, BND_PRT_OPEN = range(4)
+DEPOSIT_DEFAULT, DEPOSIT_VAR1, DEPOSIT_SPLIT = -1, 0, 1
+
+# ParticleSimple<float>, src/include/particle_simple.hxx:10-42
+PRT_DTYPE = np.dtype(
+    [("x", "<f4", (3,)), ("u", "<f4", (3,)), ("kind", "<i4"), ("qni_wni", "<f4")])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Grid:
+    """Grid_t (src/include/grid.hxx:68-101): domain, BCs, kinds, normalisation, dt.
+    Owns the device context of this rank."""
+
+    def __init__(self, gdims, length, np=(1, 1, 1), dt=1.0, kinds=((1.0, 1.0),),
+                 nicell=None, fnqs=None, eta=1.0, corner=(0., 0., 0.),
+                 bc_fld_lo=None, bc_fld_hi=None, bc_prt_lo=None, bc_prt_hi=None,
+                 deposit=DEPOSIT_DEFAULT, rank=0, n_ranks=1, n_patches_by_rank=None,
+                 device=-1, max_n_prts=0):
+        d = GridDesc()
+        d.gdims = i3(*gdims)
+        d.np = i3(*np)
+        d.length = d3(*[float(v) for v in length])
+        d.corner = d3(*[float(v) for v in corner])
+        d.dt = dt
+        if fnqs is None:
+            # Grid_t::Normalization, dimensionless (grid.hxx:205-220,265-293): 1/nicell
+            fnqs = 1.0 / nicell if nicell else 1.0
+        d.fnqs, d.eta = fnqs, eta
+        assert len(kinds) <= MAX_KINDS
+        d.n_kinds = len(kinds)
+        for k, (q, m) in enumerate(kinds):
+            d.q[k], d.m[k] = q, m
+        d.bc_fld_lo = i3(*(bc_fld_lo or [BND_FLD_PERIODIC] * 3))
+        d.bc_fld_hi = i3(*(bc_fld_hi or [BND_FLD_PERIODIC] * 3))
+        d.bc_prt_lo = i3(*(bc_prt_lo or [BND_PRT_PERIODIC] * 3))
+        d.bc_prt_hi = i3(*(bc_prt_hi or [BND_PRT_PERIODIC] * 3))
+        d.deposit = deposit
+        d.rank, d.n_ranks = rank, n_ranks
+        self._npr = None
+        if n_patches_by_rank is not None:
+            self._npr = (C.c_int * n_ranks)(*n_patches_by_rank)
+            d.n_patches_by_rank = self._npr
+        d.device = device
+        d.max_n_prts = max_n_prts
+        self.desc = d
+        self.kinds = [tuple(k) for k in kinds]
+        self.lib = load()
+        self.ctx = C.c_void_p()
+        check(self.lib.psc_b200_create(C.byref(d), C.byref(self.ctx)))
+        ld, ibn = i3(), i3()
+        check(self.lib.psc_b200_get_ldims(self.ctx, ld, ibn))
+        self.ldims, self.ibn = tuple(ld), tuple(ibn)
+        self.im = tuple(l + 2 * b for l, b in zip(self.ldims, self.ibn))
+        self.ib = tuple(-b for b in self.ibn)
+        self.gdims, self.np3 = tuple(gdims), tuple(np)
+        self.dx = tuple(L / g for L, g in zip(length, gdims))
+        self.dt = dt
+        self.timestep = 0
+
+    def n_patches(self):
+        return self.lib.psc_b200_n_patches(self.ctx)
+
+    def patch_begin(self):
+        return self.lib.psc_b200_patch_begin(self.ctx)
+
+    def sync(self):
+        check(self.lib.psc_b200_sync(self.ctx))
+
+    def set_option(self, name, value):
+        check(self.lib.psc_b200_set_option(self.ctx, name.encode(), float(value)))
+
+    def get_stat(self, name):
+        v = C.c_double()
+        check(self.lib.psc_b200_get_stat(self.ctx, name.encode(), C.byref(v)))
+        return v.value
+
+    def timer_start(self):
+        check(self.lib.psc_b200_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.psc_b200_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def profile(self):
+        n = 64
+        names = (C.c_char_p * n)()
+        ms = (C.c_float * n)()
+        cnt = (C.c_uint64 * n)()
+        k = self.lib.psc_b200_prof_get(self.ctx, n, names, ms, cnt)
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
+
+    def profile_reset(self):
+        check(self.lib.psc_b200_prof_reset(self.ctx))
+
+    def nccl_init(self, unique_id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id_bytes)
+        check(self.lib.psc_b200_nccl_init(self.ctx, buf))
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_char * 128)()
+        check(load().psc_b200_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if self.ctx:
+            self.lib.psc_b200_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mparticles:
+    """MparticlesB200 ~ MparticlesSimple (src/include/particles_simple.hxx:123-247)"""
+
+    def __init__(self, grid):
+        self.grid_ = grid
+
+    def grid(self):
+        return self.grid_
+
+    def n_patches(self):
+        return self.grid_.n_patches()
+
+    def size(self):
+        n = C.c_uint64()
+        check(self.grid_.lib.psc_b200_mprts_size(self.grid_.ctx, C.byref(n)))
+        return n.value
+
+    def sizeByPatch(self):
+        n = np.zeros(self.n_patches(), dtype=np.uint32)
+        check(self.grid_.lib.psc_b200_mprts_size_by_patch(self.grid_.ctx, _ptr(n)))
+        return n
+
+    def set(self, prts, n_by_patch):
+        prts = np.ascontiguousarray(prts, dtype=PRT_DTYPE)
+        n = np.ascontiguousarray(n_by_patch, dtype=np.uint32)
+        assert len(n) == self.n_patches() and int(n.sum()) == len(prts)
+        check(self.grid_.lib.psc_b200_mprts_set(self.grid_.ctx, _ptr(prts), _ptr(n)))
+
+    def inject(self, prts, n_by_patch):
+        """injector()[p](...) for every patch at once (injector_simple.hxx:24-43)"""
+        prts = np.ascontiguousarray(prts, dtype=PRT_DTYPE)
+        n = np.ascontiguousarray(n_by_patch, dtype=np.uint32)
+        assert len(n) == self.n_patches() and int(n.sum()) == len(prts)
+        check(self.grid_.lib.psc_b200_mprts_inject(self.grid_.ctx, _ptr(prts), _ptr(n)))
+
+    def get(self):
+        """get_as<MparticlesSingle>() (src/include/particles.hxx:35-54): (records, off)"""
+        n = self.size()
+        prts = np.zeros(n, dtype=PRT_DTYPE)
+        off = np.zeros(self.n_patches() + 1, dtype=np.uint32)
+        check(self.grid_.lib.psc_b200_mprts_get(self.grid_.ctx, _ptr(prts), _ptr(off)))
+        return prts, off
+
+    def setup_thermal(self, ppc, vth, seed=0):
+        v = np.ascontiguousarray(vth, dtype=np.float64)
+        assert len(v) == len(self.grid_.kinds)
+        check(self.grid_.lib.psc_b200_mprts_setup_thermal(self.grid_.ctx, ppc, _ptr(v), seed))
+
+
+class Mfields:
+    """MfieldsB200 (scratch field container with n_comps components)"""
+
+    def __init__(self, grid, n_comps, field_id=None):
+        self.grid_ = grid
+        self.n_comps_ = n_comps
+        if field_id is None:
+            fid = C.c_int()
+            check(grid.lib.psc_b200_mflds_create(grid.ctx, n_comps, C.byref(fid)))
+            field_id = fid.value
+        self.id = field_id
+
+    def grid(self):
+        return self.grid_
+
+    def n_comps(self):
+        return self.n_comps_
+
+    def n_patches(self):
+        return self.grid_.n_patches()
+
+    def shape(self, n_comps=None):
+        im = self.grid_.im
+        return (self.n_patches(), n_comps or self.n_comps_, im[2], im[1], im[0])
+
+    def upload(self, host, mb=0, me=None):
+        me = self.n_comps_ if me is None else me
+        host = np.ascontiguousarray(host, dtype=np.float32)
+        assert host.shape == self.shape(me - mb), (host.shape, self.shape(me - mb))
+        check(self.grid_.lib.psc_b200_mflds_upload(self.grid_.ctx, self.id, mb, me, _ptr(host)))
+
+    def download(self, mb=0, me=None):
+        me = self.n_comps_ if me is None else me
+        host = np.zeros(self.shape(me - mb), dtype=np.float32)
+        check(self.grid_.lib.psc_b200_mflds_download(self.grid_.ctx, self.id, mb, me, _ptr(host)))
+        return host
+
+    def zero(self, mb=0, me=None):
+        me = self.n_comps_ if me is None else me
+        check(self.grid_.lib.psc_b200_mflds_zero(self.grid_.ctx, self.id, mb, me))
+
+    def fill(self, m, value):
+        check(self.grid_.lib.psc_b200_mflds_fill(self.grid_.ctx, self.id, m, value))
+
+
+class MfieldsState(Mfields):
+    """MfieldsStateB200: 9 components JXI..HZ, ghosts grid.ibn (fields3d.hxx:415-464)"""
+
+    def __init__(self, grid):
+        super().__init__(grid, NR_FIELDS, field_id=0)
+
+
+class PushParticles:
+    """PushParticlesB200<Dim>: push_particles_1vb.hxx:27-84"""
+
+    def push_mprts(self, mprts, mflds):
+        g = mprts.grid()
+        check(g.lib.psc_b200_push_mprts(g.ctx))
+
+
+class Sort:
+    """SortB200: SortCountsort2 semantics (psc_sort_impl.hxx:65-124)"""
+
+    def __call__(self, mprts):
+        g = mprts.grid()
+        check(g.lib.psc_b200_sort(g.ctx))
+
+
+class BndParticles:
+    """BndParticlesB200 (bnd_particles_impl.hxx:234-247)"""
+
+    def __init__(self, grid):
+        self.grid_ = grid
+
+    def __call__(self, mprts):
+        g = mprts.grid()
+        check(g.lib.psc_b200_bnd_particles(g.ctx))
+
+
+class Bnd:
+    """BndB200 (psc_bnd_impl.hxx:105-158)"""
+
+    def add_ghosts(self, mflds, mb, me):
+        g = mflds.grid()
+        check(g.lib.psc_b200_bnd_add_ghosts(g.ctx, mflds.id, mb, me))
+
+    def fill_ghosts(self, mflds, mb, me):
+        g = mflds.grid()
+        check(g.lib.psc_b200_bnd_fill_ghosts(g.ctx, mflds.id, mb, me))
+
+
+class BndFields:
+    """BndFieldsB200<Dim> (psc_bnd_fields_impl.hxx:27-188)"""
+
+    def fill_ghosts_E(self, mflds):
+        g = mflds.grid()
+        check(g.lib.psc_b200_bndf_fill_ghosts_E(g.ctx))
+
+    def fill_ghosts_H(self, mflds):
+        g = mflds.grid()
+        check(g.lib.psc_b200_bndf_fill_ghosts_H(g.ctx))
+
+    def add_ghosts_J(self, mflds):
+        g = mflds.grid()
+        check(g.lib.psc_b200_bndf_add_ghosts_J(g.ctx))
+
+
+class PushFields:
+    """PushFieldsB200 (psc_push_fields_impl.hxx:134-178)"""
+
+    def push_E(self, mflds, dt_fac, dim=None):
+        g = mflds.grid()
+        check(g.lib.psc_b200_push_E(g.ctx, dt_fac))
+
+    def push_H(self, mflds, dt_fac, dim=None):
+        g = mflds.grid()
+        check(g.lib.psc_b200_push_H(g.ctx, dt_fac))
+
+
+class Marder:
+    """MarderB200 (marder_impl.hxx:150-264): Marder(grid, diffusion, loop, dump)"""
+
+    def __init__(self, grid, diffusion, loop, dump=False):
+        self.diffusion, self.loop = diffusion, loop
+
+    def correct_gauss(self, mflds, mprts):
+        g = mflds.grid()
+        check(g.lib.psc_b200_marder(g.ctx, self.diffusion, self.loop))
+
+    __call__ = correct_gauss
+
+
+class _Continuity:
+    def __init__(self, grid, interval):
+        self.grid_, self.check_interval, self.last_max_err = grid, interval, 0.0
+
+    def should_do_check(self, timestep):
+        return self.check_interval > 0 and timestep % self.check_interval == 0
+
+    def before_particle_push(self, mprts):
+        if self.should_do_check(self.grid_.timestep):
+            check(self.grid_.lib.psc_b200_check_continuity_begin(self.grid_.ctx))
+
+    def after_particle_push(self, mprts, mflds):
+        if self.should_do_check(self.grid_.timestep):
+            e = C.c_double()
+            check(self.grid_.lib.psc_b200_check_continuity_end(self.grid_.ctx, C.byref(e)))
+            self.last_max_err = e.value
+
+
+class _Gauss:
+    def __init__(self, grid, interval):
+        self.grid_, self.check_interval, self.last_max_err = grid, interval, 0.0
+
+    def should_do_check(self, timestep):
+        return self.check_interval > 0 and timestep % self.check_interval == 0
+
+    def __call__(self, mprts, mflds):
+        if self.should_do_check(self.grid_.timestep):
+            e = C.c_double()
+            check(self.grid_.lib.psc_b200_check_gauss(self.grid_.ctx, C.byref(e)))
+            self.last_max_err = e.value
+
+
+class Checks:
+    """ChecksB200 (checks_impl.hxx:33-215; ChecksParams: checks_params.hxx)"""
+
+    def __init__(self, grid, continuity_interval=0, gauss_interval=0):
+        self.continuity = _Continuity(grid, continuity_interval)
+        self.gauss = _Gauss(grid, gauss_interval)
+
+
+def energies(grid):
+    """DiagEnergies: [EX2 EY2 EZ2 HX2 HY2 HZ2 E_electron E_ion]"""
+    out = np.zeros(8, dtype=np.float64)
+    check(grid.lib.psc_b200_energies(grid.ctx, _ptr(out)))
+    return out
+
+
+class Psc:
+    """Psc<PscConfig1vbecB200>: step() sequences the operators exactly as
+    Psc::step does (src/include/psc.hxx:321-486); PscParams cadence fields:
+    sort_interval, marder_interval (psc.hxx:66-83).  `fused=True` issues the same
+    sequence through the single C-ABI call psc_b200_step (host C++ driver)."""
+
+    def __init__(self, grid, mflds, mprts, sort_interval=1, marder_interval=0,
+                 marder_diffusion=0.9, marder_loop=3, checks=None, fused=False):
+        self.grid_, self.mflds_, self.mprts_ = grid, mflds, mprts
+        self.sort_interval, self.marder_interval = sort_interval, marder_interval
+        self.marder = Marder(grid, marder_diffusion, marder_loop)
+        self.checks = checks or Checks(grid)
+        self.fused = fused
+        self.sort_, self.pushp_, self.pushf_ = Sort(), PushParticles(), PushFields()
+        self.bnd_, self.bndf, self.bndp_ = Bnd(), BndFields(), BndParticles(grid)
+
+    def initialize(self):
+        """psc.hxx:220-238 pre_first_step: fill H, J, E ghosts"""
+        self.bndf.fill_ghosts_H(self.mflds_)
+        self.bnd_.fill_ghosts(self.mflds_, HX, HX + 3)
+        self.bnd_.fill_ghosts(self.mflds_, JXI, JXI + 3)
+        self.bndf.fill_ghosts_E(self.mflds_)
+        self.bnd_.fill_ghosts(self.mflds_, EX, EX + 3)
+
+    def step(self):
+        g, mflds, mprts = self.grid_, self.mflds_, self.mprts_
+        g.timestep += 1
+        t = g.timestep
+        do_sort = self.sort_interval > 0 and t % self.sort_interval == 0
+        do_marder = self.marder_interval > 0 and t % self.marder_interval == 0
+        if self.fused:
+            prm = StepParams(sort=int(do_sort), marder_loop=self.marder.loop if do_marder else 0,
+                             marder_diffusion=self.marder.diffusion, push_fields=1,
+                             checks=int(self.checks.continuity.should_do_check(t)))
+            check(g.lib.psc_b200_step(g.ctx, C.byref(prm)))
+            return
+        if do_sort:
+            self.sort_(mprts)                                    # psc.hxx:356-361
+        self.checks.continuity.before_particle_push(mprts)       # :379-384
+        self.pushp_.push_mprts(mprts, mflds)                     # :389
+        self.bndp_(mprts)                                        # :412
+        self.bndf.add_ghosts_J(mflds)                            # :417
+        self.bnd_.add_ghosts(mflds, JXI, JXI + 3)                # :418
+        self.bnd_.fill_ghosts(mflds, JXI, JXI + 3)               # :419
+        self.pushf_.push_H(mflds, .5)                            # :426
+        self.bndf.fill_ghosts_H(mflds)                           # :428
+        self.bnd_.fill_ghosts(mflds, HX, HX + 3)                 # :432
+        self.pushf_.push_E(mflds, 1.)                            # :439
+        self.bndf.fill_ghosts_E(mflds)                           # :441
+        self.bnd_.fill_ghosts(mflds, EX, EX + 3)                 # :445
+        if do_marder:
+            self.marder(mflds, mprts)                            # :448-455
+        self.pushf_.push_H(mflds, .5)                            # :461
+        self.bndf.fill_ghosts_H(mflds)                           # :463
+        self.bnd_.fill_ghosts(mflds, HX, HX + 3)                 # :467
+        self.checks.continuity.after_particle_push(mprts, mflds)  # :471-476
+        self.checks.gauss(mprts, mflds)                          # :479-483

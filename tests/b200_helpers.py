@@ -1,0 +1,64 @@
+"""helpers shared by the tests that exercise the product (host logic on CPU, CUDA
+path on the GPU box)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def desc_from_grid(grid, rank=0, n_ranks=1, n_patches_by_rank=None, max_n_prts=0):
+    """psc_b200_grid_desc for the same grid the oracle uses"""
+    from psc_b200._lib import GridDesc, i3, d3
+    g = grid.g
+    d = GridDesc()
+    d.gdims = i3(*g.gdims)
+    d.np = i3(*g.np)
+    d.length = d3(*g.length)
+    d.corner = d3(*g.corner)
+    d.dt, d.fnqs, d.eta = g.dt, g.fnqs, g.eta
+    d.n_kinds = g.n_kinds
+    for k in range(g.n_kinds):
+        d.q[k] = g.q[k]
+        d.m[k] = g.m[k]
+    d.bc_fld_lo = i3(*g.bc_fld_lo)
+    d.bc_fld_hi = i3(*g.bc_fld_hi)
+    d.bc_prt_lo = i3(*g.bc_prt_lo)
+    d.bc_prt_hi = i3(*g.bc_prt_hi)
+    d.deposit = g.deposit
+    d.rank, d.n_ranks = rank, n_ranks
+    if n_patches_by_rank is not None:
+        arr = (C.c_int * n_ranks)(*n_patches_by_rank)
+        d.n_patches_by_rank = arr
+        d._keep = arr
+    d.device = -1
+    d.max_n_prts = max_n_prts
+    return d
+
+
+_hc = None
+
+
+def hostcheck():
+    """host build of the product's per-particle math (tests/hostcheck/), CPU only"""
+    global _hc
+    if _hc is None:
+        src = os.path.join(ROOT, "tests", "hostcheck", "pic_math_host.cpp")
+        so = os.path.join(ROOT, "tests", "hostcheck", "libpic_math_host.so")
+        deps = [src, os.path.join(ROOT, "psc_b200", "csrc", "pic_math.cuh"),
+                os.path.join(ROOT, "psc_b200", "csrc", "grid.hpp"),
+                os.path.join(ROOT, "include", "psc_b200.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(map(os.path.getmtime, deps)):
+            subprocess.check_call(["g++", "-std=c++17", "-O3", "-ffp-contract=off", "-fPIC",
+                                   "-shared", src, "-o", so])
+        L = C.CDLL(so)
+        P = C.c_void_p
+        L.hc_push_mprts.argtypes = [P, P, P, P]
+        L.hc_bnd_classify.argtypes = [P, P, P, P, P]
+        L.hc_grid_info.argtypes = [P, P, P, P, P]
+        _hc = L
+    return _hc
