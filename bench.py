@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the PIC hot path (push + deposit + boundary exchange +
+sort, plus the field half of Psc::step) on synthetic 3D thermal plasma (SURVEY.md 8d,
+BASELINE.json configs[4]): per GPU 256^3 cells x 64 particles per cell in 8x8x8 patches of
+32^3, periodic, uniform B_z; ranks stack their slabs along z (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo (CUDA, C ABI)
+  python bench.py --impl reference ...                           # CPU arm: the reference's
+        1vb path on the box's host cores (oracle/_ref not needed: the plain-C port of
+        oracle/ is what runs; see DESIGN.md "CPU baseline")
+
+One JSON line on rank 0.  `value` times K steps with the state resident in HBM (CUDA
+events on the context's stream, max over ranks); `e2e` is the same step through the
+operator-level C ABI with HOST buffers in the loop every step (E/B uploaded from pinned
+host memory, deposited J and energies read back); `roofline` is the dominant kernel
+against the measured HBM copy bandwidth; `cpu_baseline` is the oracle port on host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_PUSH = 64.0    # algorithmic bytes per particle of push+deposit: read 32 B, write 32 B
+B_SORT = 72.0    # key write+read 8 B, particle read+write 64 B
+B_STEP = B_PUSH + B_SORT
+KINDS = ((-1., 1.), (1., 100.))
+VTH = (0.05, 0.005)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_GBs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        for v in d.values():
+            if isinstance(v, dict) and "hbm_gbs" in v:
+                return float(v["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_ev, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_ev.set()
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4)
+                          if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------- CPU arm
+
+def cpu_arm(cells, ppc, n_patches_target, steps, warmup, threads):
+    """the reference's CPU 1vb path (oracle port: push_particles_1vb.hxx + psc_sort_impl.hxx
+    + bnd_particles_impl.hxx restated in oracle/psc_oracle.c), patches spread over host
+    threads the way PSC spreads them over MPI ranks"""
+    import oracle_lib as ol
+    from gen import thermal_plasma
+    from concurrent.futures import ThreadPoolExecutor
+    pz = max(1, n_patches_target // 4)
+    og = ol.Grid(gdims=(cells * 2, cells * 2, cells * pz), length=(2. * cells, 2. * cells, 1. * cells * pz),
+                 np_=(2, 2, pz), dt=0.75 / np.sqrt(3.), kinds=KINDS, nicell=ppc // 2)
+    flds = og.zeros_fields()
+    flds[:, ol.HZ] = 0.1
+    prts, off = thermal_plasma(og, ppc=ppc // 2, seed=1234, vth=VTH, shuffle=False)
+    n = len(prts)
+    L, G = ol.lib(), og.byref()
+    npch = og.n_patches
+    threads = max(1, min(threads, npch))
+    bounds = [(t * npch // threads, (t + 1) * npch // threads) for t in range(threads)]
+    pool = ThreadPoolExecutor(threads)
+
+    def one_step(prts, off):
+        def work(b):
+            L.po_sort_range(G, ol.ptr(prts), ol.ptr(off), None, b[0], b[1])
+            L.po_push_mprts_range(G, ol.ptr(flds), ol.ptr(prts), ol.ptr(off), b[0], b[1])
+        list(pool.map(work, bounds))
+        p2, o2, _ = ol.bnd_particles(og, prts, off)
+        return p2, o2
+
+    for _ in range(warmup):
+        prts, off = one_step(prts, off)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        prts, off = one_step(prts, off)
+    dt = time.perf_counter() - t0
+    pool.shutdown()
+    sample = ("%d patches of %d^3 cells x %d ppc = %d particles, %d steps of sort+push+deposit+"
+              "boundary exchange, %d host threads over patches" % (npch, cells, ppc, n, steps, threads))
+    return n * steps / dt, dt / steps * 1e3, sample, threads
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cells, ppc = 32, 64
+    # ~4 patches per thread keeps a step around a few seconds
+    val, ms, sample, used = cpu_arm(cells, ppc, max(4, 2 * cores), args.steps, min(args.warmup, 1), cores)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec (push+deposit+sort)", "value": val,
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "S3D-thermal (SURVEY.md 8d), bounded sample: " + sample},
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": used, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU arm
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import psc_b200 as pb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, ppc, pe = args.cells, args.ppc, args.patch
+    npd = n // pe
+    gdims = (n, n, n * world)
+    grid = pb.Grid(gdims=gdims, length=tuple(float(g) for g in gdims), np=(npd, npd, npd * world),
+                   dt=0.75 / np.sqrt(3.), kinds=KINDS, nicell=ppc // 2, rank=rank, n_ranks=world,
+                   device=local_rank, max_n_prts=int(n ** 3 * ppc * 1.02))
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pb.Grid.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
+    for k, v in (("fma", args.fma), ("tiled", args.tiled), ("tma", args.tma),
+                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort)):
+        grid.set_option(k, v)
+    if args.tile:
+        grid.set_option("tile", args.tile)
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    mprts.setup_thermal(ppc // 2, list(VTH), seed=1234)
+    mflds.fill(pb.HZ, 0.1)
+    n_prts = mprts.size()
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=True)
+    psc.initialize()
+
+    def barrier():
+        grid.sync()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        psc.step()
+    grid.set_option("profile", 1)
+    grid.profile_reset()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = grid.get_stat("n_launches")
+    grid.timer_start()
+    for _ in range(args.steps):
+        psc.step()
+    ms = grid.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(grid.get_stat("n_launches") - l0)
+    prof = grid.profile()
+    grid.set_option("profile", 0)
+    n_after = mprts.size()
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cnt = torch.tensor([float(n_prts), float(n_after)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt)
+        n_total, n_after_total = int(cnt[0].item()), int(cnt[1].item())
+    else:
+        n_total, n_after_total = n_prts, n_after
+    assert n_after_total == n_total, "periodic run lost particles: %d -> %d" % (n_total, n_after_total)
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: operator-level C ABI with host buffers in the loop
+    e2e = None
+    if not args.no_e2e:
+        shape_eb, shape_j = mflds.shape(6), mflds.shape(3)
+        h_eb = torch.empty(shape_eb, dtype=torch.float32, pin_memory=True).numpy()
+        h_eb[:] = mflds.download(pb.EX, pb.EX + 6)
+        h_j = torch.empty(shape_j, dtype=torch.float32, pin_memory=True).numpy()
+        lib, ctx = grid.lib, grid.ctx
+        k_e2e = max(1, min(args.steps, args.e2e_steps))
+        sort_, pushp, bndp, bnd, bndf = pb.Sort(), pb.PushParticles(), pb.BndParticles(grid), pb.Bnd(), pb.BndFields()
+        out_en = np.zeros(8)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            pb.check(lib.psc_b200_mflds_upload(ctx, 0, pb.EX, pb.EX + 6, h_eb.ctypes.data_as(C.c_void_p)))
+            prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=1, checks=0)
+            pb.check(lib.psc_b200_step(ctx, C.byref(prm)))
+            pb.check(lib.psc_b200_mflds_download(ctx, 0, pb.JXI, pb.JXI + 3, h_j.ctypes.data_as(C.c_void_p)))
+            pb.check(lib.psc_b200_energies(ctx, out_en.ctypes.data_as(C.c_void_p)))
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+        if dist:
+            t = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_e2e = float(t.item())
+        e2e = {"value": n_total * k_e2e / dt_e2e, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": int(h_eb.nbytes) * world, "d2h_bytes_per_step": (int(h_j.nbytes) + 64) * world,
+               "steps": k_e2e,
+               "what": "per step: upload E,B (6 comps, all patches) from pinned host memory, "
+                       "psc_b200_step, download J (3 comps) + energies"}
+
+    if rank != 0:
+        grid.close()
+        return
+    peak, peak_src = measured_peak()
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+               for k, v in prof.items()}
+    push_key = next((k for k in ("push_tiled_tma", "push_tiled", "push_general") if k in prof), None)
+    roofline = None
+    if push_key:
+        t_push = prof[push_key][0] / max(1, prof[push_key][1]) * 1e-3
+        ach = B_PUSH * n_prts / t_push / 1e9
+        roofline = {"bound": "hbm", "kernel": push_key, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_particle": B_PUSH,
+                    "step_frac": (value / world) * B_STEP / 1e9 / peak,
+                    "step_algorithmic_bytes_per_particle": B_STEP}
+    cpu = None
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, _, sample, used = cpu_arm(32, 64, max(4, 2 * cores), 2, 1, cores)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": used, "kind": "port", "sample": sample}
+    line = {
+        "metric": "particle-steps/sec (push+deposit+sort)", "value": value, "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "S3D-thermal: %d^3 cells x %d ppc per GPU, %d^3-cell patches, periodic, "
+                               "full Psc::step (sort+push+deposit+exchange+J ghosts+Yee E/H), sort every step"
+                               % (n, ppc, pe),
+                   "particles_per_gpu": n_prts, "cells_per_gpu": n ** 3, "parallelism": "slabs along z, %d rank(s)" % world,
+                   "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
+                   "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma, "warp_reduce": args.warp_reduce,
+                                                "fused_sort": args.fused_sort}},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu, "kernels": kernels,
+    }
+    print(json.dumps(line), flush=True)
+    grid.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=256, help="cells per GPU edge")
+    ap.add_argument("--patch", type=int, default=32, help="cells per patch edge")
+    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--fma", type=int, default=0)
+    ap.add_argument("--tiled", type=int, default=1)
+    ap.add_argument("--tma", type=int, default=1)
+    ap.add_argument("--warp-reduce", dest="warp_reduce", type=int, default=1)
+    ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,647 @@
+// psc_b200: the C ABI (include/psc_b200.h) -- context life cycle, per-patch tables,
+// options/timers, the Psc::step sequence and the entry points that forward to the
+// operator implementations.  No exception crosses this boundary and there is no CPU
+// fallback: without a CUDA device psc_b200_create fails.
+#include "dev_util.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <exception>
+
+namespace psc_b200
+{
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg)
+{
+  g_last_error = msg;
+}
+
+int fail(const std::string& msg)
+{
+  g_last_error = msg;
+  return 1;
+}
+
+int check_launch(Ctx* c, const char* what)
+{
+  (void)c;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int DevBuf::reserve(size_t n)
+{
+  if (n <= bytes) {
+    return 0;
+  }
+  if (p) {
+    cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  size_t want = (n + n / 8 + 255) & ~size_t(255);
+  PSC_CUDA_TRY(cudaMalloc(&p, want));
+  bytes = want;
+  return 0;
+}
+
+void DevBuf::release()
+{
+  if (p) {
+    cudaFree(p);
+  }
+  p = nullptr;
+  bytes = 0;
+}
+
+KernelScope::KernelScope(Ctx* ctx, const char* name, int) : c(ctx)
+{
+  if (!c->opt_profile) {
+    return;
+  }
+  for (size_t i = 0; i < c->prof.size(); i++) {
+    if (c->prof[i].name == name || !strcmp(c->prof[i].name, name)) {
+      idx = (int)i;
+    }
+  }
+  if (idx < 0) {
+    ProfEntry e;
+    e.name = name;
+    c->prof.push_back(e);
+    idx = (int)c->prof.size() - 1;
+  }
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, c->stream);
+}
+
+KernelScope::~KernelScope()
+{
+  if (idx < 0) {
+    return;
+  }
+  cudaEventRecord(b, c->stream);
+  c->prof_pending.push_back({idx, {a, b}});
+}
+
+static void prof_collect(Ctx* c)
+{
+  if (c->prof_pending.empty()) {
+    return;
+  }
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->prof_pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+    c->prof[e.first].ms += ms;
+    c->prof[e.first].launches++;
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  c->prof_pending.clear();
+}
+
+// neighbour / boundary tables of this rank's patches
+int build_patch_tables(Ctx* c)
+{
+  const GridHost& g = c->g;
+  int np = g.n_patches;
+  std::vector<pm::PatchBnd> pb(np);
+  c->h_nei_patch.assign((size_t)np * 27, -1);
+  c->h_nei_slot.assign((size_t)np * 27, -1);
+  std::vector<int8_t> add_order((size_t)np * 26, -1);
+  // proxies: remote neighbour patches in ascending global index
+  std::vector<int> remote;
+  for (int p = 0; p < np; p++) {
+    int gp = g.patch_begin + p;
+    for (int di = 0; di < 27; di++) {
+      if (di == 13) {
+        continue;
+      }
+      int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+      int ngp = g.neighbor_patch(gp, dir);
+      if (ngp >= 0 && g.rank_of_patch(ngp) != g.rank) {
+        remote.push_back(ngp);
+      }
+    }
+  }
+  std::sort(remote.begin(), remote.end());
+  remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+  c->n_slots = np + (int)remote.size();
+  c->proxy_gp = remote;
+  for (int p = 0; p < np; p++) {
+    int gp = g.patch_begin + p;
+    pb[p] = make_patch_bnd(g, gp);
+    std::vector<std::pair<std::pair<int, int>, int>> order; // ((sender gp, sender dir idx), di)
+    for (int di = 0; di < 27; di++) {
+      if (di == 13) {
+        continue;
+      }
+      int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+      int ngp = g.neighbor_patch(gp, dir);
+      if (ngp < 0) {
+        continue;
+      }
+      int r = g.rank_of_patch(ngp);
+      if (r == g.rank) {
+        c->h_nei_patch[p * 27 + di] = ngp - g.patch_begin;
+        c->h_nei_slot[p * 27 + di] = ngp - g.patch_begin;
+      } else {
+        c->h_nei_patch[p * 27 + di] = -2 - r;
+        c->h_nei_slot[p * 27 + di] =
+          np + (int)(std::lower_bound(remote.begin(), remote.end(), ngp) - remote.begin());
+      }
+      order.push_back({{ngp, 26 - di}, di});
+    }
+    // the reference adds contributions in the order its sequential loop produces them:
+    // sender patch ascending, then the sender's direction index ascending
+    // (mrc_ddc_multi.c:519-538)
+    std::sort(order.begin(), order.end());
+    for (size_t o = 0; o < order.size(); o++) {
+      add_order[(size_t)p * 26 + o] = (int8_t)order[o].second;
+    }
+  }
+  PSC_CUDA_TRY(cudaMalloc(&c->d_patch_bnd, np * sizeof(pm::PatchBnd)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_nei_patch, (size_t)np * 27 * sizeof(int)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_nei_slot, (size_t)np * 27 * sizeof(int)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_add_order, (size_t)np * 26));
+  PSC_CUDA_TRY(cudaMemcpy(c->d_patch_bnd, pb.data(), np * sizeof(pm::PatchBnd),
+                          cudaMemcpyHostToDevice));
+  PSC_CUDA_TRY(cudaMemcpy(c->d_nei_patch, c->h_nei_patch.data(), (size_t)np * 27 * sizeof(int),
+                          cudaMemcpyHostToDevice));
+  PSC_CUDA_TRY(cudaMemcpy(c->d_nei_slot, c->h_nei_slot.data(), (size_t)np * 27 * sizeof(int),
+                          cudaMemcpyHostToDevice));
+  PSC_CUDA_TRY(cudaMemcpy(c->d_add_order, add_order.data(), (size_t)np * 26,
+                          cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int ctx_create(const psc_b200_grid_desc* desc, Ctx** out)
+{
+  std::string err;
+  Ctx* c = new Ctx;
+  if (!grid_setup(*desc, c->g, err)) {
+    delete c;
+    return fail(err);
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    delete c;
+    return fail(std::string("psc_b200 needs a CUDA device and there is no CPU fallback: ") +
+                cudaGetErrorString(e));
+  }
+  if (desc->device >= 0) {
+    PSC_CUDA_TRY(cudaSetDevice(desc->device));
+  }
+  PSC_CUDA_TRY(cudaGetDevice(&c->device));
+  PSC_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  PSC_CUDA_TRY(cudaEventCreate(&c->ev_start));
+  PSC_CUDA_TRY(cudaEventCreate(&c->ev_stop));
+
+  const GridHost& g = c->g;
+  GridDev& G = c->gd;
+  for (int d = 0; d < 3; d++) {
+    G.ldims[d] = g.ldims[d];
+    G.im[d] = g.im[d];
+    G.ibn[d] = g.ibn[d];
+  }
+  G.n_patches = g.n_patches;
+  G.n_cells = g.n_cells;
+  G.fld_len = g.fld_len;
+  G.dim = g.dim;
+  G.deposit = g.deposit;
+  G.pc = make_push_const(g);
+
+  c->h_off.assign(g.n_patches + 1, 0);
+  PSC_CUDA_TRY(cudaMalloc(&c->d_off, (g.n_patches + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMemset(c->d_off, 0, (g.n_patches + 1) * sizeof(uint32_t)));
+  size_t nct = (size_t)g.n_cells * g.n_patches;
+  PSC_CUDA_TRY(cudaMalloc(&c->d_cell_off, (nct + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMemset(c->d_cell_off, 0, (nct + 1) * sizeof(uint32_t)));
+  PSC_TRY(build_patch_tables(c));
+  int id;
+  PSC_TRY(flds_create(c, PSC_B200_NR_FIELDS, &id)); // field 0 = MfieldsState
+  if (desc->max_n_prts) {
+    PSC_TRY(prts_reserve(c, desc->max_n_prts));
+  }
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+static void ctx_destroy(Ctx* c)
+{
+  if (!c) {
+    return;
+  }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->xi4[b]);
+    cudaFree(c->pxi4[b]);
+  }
+  cudaFree(c->d_off);
+  cudaFree(c->d_cell_off);
+  cudaFree(c->d_patch_bnd);
+  cudaFree(c->d_nei_patch);
+  cudaFree(c->d_nei_slot);
+  cudaFree(c->d_add_order);
+  for (auto& f : c->flds) {
+    cudaFree(f.d);
+  }
+  for (auto& s : c->scr) {
+    s.release();
+  }
+  c->stage.release();
+  for (auto& e : c->prof_pending) {
+    cudaEventDestroy(e.second.first);
+    cudaEventDestroy(e.second.second);
+  }
+  cudaEventDestroy(c->ev_start);
+  cudaEventDestroy(c->ev_stop);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int push_mprts(Ctx* c)
+{
+  return c->opt_fma ? push_mprts_fast(c) : push_mprts_exact(c);
+}
+
+// Psc::step (src/include/psc.hxx:321-486) without collisions / injection / output
+static int step(Ctx* c, const psc_b200_step_params* prm)
+{
+  if (prm->sort && !c->sorted) {
+    PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
+  }
+  if (prm->checks) {
+    PSC_TRY(check_continuity_begin(c)); // :379-384
+  }
+  PSC_TRY(push_mprts(c)); // :389
+  // :412 bndp_ -- when this step's store was cell-ordered, the exchange is fused with
+  // the sort the next step would start with (same result, one pass over the particles)
+  if (prm->sort && c->opt_fused_sort && c->pushed_from_sorted) {
+    PSC_TRY(fused_bnd_sort(c));
+  } else {
+    PSC_TRY(bnd_particles(c));
+  }
+  PSC_TRY(bndf_add_ghosts_J(c));                       // :417
+  PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
+  PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
+  if (prm->push_fields) {
+    PSC_TRY(push_H(c, .5)); // :426
+    PSC_TRY(bndf_fill_ghosts_H(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+    PSC_TRY(push_E(c, 1.)); // :439
+    PSC_TRY(bndf_fill_ghosts_E(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
+    if (prm->marder_loop > 0) {
+      PSC_TRY(marder(c, prm->marder_diffusion, prm->marder_loop)); // :448-455
+    }
+    PSC_TRY(push_H(c, .5)); // :461
+    PSC_TRY(bndf_fill_ghosts_H(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+  }
+  if (prm->checks) {
+    double e;
+    PSC_TRY(check_continuity_end(c, &e)); // :471-476
+    PSC_TRY(check_gauss(c, &e));          // :479-483
+  }
+  return 0;
+}
+
+} // namespace psc_b200
+
+using namespace psc_b200;
+
+#define CTX(ctx) reinterpret_cast<Ctx*>(ctx)
+#define GUARD(body)                                                                      \
+  try {                                                                                  \
+    if (!ctx) {                                                                          \
+      return fail("null context");                                                       \
+    }                                                                                    \
+    Ctx* c = CTX(ctx);                                                                   \
+    cudaSetDevice(c->device);                                                            \
+    body                                                                                 \
+  } catch (const std::exception& e) {                                                    \
+    return fail(std::string("exception: ") + e.what());                                  \
+  } catch (...) {                                                                        \
+    return fail("unknown exception");                                                    \
+  }
+
+extern "C" {
+
+const char* psc_b200_last_error(void)
+{
+  return g_last_error.c_str();
+}
+
+const char* psc_b200_version(void)
+{
+  return "psc_b200 0.1 (sm_100a)";
+}
+
+int psc_b200_create(const psc_b200_grid_desc* desc, psc_b200_ctx** ctx)
+{
+  try {
+    if (!desc || !ctx) {
+      return fail("null argument");
+    }
+    Ctx* c = nullptr;
+    int rc = ctx_create(desc, &c);
+    *ctx = reinterpret_cast<psc_b200_ctx*>(c);
+    return rc;
+  } catch (const std::exception& e) {
+    return fail(std::string("exception: ") + e.what());
+  }
+}
+
+void psc_b200_destroy(psc_b200_ctx* ctx)
+{
+  ctx_destroy(CTX(ctx));
+}
+
+int psc_b200_sync(psc_b200_ctx* ctx)
+{
+  GUARD(PSC_CUDA_TRY(cudaStreamSynchronize(c->stream)); return check_launch(c, "sync");)
+}
+
+int psc_b200_n_patches(const psc_b200_ctx* ctx)
+{
+  return ctx ? reinterpret_cast<const Ctx*>(ctx)->g.n_patches : -1;
+}
+
+int psc_b200_patch_begin(const psc_b200_ctx* ctx)
+{
+  return ctx ? reinterpret_cast<const Ctx*>(ctx)->g.patch_begin : -1;
+}
+
+int psc_b200_get_ldims(const psc_b200_ctx* ctx, int ldims[3], int ibn[3])
+{
+  if (!ctx) {
+    return fail("null context");
+  }
+  const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+  for (int d = 0; d < 3; d++) {
+    ldims[d] = c->g.ldims[d];
+    ibn[d] = c->g.ibn[d];
+  }
+  return 0;
+}
+
+int psc_b200_mprts_set(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
+{
+  GUARD(return prts_set(c, prts, n_by_patch);)
+}
+
+int psc_b200_mprts_inject(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
+{
+  GUARD(return prts_inject(c, prts, n_by_patch);)
+}
+
+int psc_b200_mprts_size(psc_b200_ctx* ctx, uint64_t* n_total)
+{
+  GUARD(*n_total = c->n_prts; return 0;)
+}
+
+int psc_b200_mprts_size_by_patch(psc_b200_ctx* ctx, uint32_t* n_by_patch)
+{
+  GUARD(for (int p = 0; p < c->g.n_patches; p++) { n_by_patch[p] = c->h_off[p + 1] - c->h_off[p]; } return 0;)
+}
+
+int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts, uint32_t* off)
+{
+  GUARD(return prts_get(c, prts, off);)
+}
+
+int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth, uint64_t seed)
+{
+  GUARD(return prts_setup_thermal(c, ppc, vth, seed);)
+}
+
+int psc_b200_mflds_create(psc_b200_ctx* ctx, int n_comps, int* field_id)
+{
+  GUARD(return flds_create(c, n_comps, field_id);)
+}
+
+int psc_b200_mflds_upload(psc_b200_ctx* ctx, int id, int mb, int me, const float* host)
+{
+  GUARD(return flds_upload(c, id, mb, me, host);)
+}
+
+int psc_b200_mflds_download(psc_b200_ctx* ctx, int id, int mb, int me, float* host)
+{
+  GUARD(return flds_download(c, id, mb, me, host);)
+}
+
+int psc_b200_mflds_zero(psc_b200_ctx* ctx, int id, int mb, int me)
+{
+  GUARD(return flds_zero(c, id, mb, me);)
+}
+
+int psc_b200_mflds_fill(psc_b200_ctx* ctx, int id, int m, float value)
+{
+  GUARD(return flds_fill(c, id, m, value);)
+}
+
+int psc_b200_push_mprts(psc_b200_ctx* ctx)
+{
+  GUARD(return push_mprts(c);)
+}
+
+int psc_b200_sort(psc_b200_ctx* ctx)
+{
+  GUARD(return sort_mprts(c);)
+}
+
+int psc_b200_bnd_particles(psc_b200_ctx* ctx)
+{
+  GUARD(return bnd_particles(c);)
+}
+
+int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
+{
+  GUARD(return bnd_add_ghosts(c, id, mb, me);)
+}
+
+int psc_b200_bnd_fill_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
+{
+  GUARD(return bnd_fill_ghosts(c, id, mb, me);)
+}
+
+int psc_b200_bndf_fill_ghosts_E(psc_b200_ctx* ctx)
+{
+  GUARD(return bndf_fill_ghosts_E(c);)
+}
+
+int psc_b200_bndf_fill_ghosts_H(psc_b200_ctx* ctx)
+{
+  GUARD(return bndf_fill_ghosts_H(c);)
+}
+
+int psc_b200_bndf_add_ghosts_J(psc_b200_ctx* ctx)
+{
+  GUARD(return bndf_add_ghosts_J(c);)
+}
+
+int psc_b200_push_E(psc_b200_ctx* ctx, double dt_fac)
+{
+  GUARD(return push_E(c, dt_fac);)
+}
+
+int psc_b200_push_H(psc_b200_ctx* ctx, double dt_fac)
+{
+  GUARD(return push_H(c, dt_fac);)
+}
+
+int psc_b200_marder(psc_b200_ctx* ctx, double diffusion, int loop)
+{
+  GUARD(return marder(c, diffusion, loop);)
+}
+
+int psc_b200_moment_rho_1st_nc(psc_b200_ctx* ctx, int field_id)
+{
+  GUARD(return moment_rho_1st_nc(c, field_id);)
+}
+
+int psc_b200_check_continuity_begin(psc_b200_ctx* ctx)
+{
+  GUARD(return check_continuity_begin(c);)
+}
+
+int psc_b200_check_continuity_end(psc_b200_ctx* ctx, double* max_err)
+{
+  GUARD(return check_continuity_end(c, max_err);)
+}
+
+int psc_b200_check_gauss(psc_b200_ctx* ctx, double* max_err)
+{
+  GUARD(return check_gauss(c, max_err);)
+}
+
+int psc_b200_energies(psc_b200_ctx* ctx, double out[8])
+{
+  GUARD(PSC_TRY(field_energies(c, out)); PSC_TRY(prts_energies(c, out + 6));
+        if (c->comm) { PSC_TRY(comm_allreduce_sum(c, out, 8)); } return 0;)
+}
+
+int psc_b200_step(psc_b200_ctx* ctx, const psc_b200_step_params* prm)
+{
+  GUARD(return step(c, prm);)
+}
+
+int psc_b200_last_checks(psc_b200_ctx* ctx, double* continuity, double* gauss)
+{
+  GUARD(*continuity = c->last_continuity; *gauss = c->last_gauss; return 0;)
+}
+
+int psc_b200_nccl_unique_id(void* id128)
+{
+  try {
+    return comm_unique_id(id128);
+  } catch (...) {
+    return fail("exception in nccl_unique_id");
+  }
+}
+
+int psc_b200_nccl_init(psc_b200_ctx* ctx, const void* id128)
+{
+  GUARD(return comm_init(c, id128);)
+}
+
+int psc_b200_balance(psc_b200_ctx* ctx, double factor_fields, int* changed)
+{
+  GUARD(return balance(c, factor_fields, changed);)
+}
+
+int psc_b200_best_mapping(int n_ranks, const double* capability, int n_patches,
+                          const double* loads, int* n_patches_by_rank)
+{
+  try {
+    std::vector<double> cap(capability, capability + n_ranks), ld(loads, loads + n_patches);
+    std::vector<int> r = best_mapping(cap, ld);
+    for (int i = 0; i < n_ranks; i++) {
+      n_patches_by_rank[i] = r[i];
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(std::string("exception: ") + e.what());
+  }
+}
+
+int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
+{
+  GUARD(
+    std::string n(name); int v = (int)value;
+    if (n == "tiled") { c->opt_tiled = v; }
+    else if (n == "warp_reduce") { c->opt_warp_reduce = v; }
+    else if (n == "fma") { c->opt_fma = v; }
+    else if (n == "tma") { c->opt_tma = v; }
+    else if (n == "threads") { c->opt_threads = v; }
+    else if (n == "tile") { c->opt_tile[0] = c->opt_tile[1] = c->opt_tile[2] = v; }
+    else if (n == "tile_x") { c->opt_tile[0] = v; }
+    else if (n == "tile_y") { c->opt_tile[1] = v; }
+    else if (n == "tile_z") { c->opt_tile[2] = v; }
+    else if (n == "profile") { c->opt_profile = v; }
+    else if (n == "fused_sort") { c->opt_fused_sort = v; }
+    else { return fail("unknown option " + n); }
+    return 0;)
+}
+
+int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
+{
+  GUARD(
+    std::string n(name);
+    if (n == "n_launches") { *value = (double)c->n_launches; }
+    else if (n == "n_dropped") { *value = (double)c->n_dropped; }
+    else if (n == "sorted") { *value = c->sorted; }
+    else if (n == "n_prts") { *value = c->n_prts; }
+    else if (n == "capacity") { *value = (double)c->cap; }
+    else if (n == "n_slots") { *value = c->n_slots; }
+    else if (n == "fused_steps") { *value = (double)c->n_fused; }
+    else { return fail("unknown stat " + n); }
+    return 0;)
+}
+
+int psc_b200_timer_start(psc_b200_ctx* ctx)
+{
+  GUARD(PSC_CUDA_TRY(cudaEventRecord(c->ev_start, c->stream)); return 0;)
+}
+
+int psc_b200_timer_stop(psc_b200_ctx* ctx, float* ms)
+{
+  GUARD(PSC_CUDA_TRY(cudaEventRecord(c->ev_stop, c->stream));
+        PSC_CUDA_TRY(cudaEventSynchronize(c->ev_stop));
+        PSC_CUDA_TRY(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop)); return 0;)
+}
+
+int psc_b200_prof_get(psc_b200_ctx* ctx, int max, const char** names, float* ms,
+                      uint64_t* launches)
+{
+  if (!ctx) {
+    return 0;
+  }
+  Ctx* c = CTX(ctx);
+  prof_collect(c);
+  int n = std::min<int>(max, (int)c->prof.size());
+  for (int i = 0; i < n; i++) {
+    names[i] = c->prof[i].name;
+    ms[i] = c->prof[i].ms;
+    launches[i] = c->prof[i].launches;
+  }
+  return n;
+}
+
+int psc_b200_prof_reset(psc_b200_ctx* ctx)
+{
+  GUARD(prof_collect(c); c->prof.clear(); return 0;)
+}
+
+} // extern "C"

@@ -1,0 +1,223 @@
+// psc_b200: the per-rank device context behind the C ABI (include/psc_b200.h).
+//
+// One context = one process = one GPU.  It owns
+//   - the particle store: two float4 streams (xi4 = x,y,z,kind ; pxi4 = ux,uy,uz,q*w),
+//     double-buffered, all patches back to back, patch p = [off[p], off[p+1]);
+//     when `sorted` is set the store is ordered by (patch, cell) and cell_off holds
+//     the per-cell offsets (what the tiled push kernel walks)
+//   - the field arrays in PSC's layout float [slot][m][iz][iy][ix]; slots
+//     0..n_patches-1 are this rank's patches, the following ones are proxies of
+//     patches owned by neighbouring ranks (filled by the NCCL halo exchange)
+//   - scratch memory, the stream, NCCL state and per-kernel timers.
+#pragma once
+
+#include "grid.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace psc_b200
+{
+
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+
+#define PSC_CUDA_TRY(expr)                                                               \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      return ::psc_b200::fail(std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    }                                                                                    \
+  } while (0)
+
+#define PSC_TRY(expr)                                                                    \
+  do {                                                                                   \
+    int rc__ = (expr);                                                                   \
+    if (rc__) {                                                                          \
+      return rc__;                                                                       \
+    }                                                                                    \
+  } while (0)
+
+// grid facts every kernel needs, passed by value
+struct GridDev
+{
+  int ldims[3], im[3], ibn[3];
+  int n_patches; // local
+  int n_cells;   // per patch
+  long fld_len;  // im0*im1*im2
+  int dim;       // pm::DIM_*
+  int deposit;   // pm::DEPOSIT_*
+  pm::PushConst pc;
+};
+
+// grow-only device allocation
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n);
+  void release();
+  template <typename T>
+  T* as()
+  {
+    return static_cast<T*>(p);
+  }
+};
+
+struct FieldArr
+{
+  float* d = nullptr;
+  int n_comps = 0;
+};
+
+struct ProfEntry
+{
+  const char* name;
+  float ms = 0.f;
+  uint64_t launches = 0;
+};
+
+struct Comm; // nccl.cpp
+
+struct Ctx
+{
+  GridHost g;
+  GridDev gd;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+
+  // ---- options (psc_b200_set_option)
+  int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
+  int opt_warp_reduce = 1; // warp-level pre-reduction of deposits in the tiled push
+  int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
+  int opt_tma = 1;         // stage the E/B tile with cp.async.bulk (TMA) instead of LDG/STS
+  int opt_threads = 512;   // CTA size of the tiled push
+  int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
+  int opt_profile = 0;
+  int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
+
+  // ---- particles
+  float4* xi4[2] = {nullptr, nullptr};
+  float4* pxi4[2] = {nullptr, nullptr};
+  int cur = 0;
+  size_t cap = 0;
+  uint32_t n_prts = 0;
+  std::vector<uint32_t> h_off; // n_patches + 1
+  uint32_t* d_off = nullptr;
+  bool sorted = false;           // store ordered by (patch, cell) and cell_off valid
+  bool pushed_from_sorted = false; // store = cell-ordered store after exactly one push;
+                                   // cell_off still describes the pre-push cell runs
+  uint64_t n_fused = 0;          // steps that took the fused boundary+sort pass
+  uint32_t* d_cell_off = nullptr; // n_patches * n_cells + 1
+  uint64_t n_dropped = 0;        // absorbed at open/absorbing walls so far
+
+  // ---- per-patch tables (device)
+  pm::PatchBnd* d_patch_bnd = nullptr; // n_patches
+  int* d_nei_slot = nullptr;   // [n_patches][27] field slot of the neighbour or -1
+  int* d_nei_patch = nullptr;  // [n_patches][27] local patch index, -1 none, -2-r remote rank r
+  int8_t* d_add_order = nullptr; // [n_patches][26] receiver-side dir idx in reference order
+  std::vector<int> h_nei_patch, h_nei_slot;
+  int n_slots = 0; // n_patches + proxies
+  std::vector<int> proxy_gp; // global patch index of each proxy slot (ascending)
+
+  // ---- fields
+  std::vector<FieldArr> flds;
+
+  // ---- scratch
+  DevBuf scr[12];
+  DevBuf stage; // host<->device staging of AoS records
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+
+  // ---- checks
+  int rho_m_id = -1, rho_p_id = -1, div_id = -1;
+  double last_continuity = 0., last_gauss = 0.;
+
+  // ---- timers
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::vector<ProfEntry> prof;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_pending;
+  uint64_t n_launches = 0;
+
+  // ---- multi-GPU
+  Comm* comm = nullptr;
+
+  float4* xi() { return xi4[cur]; }
+  float4* pxi() { return pxi4[cur]; }
+  float4* xi_alt() { return xi4[cur ^ 1]; }
+  float4* pxi_alt() { return pxi4[cur ^ 1]; }
+  float* fld(int id) { return flds[id].d; }
+  long fld_slot_len(int id) const { return gd.fld_len * flds[id].n_comps; }
+};
+
+// RAII-free kernel timing helper: KernelScope ks(ctx, "name"); launch...; (dtor records)
+struct KernelScope
+{
+  Ctx* c;
+  int idx = -1;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KernelScope(Ctx* ctx, const char* name, int n_launches = 1);
+  ~KernelScope();
+};
+
+// ---- particles.cu
+int prts_reserve(Ctx* c, size_t n);
+int prts_set(Ctx* c, const void* aos, const uint32_t* n_by_patch);
+int prts_inject(Ctx* c, const void* aos, const uint32_t* n_by_patch);
+int prts_get(Ctx* c, void* aos, uint32_t* off);
+int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed);
+int prts_upload_off(Ctx* c);
+int prts_energies(Ctx* c, double out2[2]);
+
+// ---- push.cu (two builds of the same source: exact = -fmad=false, fast = FMA)
+int push_mprts_exact(Ctx* c);
+int push_mprts_fast(Ctx* c);
+
+// ---- sort.cu
+int sort_mprts(Ctx* c);
+int sort_pairs(Ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
+               size_t n, int key_bits, bool iota_vals, bool* result_in_alt);
+int fused_bnd_sort(Ctx* c); // boundary exchange + sort of a pushed, previously sorted store
+
+// ---- bndp.cu
+int bnd_particles(Ctx* c);
+
+// ---- fields.cu
+int flds_create(Ctx* c, int n_comps, int* id);
+int flds_zero(Ctx* c, int id, int mb, int me);
+int flds_fill(Ctx* c, int id, int m, float v);
+int flds_upload(Ctx* c, int id, int mb, int me, const float* host);
+int flds_download(Ctx* c, int id, int mb, int me, float* host);
+int bnd_fill_ghosts(Ctx* c, int id, int mb, int me);
+int bnd_add_ghosts(Ctx* c, int id, int mb, int me);
+int bndf_fill_ghosts_E(Ctx* c);
+int bndf_fill_ghosts_H(Ctx* c);
+int bndf_add_ghosts_J(Ctx* c);
+int push_E(Ctx* c, double dt_fac);
+int push_H(Ctx* c, double dt_fac);
+int moment_rho_1st_nc(Ctx* c, int id);
+int marder(Ctx* c, double diffusion, int loop);
+int check_continuity_begin(Ctx* c);
+int check_continuity_end(Ctx* c, double* err);
+int check_gauss(Ctx* c, double* err);
+int field_energies(Ctx* c, double out6[6]);
+
+// ---- comm.cpp (NCCL through dlopen; nothing here runs unless nccl_init was called)
+int comm_unique_id(void* id128);
+int comm_init(Ctx* c, const void* id128);
+void comm_destroy(Ctx* c);
+int comm_halo_exchange(Ctx* c, int id, int mb, int me, bool add);
+int comm_allreduce_max(Ctx* c, double* v, int n);
+int comm_allreduce_sum(Ctx* c, double* v, int n);
+
+// ---- tables
+int build_patch_tables(Ctx* c);
+
+// ---- balance (comm.cu)
+int balance(Ctx* c, double factor_fields, int* changed);
+
+} // namespace psc_b200

@@ -1,0 +1,923 @@
+// psc_b200: field-side operators of the hot path, every one a data-parallel kernel over
+// all patches of the rank at once (PSC launches per patch / per expression):
+//   PushFieldsB200   Yee E/H leapfrog        include/psc_push_fields_impl.hxx:24-178
+//   BndB200          fill_ghosts/add_ghosts  libpsc/psc_bnd/psc_bnd_impl.hxx:105-158 with the
+//                    box patterns of libmrc/src/mrc_ddc_multi.c:60-135 -- written as a
+//                    *gather*: every ghost (fill) or near-boundary interior (add) point
+//                    pulls from its neighbour patches, in the reference's summation order,
+//                    so there are no atomics and the result is deterministic
+//   BndFieldsB200    conducting wall         libpsc/psc_bnd_fields/psc_bnd_fields_impl.hxx:301-530
+//   Moment_rho_1st_nc, div_nc, continuity / Gauss checks, Marder correction, field energies
+//                    include/psc/moment.hxx:149-171, psc/deposit.hxx:24-65,
+//                    psc_output_fields/fields_item_fields.hxx:65-104,
+//                    libpsc/psc_checks/checks_impl.hxx:33-215,
+//                    libpsc/psc_push_fields/marder_impl.hxx:26-61,197-264,
+//                    include/DiagEnergiesField.h:19-42
+// Fields keep PSC's layout float [slot][m][iz][iy][ix] (fields3d.hxx:29-32).
+#include "dev_util.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace psc_b200
+{
+
+namespace
+{
+
+struct Idx3
+{
+  int p, m, i, j, k;
+};
+
+// decode a linear index over [n_patches][n_m][im2][im1][im0] (array coordinates)
+__device__ __forceinline__ Idx3 decode_full(const GridDev& G, size_t idx, int n_m)
+{
+  Idx3 r;
+  r.i = (int)(idx % G.im[0]) - G.ibn[0];
+  idx /= G.im[0];
+  r.j = (int)(idx % G.im[1]) - G.ibn[1];
+  idx /= G.im[1];
+  r.k = (int)(idx % G.im[2]) - G.ibn[2];
+  idx /= G.im[2];
+  r.m = (int)(idx % n_m);
+  r.p = (int)(idx / n_m);
+  return r;
+}
+
+__global__ void k_fill_value(float* F, long slot_len, long fld_len, int n_slots, int m, float v)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)n_slots * fld_len) {
+    size_t s = idx / fld_len, r = idx % fld_len;
+    F[s * slot_len + (size_t)m * fld_len + r] = v;
+  }
+}
+
+// ---------------------------------------------------------------- ghost exchange
+
+__global__ void k_fill_ghosts(GridDev G, float* __restrict__ F, long slot_len, int mb, int me,
+                              const int* __restrict__ nei_slot)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_m = me - mb;
+  if (idx >= (size_t)G.n_patches * n_m * G.fld_len) {
+    return;
+  }
+  Idx3 a = decode_full(G, idx, n_m);
+  int dir[3];
+  dir[0] = a.i < 0 ? -1 : (a.i >= G.ldims[0] ? 1 : 0);
+  dir[1] = a.j < 0 ? -1 : (a.j >= G.ldims[1] ? 1 : 0);
+  dir[2] = a.k < 0 ? -1 : (a.k >= G.ldims[2] ? 1 : 0);
+  if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) {
+    return;
+  }
+  int slot = nei_slot[a.p * 27 + pm::dir2idx(dir)];
+  if (slot < 0) {
+    return;
+  }
+  int m = mb + a.m;
+  F[a.p * slot_len + fld_off(G, m, a.i, a.j, a.k)] =
+    F[slot * slot_len + fld_off(G, m, a.i - dir[0] * G.ldims[0], a.j - dir[1] * G.ldims[1],
+                                a.k - dir[2] * G.ldims[2])];
+}
+
+__global__ void k_add_ghosts(GridDev G, float* __restrict__ F, long slot_len, int mb, int me,
+                             const int* __restrict__ nei_slot,
+                             const int8_t* __restrict__ add_order)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int n_m = me - mb;
+  if (idx >= (size_t)G.n_patches * n_m * G.n_cells) {
+    return;
+  }
+  int i = (int)(idx % G.ldims[0]);
+  idx /= G.ldims[0];
+  int j = (int)(idx % G.ldims[1]);
+  idx /= G.ldims[1];
+  int k = (int)(idx % G.ldims[2]);
+  idx /= G.ldims[2];
+  int m = mb + (int)(idx % n_m);
+  int p = (int)(idx / n_m);
+  int c[3] = {i, j, k};
+  bool lo[3], hi[3], any = false;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    lo[d] = c[d] < G.ibn[d];
+    hi[d] = c[d] >= G.ldims[d] - G.ibn[d] && G.ibn[d] > 0;
+    any = any || lo[d] || hi[d];
+  }
+  if (!any) {
+    return;
+  }
+  float* dst = F + p * slot_len + fld_off(G, m, i, j, k);
+  float acc = *dst;
+  for (int o = 0; o < 26; o++) {
+    int di = add_order[p * 26 + o];
+    if (di < 0) {
+      break;
+    }
+    int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+    bool member = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      member = member && (dir[d] == 0 || (dir[d] < 0 ? lo[d] : hi[d]));
+    }
+    if (member) {
+      int slot = nei_slot[p * 27 + di];
+      acc += F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
+                                          k - dir[2] * G.ldims[2])];
+    }
+  }
+  *dst = acc;
+}
+
+// ---------------------------------------------------------------- Yee
+
+struct YeeDev
+{
+  float dth, cnx, cny, cnz;
+  int inv[3];
+};
+
+#define FX(m, ii, jj, kk) Fp[fld_off(G, (m), Y.inv[0] ? 0 : (ii), (jj), (kk))]
+
+template <bool IS_E>
+__global__ void k_push_fields(GridDev G, YeeDev Y, float* __restrict__ F, long slot_len)
+{
+  // loop bounds grid.hxx:124-139 with (l, r) = (1, 2) for E, (2, 1) for H
+  const int l = IS_E ? 1 : 2, r = IS_E ? 2 : 1;
+  int e0 = Y.inv[0] ? 1 : G.ldims[0] + l + r;
+  int e1 = G.ldims[1] + l + r, e2 = G.ldims[2] + l + r;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * e0 * e1 * e2) {
+    return;
+  }
+  int i = (int)(idx % e0) - (Y.inv[0] ? 0 : l);
+  idx /= e0;
+  int j = (int)(idx % e1) - l;
+  idx /= e1;
+  int k = (int)(idx % e2) - l;
+  int p = (int)(idx / e2);
+  float* Fp = F + p * slot_len;
+  if (IS_E) {
+    FX(pm::EX, i, j, k) += (Y.cny * (FX(pm::HZ, i, j, k) - FX(pm::HZ, i, j - 1, k)) -
+                            Y.cnz * (FX(pm::HY, i, j, k) - FX(pm::HY, i, j, k - 1)) -
+                            Y.dth * FX(pm::JXI, i, j, k));
+    FX(pm::EY, i, j, k) += (Y.cnz * (FX(pm::HX, i, j, k) - FX(pm::HX, i, j, k - 1)) -
+                            Y.cnx * (FX(pm::HZ, i, j, k) - FX(pm::HZ, i - 1, j, k)) -
+                            Y.dth * FX(pm::JYI, i, j, k));
+    FX(pm::EZ, i, j, k) += (Y.cnx * (FX(pm::HY, i, j, k) - FX(pm::HY, i - 1, j, k)) -
+                            Y.cny * (FX(pm::HX, i, j, k) - FX(pm::HX, i, j - 1, k)) -
+                            Y.dth * FX(pm::JZI, i, j, k));
+  } else {
+    FX(pm::HX, i, j, k) -= (Y.cny * (FX(pm::EZ, i, j + 1, k) - FX(pm::EZ, i, j, k)) -
+                            Y.cnz * (FX(pm::EY, i, j, k + 1) - FX(pm::EY, i, j, k)));
+    FX(pm::HY, i, j, k) -= (Y.cnz * (FX(pm::EX, i, j, k + 1) - FX(pm::EX, i, j, k)) -
+                            Y.cnx * (FX(pm::EZ, i + 1, j, k) - FX(pm::EZ, i, j, k)));
+    FX(pm::HZ, i, j, k) -= (Y.cnx * (FX(pm::EY, i + 1, j, k) - FX(pm::EY, i, j, k)) -
+                            Y.cny * (FX(pm::EX, i, j + 1, k) - FX(pm::EX, i, j, k)));
+  }
+}
+#undef FX
+
+// ---------------------------------------------------------------- conducting wall
+
+enum
+{
+  CW_E,
+  CW_H,
+  CW_J
+};
+
+// one thread per (patch, transverse index t, x index) of the wall plane in dim d (1 or 2)
+template <int OP>
+__global__ void k_conducting_wall(GridDev G, float* __restrict__ F, long slot_len, int d, int hi,
+                                  const pm::PatchBnd* __restrict__ pbs)
+{
+  const int x0 = G.ibn[0] ? -2 : 0, nx = G.ibn[0] ? G.ldims[0] + 4 : 1;
+  const int dt = d == 1 ? 2 : 1; // transverse dim
+  int t_lo = -2;
+  if (OP == CW_H && d == 1 && !hi) {
+    t_lo = -1; // psc_bnd_fields_impl.hxx:393 starts at -1
+  }
+  const int nt = G.ldims[dt] + 2 - t_lo;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * nt * nx) {
+    return;
+  }
+  int ix = x0 + (int)(idx % nx);
+  idx /= nx;
+  int it = t_lo + (int)(idx % nt);
+  int p = (int)(idx / nt);
+  pm::PatchBnd pb = pbs[p];
+  if (!(((hi ? pb.at_hi : pb.at_lo) >> d) & 1)) {
+    return;
+  }
+  float* Fp = F + p * slot_len;
+  const int M = G.ldims[d];
+  // a(m, n): component m at wall-normal index n
+#define A(m, n) Fp[d == 1 ? fld_off(G, (m), ix, (n), it) : fld_off(G, (m), ix, it, (n))]
+  // tangential components of a wall in y are x,z; in z they are x,y
+  const int T1 = 0, T2 = d == 1 ? 2 : 1, N = d == 1 ? 1 : 2;
+  if (OP == CW_E) {
+    const int E = pm::EX;
+    if (!hi) {
+      A(E + T1, 0) = 0.f;
+      A(E + T1, -1) = A(E + T1, 1);
+      A(E + T2, 0) = 0.f;
+      A(E + T2, -1) = A(E + T2, 1);
+      A(E + N, -1) = -A(E + N, 0);
+    } else {
+      A(E + T1, M) = 0.f;
+      A(E + T1, M + 1) = A(E + T1, M - 1);
+      A(E + T2, M) = 0.f;
+      A(E + T2, M + 1) = A(E + T2, M - 1);
+      A(E + N, M) = -A(E + N, M - 1);
+    }
+  } else if (OP == CW_H) {
+    const int H = pm::HX;
+    if (!hi) {
+      A(H + T1, -1) = -A(H + T1, 0);
+      A(H + T2, -1) = -A(H + T2, 0);
+      A(H + N, -1) = A(H + N, 1);
+    } else {
+      A(H + T1, M) = -A(H + T1, M - 1);
+      A(H + T2, M) = -A(H + T2, M - 1);
+      A(H + N, M + 1) = A(H + N, M - 1);
+    }
+  } else {
+    const int J = pm::JXI;
+    if (!hi) {
+      A(J + T1, 1) += A(J + T1, -1);
+      A(J + T1, -1) = 0.f;
+      A(J + T2, 1) += A(J + T2, -1);
+      A(J + T2, -1) = 0.f;
+      A(J + N, 0) -= A(J + N, -1);
+      A(J + N, -1) = 0.f;
+    } else {
+      A(J + T1, M - 1) += A(J + T1, M + 1);
+      A(J + T1, M + 1) = 0.f;
+      A(J + T2, M - 1) += A(J + T2, M + 1);
+      A(J + T2, M + 1) = 0.f;
+      A(J + N, M - 1) -= A(J + N, M);
+      A(J + N, M) = 0.f;
+    }
+  }
+#undef A
+}
+
+// ---------------------------------------------------------------- moments, div, checks
+
+__global__ void k_rho_1st_nc(GridDev G, uint32_t n, const uint32_t* __restrict__ off,
+                             const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
+                             float* __restrict__ R, long slot_len, float fnqs,
+                             const float* __restrict__ qk)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  int p = patch_of(off, G.n_patches, i);
+  float4 X = xi4[i];
+  float qw = pxi4[i].w;
+  float q = qk[__float_as_int(X.w)];
+  // const_accessor_simple.hxx:60-63 w = qni_wni / q ; moment.hxx:77 val = w * q ; fnqs * val
+  float w = qw / q;
+  float value = fnqs * (w * q);
+  float x[3] = {X.x, X.y, X.z};
+  int l[3];
+  float h[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    float xn = x[d] * G.pc.dxi[d];
+    l[d] = pm::fint(xn);
+    h[d] = xn - (float)l[d];
+  }
+  float* Rp = R + p * slot_len;
+  if (G.dim == pm::DIM_YZ) {
+    atomicAdd(Rp + fld_off(G, 0, 0, l[1], l[2]), value * (1.f - h[1]) * (1.f - h[2]));
+    atomicAdd(Rp + fld_off(G, 0, 0, l[1] + 1, l[2]), value * h[1] * (1.f - h[2]));
+    atomicAdd(Rp + fld_off(G, 0, 0, l[1], l[2] + 1), value * (1.f - h[1]) * h[2]);
+    atomicAdd(Rp + fld_off(G, 0, 0, l[1] + 1, l[2] + 1), value * h[1] * h[2]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      int ox = c & 1, oy = (c >> 1) & 1, oz = c >> 2;
+      float wgt = value * (ox ? h[0] : 1.f - h[0]) * (oy ? h[1] : 1.f - h[1]) *
+                  (oz ? h[2] : 1.f - h[2]);
+      atomicAdd(Rp + fld_off(G, 0, l[0] + ox, l[1] + oy, l[2] + oz), wgt);
+    }
+  }
+}
+
+// add_ghosts_reflecting.hxx:77-154, node-centred, one (d, hi) at a time
+__global__ void k_reflect_nc(GridDev G, float* __restrict__ R, long slot_len, int d, int hi,
+                             const pm::PatchBnd* __restrict__ pbs)
+{
+  int b[3], e[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    int unused = G.ibn[a] ? 1 : 0;
+    b[a] = -G.ibn[a] + unused;
+    e[a] = G.ldims[a] + G.ibn[a];
+  }
+  {
+    int unused = G.ibn[d] ? 1 : 0;
+    if (!hi) {
+      b[d] = 1;
+      e[d] = 1 + G.ibn[d] - unused;
+    } else {
+      b[d] = G.ldims[d] - G.ibn[d] + unused;
+      e[d] = G.ldims[d];
+    }
+  }
+  int n0 = max(e[0] - b[0], 0), n1 = max(e[1] - b[1], 0), n2 = max(e[2] - b[2], 0);
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * n0 * n1 * n2) {
+    return;
+  }
+  int c[3];
+  c[0] = b[0] + (int)(idx % n0);
+  idx /= n0;
+  c[1] = b[1] + (int)(idx % n1);
+  idx /= n1;
+  c[2] = b[2] + (int)(idx % n2);
+  int p = (int)(idx / n2);
+  pm::PatchBnd pb = pbs[p];
+  bool at = ((hi ? pb.at_hi : pb.at_lo) >> d) & 1;
+  int bc = hi ? pb.bc_hi[d] : pb.bc_lo[d];
+  if (!at || bc != pm::BND_PRT_REFLECTING) {
+    return;
+  }
+  int r[3] = {c[0], c[1], c[2]};
+  r[d] = hi ? 2 * G.ldims[d] - c[d] : -c[d];
+  float* Rp = R + p * slot_len;
+  Rp[fld_off(G, 0, c[0], c[1], c[2])] += Rp[fld_off(G, 0, r[0], r[1], r[2])];
+}
+
+struct DxDev
+{
+  double dx[3];
+  int inv[3];
+};
+
+// psc::item::div_nc, fields_item_fields.hxx:65-104 (interior points)
+__device__ __forceinline__ float div_nc_at(const GridDev& G, const DxDev& D, const float* Fp, int m0,
+                                           int i, int j, int k)
+{
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (D.inv[a]) {
+      continue;
+    }
+    int c[3] = {i, j, k};
+    c[a] -= 1;
+    float diff = Fp[fld_off(G, m0 + a, i, j, k)] - Fp[fld_off(G, m0 + a, c[0], c[1], c[2])];
+    acc = (float)((double)acc + (double)diff / D.dx[a]);
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void decode_interior(const GridDev& G, size_t idx, int& p, int& i, int& j,
+                                                int& k)
+{
+  i = (int)(idx % G.ldims[0]);
+  idx /= G.ldims[0];
+  j = (int)(idx % G.ldims[1]);
+  idx /= G.ldims[1];
+  k = (int)(idx % G.ldims[2]);
+  p = (int)(idx / G.ldims[2]);
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
+{
+  atomicMax((unsigned long long*)addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void k_div_nc(GridDev G, DxDev D, const float* __restrict__ F, long slot_len, int m0,
+                         float* __restrict__ out, long out_slot_len)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * G.n_cells) {
+    return;
+  }
+  int p, i, j, k;
+  decode_interior(G, idx, p, i, j, k);
+  out[p * out_slot_len + fld_off(G, 0, i, j, k)] = div_nc_at(G, D, F + p * slot_len, m0, i, j, k);
+}
+
+// checks_impl.hxx:60-97: max | rho_p - rho_m + dt * div J |
+__global__ void k_continuity(GridDev G, DxDev D, double dt, const float* __restrict__ F,
+                             long slot_len, const float* __restrict__ rho_m,
+                             const float* __restrict__ rho_p, double* __restrict__ err)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.;
+  if (idx < (size_t)G.n_patches * G.n_cells) {
+    int p, i, j, k;
+    decode_interior(G, idx, p, i, j, k);
+    long o = p * G.fld_len + fld_off(G, 0, i, j, k);
+    float d_rho = rho_p[o] - rho_m[o];
+    float divj = div_nc_at(G, D, F + p * slot_len, pm::JXI, i, j, k);
+    v = fabs((double)d_rho + dt * (double)divj);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
+  if ((threadIdx.x & 31) == 0 && v > 0.) {
+    atomic_max_nonneg(err, v);
+  }
+}
+
+struct WallDev
+{
+  int lo[3], hi[3]; // conducting wall / open at the lower / upper domain boundary in dim d
+};
+
+// checks_impl.hxx:157-184: max | div E - rho | (rho := div E on lower wall planes)
+__global__ void k_gauss(GridDev G, DxDev D, WallDev W, const float* __restrict__ F, long slot_len,
+                        const float* __restrict__ rho, const pm::PatchBnd* __restrict__ pbs,
+                        double* __restrict__ err)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.;
+  if (idx < (size_t)G.n_patches * G.n_cells) {
+    int p, i, j, k;
+    decode_interior(G, idx, p, i, j, k);
+    pm::PatchBnd pb = pbs[p];
+    int c[3] = {i, j, k};
+    bool skip = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      skip = skip || (((pb.at_lo >> d) & 1) && c[d] == 0 && W.lo[d]);
+    }
+    if (!skip) {
+      float dive = div_nc_at(G, D, F + p * slot_len, pm::EX, i, j, k);
+      float r = dive - rho[p * G.fld_len + fld_off(G, 0, i, j, k)];
+      v = fabs((double)r);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
+  if ((threadIdx.x & 31) == 0 && v > 0.) {
+    atomic_max_nonneg(err, v);
+  }
+}
+
+// marder_impl.hxx:213-250: res = div E - rho on [0, ldims) -- and on the upper wall plane
+// index ldims it is zeroed (it is a ghost here, the fill below overwrites or keeps 0)
+__global__ void k_marder_res(GridDev G, DxDev D, WallDev W, const float* __restrict__ F,
+                             long slot_len, const float* __restrict__ rho,
+                             const pm::PatchBnd* __restrict__ pbs, float* __restrict__ res)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * G.n_cells) {
+    return;
+  }
+  int p, i, j, k;
+  decode_interior(G, idx, p, i, j, k);
+  pm::PatchBnd pb = pbs[p];
+  int c[3] = {i, j, k};
+  bool zero = false;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    zero = zero || (((pb.at_lo >> d) & 1) && c[d] == 0 && W.lo[d]);
+  }
+  long o = p * G.fld_len + fld_off(G, 0, i, j, k);
+  res[o] = zero ? 0.f : div_nc_at(G, D, F + p * slot_len, pm::EX, i, j, k) - rho[o];
+}
+
+struct MarderDev
+{
+  float fac[3];
+  int inv[3];
+};
+
+// psc::marder::correct, marder_impl.hxx:26-61
+__global__ void k_marder_correct(GridDev G, MarderDev M, float* __restrict__ F, long slot_len,
+                                 const float* __restrict__ res)
+{
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * G.n_cells) {
+    return;
+  }
+  int p, i, j, k;
+  decode_interior(G, idx, p, i, j, k);
+  const float* R = res + p * G.fld_len;
+  float r0 = R[fld_off(G, 0, i, j, k)];
+  float* Fp = F + p * slot_len;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (M.inv[d]) {
+      continue;
+    }
+    int c[3] = {i, j, k};
+    c[d] += 1;
+    float* e = Fp + fld_off(G, pm::EX + d, i, j, k);
+    *e = *e + (R[fld_off(G, 0, c[0], c[1], c[2])] - r0) * M.fac[d];
+  }
+}
+
+// DiagEnergiesField.h:19-42
+__global__ void k_field_energies(GridDev G, const float* __restrict__ F, long slot_len, double fac,
+                                 double* __restrict__ out6)
+{
+  double s[6] = {0., 0., 0., 0., 0., 0.};
+  size_t n = (size_t)G.n_patches * G.n_cells;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int p, i, j, k;
+    decode_interior(G, idx, p, i, j, k);
+    const float* Fp = F + p * slot_len;
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+      float v = Fp[fld_off(G, pm::EX + m, i, j, k)];
+      s[m] += (double)(v * v) * fac;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[m] += __shfl_xor_sync(0xffffffffu, s[m], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&out6[m], s[m]);
+    }
+  }
+}
+
+DxDev make_dx(const Ctx* c)
+{
+  DxDev D;
+  for (int d = 0; d < 3; d++) {
+    D.dx[d] = c->g.dx[d];
+    D.inv[d] = c->g.invar[d];
+  }
+  return D;
+}
+
+WallDev make_wall(const Ctx* c)
+{
+  WallDev W;
+  for (int d = 0; d < 3; d++) {
+    int lo = c->g.desc.bc_fld_lo[d], hi = c->g.desc.bc_fld_hi[d];
+    W.lo[d] = lo == PSC_B200_BND_FLD_CONDUCTING_WALL || lo == PSC_B200_BND_FLD_OPEN;
+    W.hi[d] = hi == PSC_B200_BND_FLD_CONDUCTING_WALL || hi == PSC_B200_BND_FLD_OPEN;
+  }
+  return W;
+}
+
+int check_field(Ctx* c, int id, int mb, int me)
+{
+  if (id < 0 || id >= (int)c->flds.size() || !c->flds[id].d) {
+    return fail("invalid field id");
+  }
+  if (mb < 0 || me > c->flds[id].n_comps || mb > me) {
+    return fail("component range out of bounds");
+  }
+  return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- container
+
+int flds_create(Ctx* c, int n_comps, int* id)
+{
+  if (n_comps < 1) {
+    return fail("n_comps must be positive");
+  }
+  FieldArr f;
+  f.n_comps = n_comps;
+  size_t bytes = (size_t)c->n_slots * n_comps * c->gd.fld_len * sizeof(float);
+  PSC_CUDA_TRY(cudaMalloc(&f.d, bytes));
+  PSC_CUDA_TRY(cudaMemsetAsync(f.d, 0, bytes, c->stream));
+  c->flds.push_back(f);
+  *id = (int)c->flds.size() - 1;
+  return 0;
+}
+
+int flds_zero(Ctx* c, int id, int mb, int me)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  if (me == mb) {
+    return 0;
+  }
+  size_t pitch = (size_t)c->fld_slot_len(id) * sizeof(float);
+  PSC_CUDA_TRY(cudaMemset2DAsync(c->fld(id) + (size_t)mb * c->gd.fld_len, pitch, 0,
+                                 (size_t)(me - mb) * c->gd.fld_len * sizeof(float),
+                                 c->gd.n_patches, c->stream));
+  return 0;
+}
+
+int flds_fill(Ctx* c, int id, int m, float v)
+{
+  PSC_TRY(check_field(c, id, m, m + 1));
+  size_t n = (size_t)c->n_slots * c->gd.fld_len;
+  k_fill_value<<<div_up(n, 256), 256, 0, c->stream>>>(c->fld(id), c->fld_slot_len(id),
+                                                     c->gd.fld_len, c->n_slots, m, v);
+  c->n_launches++;
+  return check_launch(c, "flds_fill");
+}
+
+int flds_upload(Ctx* c, int id, int mb, int me, const float* host)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  size_t w = (size_t)(me - mb) * c->gd.fld_len * sizeof(float);
+  PSC_CUDA_TRY(cudaMemcpy2DAsync(c->fld(id) + (size_t)mb * c->gd.fld_len,
+                                 (size_t)c->fld_slot_len(id) * sizeof(float), host, w, w,
+                                 c->gd.n_patches, cudaMemcpyHostToDevice, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int flds_download(Ctx* c, int id, int mb, int me, float* host)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  size_t w = (size_t)(me - mb) * c->gd.fld_len * sizeof(float);
+  PSC_CUDA_TRY(cudaMemcpy2DAsync(host, w, c->fld(id) + (size_t)mb * c->gd.fld_len,
+                                 (size_t)c->fld_slot_len(id) * sizeof(float), w, c->gd.n_patches,
+                                 cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------- Bnd
+
+int bnd_fill_ghosts(Ctx* c, int id, int mb, int me)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  if (c->comm) {
+    PSC_TRY(comm_halo_exchange(c, id, mb, me, false));
+  }
+  size_t n = (size_t)c->gd.n_patches * (me - mb) * c->gd.fld_len;
+  KernelScope ks(c, "fill_ghosts");
+  k_fill_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(id), c->fld_slot_len(id), mb,
+                                                      me, c->d_nei_slot);
+  c->n_launches++;
+  return check_launch(c, "fill_ghosts");
+}
+
+int bnd_add_ghosts(Ctx* c, int id, int mb, int me)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  if (c->comm) {
+    PSC_TRY(comm_halo_exchange(c, id, mb, me, true));
+  }
+  size_t n = (size_t)c->gd.n_patches * (me - mb) * c->gd.n_cells;
+  KernelScope ks(c, "add_ghosts");
+  k_add_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(id), c->fld_slot_len(id), mb,
+                                                     me, c->d_nei_slot, c->d_add_order);
+  c->n_launches++;
+  return check_launch(c, "add_ghosts");
+}
+
+// ---------------------------------------------------------------- BndFields
+
+template <int OP>
+static int bndf_apply(Ctx* c, const char* name)
+{
+  const GridHost& g = c->g;
+  // psc_bnd_fields_impl.hxx:27-188: lower walls for d = 0..2, then upper walls
+  for (int hi = 0; hi < 2; hi++) {
+    for (int d = 0; d < 3; d++) {
+      int bc = hi ? g.desc.bc_fld_hi[d] : g.desc.bc_fld_lo[d];
+      if (bc != PSC_B200_BND_FLD_CONDUCTING_WALL) {
+        continue;
+      }
+      if (d == 0) {
+        return fail("conducting wall in x is not implemented (nor is it in PSC: "
+                    "psc_bnd_fields_impl.hxx:301-530 covers y and z)");
+      }
+      int dt = d == 1 ? 2 : 1;
+      size_t n = (size_t)c->gd.n_patches * (g.ldims[dt] + 4) * (g.ibn[0] ? g.ldims[0] + 4 : 1);
+      KernelScope ks(c, name);
+      k_conducting_wall<OP><<<div_up(n, 128), 128, 0, c->stream>>>(c->gd, c->fld(0),
+                                                                  c->fld_slot_len(0), d, hi,
+                                                                  c->d_patch_bnd);
+      c->n_launches++;
+    }
+  }
+  return check_launch(c, name);
+}
+
+int bndf_fill_ghosts_E(Ctx* c)
+{
+  return bndf_apply<CW_E>(c, "bndf_E");
+}
+int bndf_fill_ghosts_H(Ctx* c)
+{
+  return bndf_apply<CW_H>(c, "bndf_H");
+}
+int bndf_add_ghosts_J(Ctx* c)
+{
+  return bndf_apply<CW_J>(c, "bndf_J");
+}
+
+// ---------------------------------------------------------------- PushFields
+
+static int push_fields(Ctx* c, double dt_fac, bool is_E)
+{
+  YeeConst y = make_yee_const(c->g, dt_fac);
+  YeeDev Y{y.dth, y.cnx, y.cny, y.cnz, {c->g.invar[0], c->g.invar[1], c->g.invar[2]}};
+  const GridDev& G = c->gd;
+  size_t n = (size_t)G.n_patches * (G.ibn[0] ? G.ldims[0] + 3 : 1) * (G.ldims[1] + 3) *
+             (G.ldims[2] + 3);
+  KernelScope ks(c, is_E ? "push_E" : "push_H");
+  if (is_E) {
+    k_push_fields<true><<<div_up(n, 256), 256, 0, c->stream>>>(G, Y, c->fld(0), c->fld_slot_len(0));
+  } else {
+    k_push_fields<false><<<div_up(n, 256), 256, 0, c->stream>>>(G, Y, c->fld(0), c->fld_slot_len(0));
+  }
+  c->n_launches++;
+  return check_launch(c, "push_fields");
+}
+
+int push_E(Ctx* c, double dt_fac)
+{
+  return push_fields(c, dt_fac, true);
+}
+int push_H(Ctx* c, double dt_fac)
+{
+  return push_fields(c, dt_fac, false);
+}
+
+// ---------------------------------------------------------------- moments / checks / Marder
+
+int moment_rho_1st_nc(Ctx* c, int id)
+{
+  PSC_TRY(check_field(c, id, 0, 1));
+  const GridDev& G = c->gd;
+  PSC_TRY(flds_zero(c, id, 0, 1));
+  // zero proxies too (they receive neighbours' ghost sums)
+  if (c->n_slots > G.n_patches) {
+    PSC_CUDA_TRY(cudaMemsetAsync(c->fld(id) + (size_t)G.n_patches * c->fld_slot_len(id), 0,
+                                 (size_t)(c->n_slots - G.n_patches) * c->fld_slot_len(id) *
+                                   sizeof(float),
+                                 c->stream));
+  }
+  PSC_TRY(c->scr[8].reserve(pm::MAX_KINDS * sizeof(float)));
+  float qk[pm::MAX_KINDS] = {};
+  for (int k = 0; k < c->g.desc.n_kinds; k++) {
+    qk[k] = (float)c->g.desc.q[k];
+  }
+  PSC_CUDA_TRY(cudaMemcpyAsync(c->scr[8].p, qk, sizeof(qk), cudaMemcpyHostToDevice, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->n_prts) {
+    KernelScope ks(c, "rho_1st_nc");
+    k_rho_1st_nc<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(
+      G, c->n_prts, c->d_off, c->xi(), c->pxi(), c->fld(id), c->fld_slot_len(id),
+      (float)c->g.desc.fnqs, c->scr[8].as<float>());
+    c->n_launches++;
+  }
+  // ItemMomentBnd::add_ghosts, fields_item.hxx:36-90
+  for (int hi = 0; hi < 2; hi++) {
+    for (int d = 0; d < 3; d++) {
+      int bc = hi ? c->g.desc.bc_prt_hi[d] : c->g.desc.bc_prt_lo[d];
+      if (bc != PSC_B200_BND_PRT_REFLECTING || c->g.invar[d]) {
+        continue;
+      }
+      size_t n = (size_t)G.n_patches * G.fld_len;
+      k_reflect_nc<<<div_up(n, 256), 256, 0, c->stream>>>(G, c->fld(id), c->fld_slot_len(id), d, hi,
+                                                         c->d_patch_bnd);
+      c->n_launches++;
+    }
+  }
+  PSC_TRY(check_launch(c, "rho_1st_nc"));
+  return bnd_add_ghosts(c, id, 0, 1);
+}
+
+static int ensure_scalar(Ctx* c, int& id)
+{
+  if (id < 0) {
+    PSC_TRY(flds_create(c, 1, &id));
+  }
+  return 0;
+}
+
+int check_continuity_begin(Ctx* c)
+{
+  PSC_TRY(ensure_scalar(c, c->rho_m_id));
+  return moment_rho_1st_nc(c, c->rho_m_id);
+}
+
+static int read_max(Ctx* c, double* d_err, double* out)
+{
+  PSC_CUDA_TRY(cudaMemcpyAsync(out, d_err, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->comm) {
+    PSC_TRY(comm_allreduce_max(c, out, 1));
+  }
+  return 0;
+}
+
+int check_continuity_end(Ctx* c, double* err)
+{
+  if (c->rho_m_id < 0) {
+    return fail("check_continuity_end without check_continuity_begin");
+  }
+  PSC_TRY(ensure_scalar(c, c->rho_p_id));
+  PSC_TRY(moment_rho_1st_nc(c, c->rho_p_id));
+  PSC_TRY(c->scr[8].reserve(64));
+  double* d_err = c->scr[8].as<double>() + 2;
+  PSC_CUDA_TRY(cudaMemsetAsync(d_err, 0, sizeof(double), c->stream));
+  size_t n = (size_t)c->gd.n_patches * c->gd.n_cells;
+  k_continuity<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, make_dx(c), c->g.desc.dt, c->fld(0),
+                                                     c->fld_slot_len(0), c->fld(c->rho_m_id),
+                                                     c->fld(c->rho_p_id), d_err);
+  c->n_launches++;
+  PSC_TRY(check_launch(c, "continuity"));
+  PSC_TRY(read_max(c, d_err, err));
+  c->last_continuity = *err;
+  return 0;
+}
+
+int check_gauss(Ctx* c, double* err)
+{
+  PSC_TRY(ensure_scalar(c, c->rho_p_id));
+  PSC_TRY(moment_rho_1st_nc(c, c->rho_p_id));
+  PSC_TRY(c->scr[8].reserve(64));
+  double* d_err = c->scr[8].as<double>() + 2;
+  PSC_CUDA_TRY(cudaMemsetAsync(d_err, 0, sizeof(double), c->stream));
+  size_t n = (size_t)c->gd.n_patches * c->gd.n_cells;
+  k_gauss<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, make_dx(c), make_wall(c), c->fld(0),
+                                                c->fld_slot_len(0), c->fld(c->rho_p_id),
+                                                c->d_patch_bnd, d_err);
+  c->n_launches++;
+  PSC_TRY(check_launch(c, "gauss"));
+  PSC_TRY(read_max(c, d_err, err));
+  c->last_gauss = *err;
+  return 0;
+}
+
+int marder(Ctx* c, double diffusion_, int loop)
+{
+  const GridHost& g = c->g;
+  const GridDev& G = c->gd;
+  double inv_sum = 0.;
+  for (int d = 0; d < 3; d++) {
+    if (!g.invar[d]) {
+      inv_sum += g.dx_inv[d] * g.dx_inv[d];
+    }
+  }
+  // marder_impl.hxx:160-176
+  double diffusion_max = 1. / 2. / (.5 * g.desc.dt) / inv_sum;
+  double diffusion = diffusion_max * (double)(float)diffusion_;
+  PSC_TRY(ensure_scalar(c, c->rho_p_id));
+  PSC_TRY(ensure_scalar(c, c->div_id));
+  int rho = c->rho_p_id, res = c->div_id;
+  PSC_TRY(moment_rho_1st_nc(c, rho));
+  MarderDev M;
+  float s = .5f * (float)g.desc.dt * (float)diffusion;
+  for (int d = 0; d < 3; d++) {
+    M.fac[d] = s * (float)g.dx_inv[d];
+    M.inv[d] = g.invar[d];
+  }
+  size_t n = (size_t)G.n_patches * G.n_cells;
+  for (int it = 0; it < loop; it++) {
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
+    // res = 0 everywhere (ghosts included), then div E - rho on the interior
+    PSC_CUDA_TRY(cudaMemsetAsync(c->fld(res), 0,
+                                 (size_t)c->n_slots * c->fld_slot_len(res) * sizeof(float),
+                                 c->stream));
+    {
+      KernelScope ks(c, "marder_res");
+      k_marder_res<<<div_up(n, 256), 256, 0, c->stream>>>(G, make_dx(c), make_wall(c), c->fld(0),
+                                                         c->fld_slot_len(0), c->fld(rho),
+                                                         c->d_patch_bnd, c->fld(res));
+      c->n_launches++;
+    }
+    PSC_TRY(bnd_fill_ghosts(c, res, 0, 1));
+    {
+      KernelScope ks(c, "marder_correct");
+      k_marder_correct<<<div_up(n, 256), 256, 0, c->stream>>>(G, M, c->fld(0), c->fld_slot_len(0),
+                                                             c->fld(res));
+      c->n_launches++;
+    }
+  }
+  PSC_TRY(check_launch(c, "marder"));
+  return bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3);
+}
+
+int field_energies(Ctx* c, double out6[6])
+{
+  PSC_TRY(c->scr[8].reserve(128));
+  double* d = c->scr[8].as<double>() + 4;
+  PSC_CUDA_TRY(cudaMemsetAsync(d, 0, 6 * sizeof(double), c->stream));
+  size_t n = (size_t)c->gd.n_patches * c->gd.n_cells;
+  unsigned nb = std::min<unsigned>(div_up(n, 256), 148 * 8);
+  k_field_energies<<<nb, 256, 0, c->stream>>>(c->gd, c->fld(0), c->fld_slot_len(0),
+                                             c->g.dx[0] * c->g.dx[1] * c->g.dx[2], d);
+  c->n_launches++;
+  PSC_CUDA_TRY(cudaMemcpyAsync(out6, d, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return check_launch(c, "field_energies");
+}
+
+} // namespace psc_b200

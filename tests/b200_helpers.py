@@ -62,3 +62,45 @@ def hostcheck():
         L.hc_grid_info.argtypes = [P, P, P, P, P]
         _hc = L
     return _hc
+
+
+def make_gpu_grid(og, **kw):
+    """psc_b200.Grid (device context) for the same grid the oracle uses"""
+    import psc_b200 as pb
+    g = og.g
+    return pb.Grid(gdims=tuple(g.gdims), length=tuple(g.length), np=tuple(g.np), dt=g.dt,
+                   kinds=og.kinds, fnqs=g.fnqs, eta=g.eta, corner=tuple(g.corner),
+                   bc_fld_lo=list(g.bc_fld_lo), bc_fld_hi=list(g.bc_fld_hi),
+                   bc_prt_lo=list(g.bc_prt_lo), bc_prt_hi=list(g.bc_prt_hi),
+                   deposit=g.deposit, **kw)
+
+
+def gpu_state(og, flds, prts, off, options=None):
+    """device context loaded with the given fields and particles"""
+    import psc_b200 as pb
+    grid = make_gpu_grid(og)
+    for k, v in (options or {}).items():
+        grid.set_option(k, v)
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    if prts is not None:
+        mprts.set(prts, np.diff(off))
+    if flds is not None:
+        mflds.upload(flds)
+    return grid, mprts, mflds
+
+
+def gpu_push(options=None, sort_first=False):
+    """push(grid, flds, prts, off) backend running the CUDA path through the C ABI"""
+    import psc_b200 as pb
+
+    def push(og, flds, prts, off):
+        grid, mprts, mflds = gpu_state(og, flds, prts, off, options)
+        if sort_first:
+            pb.Sort()(mprts)
+        pb.PushParticles().push_mprts(mprts, mflds)
+        got, got_off = mprts.get()
+        assert np.array_equal(got_off, off)
+        prts[:] = got
+        flds[:] = mflds.download()
+        grid.close()
+    return push

@@ -1,0 +1,178 @@
+"""Field-side operators on the device vs the CPU oracle (through the C ABI):
+ghost fill/add, Yee push, conducting walls, rho moment, checks, Marder, energies."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from b200_helpers import gpu_state
+from gen import random_fields, thermal_plasma
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ((-1., 1.), (1., 100.))
+WALL_Y = dict(bc_fld_lo=[1, 2, 1], bc_fld_hi=[1, 2, 1], bc_prt_lo=[1, 0, 1], bc_prt_hi=[1, 0, 1])
+WALL_YZ = dict(bc_fld_lo=[1, 2, 2], bc_fld_hi=[1, 2, 2], bc_prt_lo=[1, 0, 0], bc_prt_hi=[1, 0, 0])
+GRIDS = {
+    "xyz": dict(gdims=(8, 12, 16), length=(5., 9., 20.), np_=(2, 1, 2)),
+    "xyz_1patch": dict(gdims=(8, 8, 8), length=(8., 8., 8.), np_=(1, 1, 1)),
+    "yz": dict(gdims=(1, 24, 16), length=(1., 30., 10.), np_=(1, 3, 2)),
+    "yz_wall_y": dict(gdims=(1, 24, 16), length=(1., 30., 10.), np_=(1, 3, 2), **WALL_Y),
+    "xyz_wall_yz": dict(gdims=(8, 12, 16), length=(5., 9., 20.), np_=(1, 3, 2), **WALL_YZ),
+}
+
+
+def _grid(name):
+    return ol.Grid(dt=0.15, kinds=KINDS, nicell=10, **GRIDS[name])
+
+
+def _all_random(og, seed):
+    rng = np.random.default_rng(seed)
+    f = og.zeros_fields()
+    f[:] = rng.standard_normal(f.shape).astype(np.float32)
+    return f
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_fill_and_add_ghosts(name):
+    import psc_b200 as pb
+    og = _grid(name)
+    f = _all_random(og, 1)
+    # test_bnd.cxx:104-180 pattern on one component: 100*i + 10*j + k per global cell
+    ld, ib = og.ldims, og.ib
+    for p in range(og.n_patches):
+        o = og.patch_off(p)
+        k, j, i = np.meshgrid(np.arange(ld[2]) + o[2], np.arange(ld[1]) + o[1],
+                              np.arange(ld[0]) + o[0], indexing="ij")
+        f[p, 4, -ib[2]:-ib[2] + ld[2], -ib[1]:-ib[1] + ld[1], -ib[0]:-ib[0] + ld[0]] = \
+            100 * i + 10 * j + k
+    grid, _, mflds = gpu_state(og, f, None, None)
+    bnd = pb.Bnd()
+    ref = f.copy()
+    ol.fill_ghosts(og, ref, 3, 6)
+    bnd.fill_ghosts(mflds, 3, 6)
+    got = mflds.download()
+    assert got.tobytes() == ref.tobytes()
+    ol.add_ghosts(og, ref, 0, 3)
+    bnd.add_ghosts(mflds, 0, 3)
+    got = mflds.download()
+    # same summation order as the reference's sequential loop => bit-exact
+    assert got.tobytes() == ref.tobytes()
+    grid.close()
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_push_fields(name):
+    import psc_b200 as pb
+    og = _grid(name)
+    f = _all_random(og, 2)
+    grid, _, mflds = gpu_state(og, f, None, None)
+    pf = pb.PushFields()
+    ref = f.copy()
+    for dt_fac, is_e in ((.5, False), (1., True), (.5, False)):
+        if is_e:
+            ol.push_E(og, ref, dt_fac)
+            pf.push_E(mflds, dt_fac)
+        else:
+            ol.push_H(og, ref, dt_fac)
+            pf.push_H(mflds, dt_fac)
+        got = mflds.download()
+        assert got.tobytes() == ref.tobytes(), (dt_fac, is_e)
+    grid.close()
+
+
+@pytest.mark.parametrize("name", ["yz_wall_y", "xyz_wall_yz"])
+def test_conducting_wall(name):
+    import psc_b200 as pb
+    og = _grid(name)
+    f = _all_random(og, 3)
+    grid, _, mflds = gpu_state(og, f, None, None)
+    bndf = pb.BndFields()
+    ref = f.copy()
+    L = ol.lib()
+    for op_ref, op_gpu in ((L.po_bndf_fill_ghosts_E, bndf.fill_ghosts_E),
+                           (L.po_bndf_fill_ghosts_H, bndf.fill_ghosts_H),
+                           (L.po_bndf_add_ghosts_J, bndf.add_ghosts_J)):
+        op_ref(og.byref(), ol.ptr(ref))
+        op_gpu(mflds)
+        got = mflds.download()
+        assert got.tobytes() == ref.tobytes(), op_gpu.__name__
+    grid.close()
+
+
+@pytest.mark.parametrize("name", list(GRIDS))
+def test_rho_checks_energies(name):
+    import psc_b200 as pb
+    og = _grid(name)
+    f = _all_random(og, 4)
+    prts, off = thermal_plasma(og, ppc=6, seed=5, vth=(0.3, 0.03))
+    grid, mprts, mflds = gpu_state(og, f, prts, off)
+    rho = pb.Mfields(grid, 1)
+    pb.check(grid.lib.psc_b200_moment_rho_1st_nc(grid.ctx, rho.id))
+    got = rho.download()
+    ref = ol.moment_rho(og, prts, off)
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    # gauss: max |div E - rho|
+    import ctypes as C
+    e = C.c_double()
+    pb.check(grid.lib.psc_b200_check_gauss(grid.ctx, C.byref(e)))
+    ref_g = ol.gauss(og, ref, f)
+    assert abs(e.value - ref_g) <= 1e-5 * abs(ref_g)
+    # energies
+    en = pb.api.energies(grid)
+    ref_e = ol.energies(og, f, prts, off)
+    np.testing.assert_allclose(en, ref_e, rtol=1e-10, atol=1e-300)
+    grid.close()
+
+
+@pytest.mark.parametrize("name", ["xyz", "yz", "yz_wall_y"])
+def test_marder(name):
+    import psc_b200 as pb
+    og = _grid(name)
+    f = _all_random(og, 6)
+    prts, off = thermal_plasma(og, ppc=6, seed=7, vth=(0.3, 0.03))
+    grid, mprts, mflds = gpu_state(og, f, prts, off)
+    ref = f.copy()
+    ol.marder(og, ref, prts, off, 0.9, 3)
+    pb.Marder(grid, 0.9, 3)(mflds, mprts)
+    got = mflds.download()
+    # rho is accumulated with atomics (order differs): compare E with a tolerance
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert got[:, [0, 1, 2, 6, 7, 8]].tobytes() == ref[:, [0, 1, 2, 6, 7, 8]].tobytes()
+    grid.close()
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["operators", "fused_step"])
+@pytest.mark.parametrize("name", ["xyz", "yz", "yz_wall_y", "xyz_wall_yz"])
+def test_psc_steps_match_oracle(name, fused):
+    """Psc::step sequence for several steps: same particle migration (exact counts),
+    x/u and fields close to the oracle's, continuity at round-off, energies within 1%"""
+    import psc_b200 as pb
+    og = _grid(name)
+    f = random_fields(og, seed=8, amp_e=0.02, amp_b=0.05)
+    ol.fill_ghosts(og, f, 3, 9)
+    prts, off = thermal_plasma(og, ppc=8, seed=9, vth=(0.2, 0.02), margin=0.05)
+    grid, mprts, mflds = gpu_state(og, f, prts, off)
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1, marder_interval=2, marder_loop=2,
+                 checks=pb.Checks(grid, continuity_interval=1), fused=fused)
+    rf, rp, ro = f.copy(), prts.copy(), off.copy()
+    for step in range(1, 5):
+        rp, ro = ol.step(og, rf, rp, ro, sort_now=True, marder_loop=2 if step % 2 == 0 else 0)
+        psc.step()
+        if fused:
+            c, g_ = pb.api.C.c_double(), pb.api.C.c_double()
+            pb.check(grid.lib.psc_b200_last_checks(grid.ctx, pb.api.C.byref(c), pb.api.C.byref(g_)))
+            cont = c.value
+        else:
+            cont = psc.checks.continuity.last_max_err
+        assert cont < 5e-6, cont
+    gp, go = mprts.get()
+    if fused:
+        ol.sort(og, rp, ro)  # the fused step already did the next step's sort
+    assert np.array_equal(go, ro)
+    gf = mflds.download()
+    assert np.abs(gf - rf).max() <= 2e-5 * np.abs(rf).max()
+    assert np.array_equal(gp["kind"], rp["kind"])
+    assert np.abs(gp["x"] - rp["x"]).max() <= 1e-5 * max(og.length)
+    assert np.abs(gp["u"] - rp["u"]).max() <= 1e-5
+    np.testing.assert_allclose(pb.api.energies(grid), ol.energies(og, rf, rp, ro), rtol=1e-4)
+    grid.close()

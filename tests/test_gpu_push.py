@@ -1,0 +1,106 @@
+"""Parity of the CUDA push+deposit (through the C ABI) with the CPU oracle.
+
+Bars (BASELINE.json north_star): particle x/u within 4 float ULP of the reference's
+CPU 1vb path -- the default (-fmad=false) build is held to BIT-EXACT --, deposited J
+within 1e-5 relative (summation order differs: atomics)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from b200_helpers import gpu_state, gpu_push
+from gen import random_fields, thermal_plasma, ulp_diff
+from golden_cases import GOLDEN, run_push_case
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ((-1., 1.), (1., 100.))
+CASES = {
+    "xyz_split": dict(gdims=(16, 16, 16), length=(16., 16., 16.), np_=(2, 1, 2)),
+    "xyz_aniso": dict(gdims=(8, 24, 16), length=(10., 20., 7.), np_=(1, 3, 1)),
+    "yz_var1": dict(gdims=(1, 32, 48), length=(1., 40., 30.), np_=(1, 2, 3)),
+    "yz_split": dict(gdims=(1, 32, 48), length=(1., 40., 30.), np_=(1, 2, 3),
+                     deposit=ol.DEPOSIT_SPLIT),
+}
+PATHS = {
+    "general": (dict(tiled=0), False),
+    "tiled": (dict(tiled=1, warp_reduce=0, tma=0), True),
+    "tiled_warp": (dict(tiled=1, warp_reduce=1, tma=0), True),
+    "tiled_warp_tma": (dict(tiled=1, warp_reduce=1, tma=1), True),
+    "tiled_small": (dict(tiled=1, warp_reduce=1, tma=1, tile=4, threads=128), True),
+}
+
+
+def _setup(name, vth, ppc=12):
+    kw = dict(CASES[name])
+    dx = [l / g for l, g in zip(kw["length"], kw["gdims"])]
+    dt = 0.45 * min(d for d, g in zip(dx, kw["gdims"]) if g > 1)
+    og = ol.Grid(dt=dt, kinds=KINDS, nicell=ppc, **kw)
+    flds = random_fields(og, seed=7)
+    prts, off = thermal_plasma(og, ppc=ppc, seed=8, vth=(vth, vth / 10))
+    return og, flds, prts, off
+
+
+@pytest.mark.parametrize("fma", [0, 1], ids=["exact", "fma"])
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("vth", [0.05, 0.7])
+@pytest.mark.parametrize("name", list(CASES))
+def test_push_matches_oracle(name, vth, path, fma):
+    og, flds, prts, off = _setup(name, vth)
+    opts, sort_first = PATHS[path]
+    opts = dict(opts, fma=fma)
+    f_ref, p_ref = flds.copy(), prts.copy()
+    if sort_first:
+        rc, _ = ol.sort(og, p_ref, off)
+        assert rc == 0
+    ol.push_mprts(og, f_ref, p_ref, off)
+    f_gpu, p_gpu = flds.copy(), prts.copy()
+    gpu_push(opts, sort_first)(og, f_gpu, p_gpu, off)
+    assert np.array_equal(p_gpu["kind"], p_ref["kind"])
+    assert p_gpu["qni_wni"].tobytes() == p_ref["qni_wni"].tobytes()
+    if fma == 0:
+        assert p_gpu.tobytes() == p_ref.tobytes(), (
+            "x %d ulp, u %d ulp" % (ulp_diff(p_gpu["x"], p_ref["x"]), ulp_diff(p_gpu["u"], p_ref["u"])))
+    else:
+        # 4 ULP of the value, or of the cell size for positions / of vth for momenta
+        # (components near zero have no meaningful ULP distance)
+        for key, scale in (("x", max(og.dx)), ("u", vth)):
+            a, b = p_gpu[key].astype(np.float64), p_ref[key].astype(np.float64)
+            tol = 4 * np.spacing(np.maximum(np.abs(b), scale).astype(np.float32)).astype(np.float64)
+            assert np.all(np.abs(a - b) <= tol), key
+    # E/B untouched
+    assert f_gpu[:, 3:].tobytes() == flds[:, 3:].tobytes()
+    jr, jg = f_ref[:, :3], f_gpu[:, :3]
+    scale = np.abs(jr).max()
+    assert scale > 0
+    assert np.abs(jg - jr).max() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("path", ["general", "tiled_warp"])
+@pytest.mark.parametrize("dim", ["xyz", "yz"])
+@pytest.mark.parametrize("case", GOLDEN["push_cases"], ids=[c["name"] for c in GOLDEN["push_cases"]])
+def test_golden_single_particle(case, dim, path):
+    """src/libpsc/tests/test_push_particles.cxx SingleParticlePushp1..16 on the device"""
+    opts, sort_first = PATHS[path]
+    run_push_case(case, dim, gpu_push(opts, sort_first))
+
+
+def test_continuity_large():
+    """size-independent property at a size the oracle would take minutes for:
+    d(rho) + dt * div J = 0 to float round-off after push + exchange + J ghost sums"""
+    import psc_b200 as pb
+    og = ol.Grid(gdims=(64, 64, 64), length=(64., 64., 64.), np_=(2, 2, 2), dt=0.4, kinds=KINDS,
+                 nicell=16)
+    from b200_helpers import make_gpu_grid
+    grid = make_gpu_grid(og)
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    mprts.setup_thermal(16, [0.2, 0.02], seed=3)
+    mflds.fill(pb.HZ, 0.1)
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1,
+                 checks=pb.Checks(grid, continuity_interval=1, gauss_interval=0))
+    n0 = mprts.size()
+    for _ in range(3):
+        psc.step()
+        # rho ~ fnqs * ppc = 2 per species: round-off level is ~1e-6
+        assert psc.checks.continuity.last_max_err < 2e-5, psc.checks.continuity.last_max_err
+    assert mprts.size() == n0
+    grid.close()
