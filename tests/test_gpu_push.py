@@ -72,7 +72,9 @@ def test_push_matches_oracle(name, vth, path, fma):
     jr, jg = f_ref[:, :3], f_gpu[:, :3]
     scale = np.abs(jr).max()
     assert scale > 0
-    assert np.abs(jg - jr).max() <= 1e-5 * scale
+    # J sums thousands of +/- contributions per node; with FMA contraction each one may
+    # differ in the last bit, so the FMA build gets 3e-5 of max|J| (exact build: 1e-5)
+    assert np.abs(jg - jr).max() <= (1e-5 if fma == 0 else 3e-5) * scale
 
 
 @pytest.mark.parametrize("path", ["general", "tiled_warp"])
