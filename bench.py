@@ -186,6 +186,10 @@ def run_b200(args, rank, world, local_rank):
         grid.set_option(k, v)
     if args.tile:
         grid.set_option("tile", args.tile)
+    if args.threads:
+        grid.set_option("threads", args.threads)
+    if args.min_blocks:
+        grid.set_option("min_blocks", args.min_blocks)
     mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
     mprts.setup_thermal(ppc // 2, list(VTH), seed=1234)
     mflds.fill(pb.HZ, 0.1)
@@ -316,6 +320,8 @@ def main():
     ap.add_argument("--warp-reduce", dest="warp_reduce", type=int, default=1)
     ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
     ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--min-blocks", dest="min_blocks", type=int, default=0)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -224,6 +224,7 @@ static int ctx_create(const psc_b200_grid_desc* desc, Ctx** out)
   size_t nct = (size_t)g.n_cells * g.n_patches;
   PSC_CUDA_TRY(cudaMalloc(&c->d_cell_off, (nct + 1) * sizeof(uint32_t)));
   PSC_CUDA_TRY(cudaMemset(c->d_cell_off, 0, (nct + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_cell_off_alt, (nct + 1) * sizeof(uint32_t)));
   PSC_TRY(build_patch_tables(c));
   int id;
   PSC_TRY(flds_create(c, PSC_B200_NR_FIELDS, &id)); // field 0 = MfieldsState
@@ -249,6 +250,7 @@ static void ctx_destroy(Ctx* c)
   }
   cudaFree(c->d_off);
   cudaFree(c->d_cell_off);
+  cudaFree(c->d_cell_off_alt);
   cudaFree(c->d_patch_bnd);
   cudaFree(c->d_nei_patch);
   cudaFree(c->d_nei_slot);
@@ -284,6 +286,7 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
   if (prm->checks) {
     PSC_TRY(check_continuity_begin(c)); // :379-384
   }
+  c->want_counts = prm->sort && c->opt_fused_sort && c->sorted;
   PSC_TRY(push_mprts(c)); // :389
   // :412 bndp_ -- when this step's store was cell-ordered, the exchange is fused with
   // the sort the next step would start with (same result, one pass over the particles)
@@ -585,6 +588,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "fma") { c->opt_fma = v; }
     else if (n == "tma") { c->opt_tma = v; }
     else if (n == "threads") { c->opt_threads = v; }
+    else if (n == "min_blocks") { c->opt_min_blocks = v; }
     else if (n == "tile") { c->opt_tile[0] = c->opt_tile[1] = c->opt_tile[2] = v; }
     else if (n == "tile_x") { c->opt_tile[0] = v; }
     else if (n == "tile_y") { c->opt_tile[1] = v; }
@@ -606,6 +610,7 @@ int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
     else if (n == "capacity") { *value = (double)c->cap; }
     else if (n == "n_slots") { *value = c->n_slots; }
     else if (n == "fused_steps") { *value = (double)c->n_fused; }
+    else if (n == "fused_fallbacks") { *value = (double)c->n_fused_fallback; }
     else { return fail("unknown stat " + n); }
     return 0;)
 }

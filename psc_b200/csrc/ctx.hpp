@@ -96,6 +96,7 @@ struct Ctx
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with cp.async.bulk (TMA) instead of LDG/STS
   int opt_threads = 512;   // CTA size of the tiled push
+  int opt_min_blocks = 2;  // resident CTAs per SM the tiled push is compiled for
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
@@ -112,7 +113,11 @@ struct Ctx
   bool pushed_from_sorted = false; // store = cell-ordered store after exactly one push;
                                    // cell_off still describes the pre-push cell runs
   uint64_t n_fused = 0;          // steps that took the fused boundary+sort pass
+  bool want_counts = false;      // step(): the next push should count per-cell destinations
+  bool counts_valid = false;     // scr[9]/scr[11] hold the counts of the last push
   uint32_t* d_cell_off = nullptr; // n_patches * n_cells + 1
+  uint32_t* d_cell_off_alt = nullptr; // written by the fused boundary+sort pass
+  uint64_t n_fused_fallback = 0;
   uint64_t n_dropped = 0;        // absorbed at open/absorbing walls so far
 
   // ---- per-patch tables (device)

@@ -56,59 +56,125 @@ __global__ void k_fill_value(float* F, long slot_len, long fld_len, int n_slots,
 
 // ---------------------------------------------------------------- ghost exchange
 
-__global__ void k_fill_ghosts(GridDev G, float* __restrict__ F, long slot_len, int mb, int me,
-                              const int* __restrict__ nei_slot)
+// Enumeration of the points a ghost exchange touches, so that no thread is spent on the
+// rest of the patch: ghost shell (fill) or the interior band within ibn of a face (add).
+// Three groups: z in band | y in band | x in band (remaining directions not in band).
+struct BandGeom
 {
+  int lo[3], hi[3]; // band widths below / above
+  int e[3];         // extent the bands wrap around: im (ghost shell) or ldims (interior band)
+  int n2, n1, n0;   // points per group
+  int inner_lo[3];  // first non-band coordinate (array coordinates of the extent)
+};
+
+inline BandGeom make_band(const GridHost& g, bool ghost_shell)
+{
+  BandGeom B;
+  for (int d = 0; d < 3; d++) {
+    if (ghost_shell) {
+      B.e[d] = g.im[d];
+      B.lo[d] = B.hi[d] = g.ibn[d];
+    } else {
+      B.e[d] = g.ldims[d];
+      B.lo[d] = std::min(g.ibn[d], g.ldims[d]);
+      B.hi[d] = std::min(g.ibn[d], g.ldims[d] - B.lo[d]);
+    }
+    B.inner_lo[d] = B.lo[d];
+  }
+  int nb[3], in[3];
+  for (int d = 0; d < 3; d++) {
+    nb[d] = B.lo[d] + B.hi[d];
+    in[d] = B.e[d] - nb[d];
+  }
+  B.n2 = nb[2] * B.e[1] * B.e[0];
+  B.n1 = in[2] * nb[1] * B.e[0];
+  B.n0 = in[2] * in[1] * nb[0];
+  return B;
+}
+
+// band index -> coordinate in [0, e)
+__device__ __forceinline__ int band_coord(const BandGeom& B, int d, int kk)
+{
+  return kk < B.lo[d] ? kk : B.e[d] - B.hi[d] + (kk - B.lo[d]);
+}
+
+// idx in [0, n2+n1+n0) -> coordinates in [0, e)^3
+__device__ __forceinline__ void band_decode(const BandGeom& B, int idx, int& x, int& y, int& z)
+{
+  if (idx < B.n2) {
+    x = idx % B.e[0];
+    idx /= B.e[0];
+    y = idx % B.e[1];
+    z = band_coord(B, 2, idx / B.e[1]);
+    return;
+  }
+  idx -= B.n2;
+  if (idx < B.n1) {
+    int nb1 = B.lo[1] + B.hi[1];
+    x = idx % B.e[0];
+    idx /= B.e[0];
+    y = band_coord(B, 1, idx % nb1);
+    z = B.inner_lo[2] + idx / nb1;
+    return;
+  }
+  idx -= B.n1;
+  int nb0 = B.lo[0] + B.hi[0];
+  int in1 = B.e[1] - B.lo[1] - B.hi[1];
+  x = band_coord(B, 0, idx % nb0);
+  idx /= nb0;
+  y = B.inner_lo[1] + idx % in1;
+  z = B.inner_lo[2] + idx / in1;
+}
+
+__global__ void k_fill_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long slot_len, int mb,
+                              int me, const int* __restrict__ nei_slot)
+{
+  const int nb = B.n2 + B.n1 + B.n0;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_m = me - mb;
-  if (idx >= (size_t)G.n_patches * n_m * G.fld_len) {
+  if (idx >= (size_t)G.n_patches * n_m * nb) {
     return;
   }
-  Idx3 a = decode_full(G, idx, n_m);
+  int x, y, z;
+  band_decode(B, (int)(idx % nb), x, y, z);
+  idx /= nb;
+  int m = mb + (int)(idx % n_m);
+  int p = (int)(idx / n_m);
+  int i = x - G.ibn[0], j = y - G.ibn[1], k = z - G.ibn[2];
   int dir[3];
-  dir[0] = a.i < 0 ? -1 : (a.i >= G.ldims[0] ? 1 : 0);
-  dir[1] = a.j < 0 ? -1 : (a.j >= G.ldims[1] ? 1 : 0);
-  dir[2] = a.k < 0 ? -1 : (a.k >= G.ldims[2] ? 1 : 0);
-  if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) {
-    return;
-  }
-  int slot = nei_slot[a.p * 27 + pm::dir2idx(dir)];
+  dir[0] = i < 0 ? -1 : (i >= G.ldims[0] ? 1 : 0);
+  dir[1] = j < 0 ? -1 : (j >= G.ldims[1] ? 1 : 0);
+  dir[2] = k < 0 ? -1 : (k >= G.ldims[2] ? 1 : 0);
+  int slot = nei_slot[p * 27 + pm::dir2idx(dir)];
   if (slot < 0) {
     return;
   }
-  int m = mb + a.m;
-  F[a.p * slot_len + fld_off(G, m, a.i, a.j, a.k)] =
-    F[slot * slot_len + fld_off(G, m, a.i - dir[0] * G.ldims[0], a.j - dir[1] * G.ldims[1],
-                                a.k - dir[2] * G.ldims[2])];
+  F[p * slot_len + fld_off(G, m, i, j, k)] =
+    F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
+                                k - dir[2] * G.ldims[2])];
 }
 
-__global__ void k_add_ghosts(GridDev G, float* __restrict__ F, long slot_len, int mb, int me,
-                             const int* __restrict__ nei_slot,
+__global__ void k_add_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long slot_len, int mb,
+                             int me, const int* __restrict__ nei_slot,
                              const int8_t* __restrict__ add_order)
 {
+  const int nb = B.n2 + B.n1 + B.n0;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int n_m = me - mb;
-  if (idx >= (size_t)G.n_patches * n_m * G.n_cells) {
+  if (idx >= (size_t)G.n_patches * n_m * nb) {
     return;
   }
-  int i = (int)(idx % G.ldims[0]);
-  idx /= G.ldims[0];
-  int j = (int)(idx % G.ldims[1]);
-  idx /= G.ldims[1];
-  int k = (int)(idx % G.ldims[2]);
-  idx /= G.ldims[2];
+  int i, j, k;
+  band_decode(B, (int)(idx % nb), i, j, k);
+  idx /= nb;
   int m = mb + (int)(idx % n_m);
   int p = (int)(idx / n_m);
   int c[3] = {i, j, k};
-  bool lo[3], hi[3], any = false;
+  bool lo[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     lo[d] = c[d] < G.ibn[d];
     hi[d] = c[d] >= G.ldims[d] - G.ibn[d] && G.ibn[d] > 0;
-    any = any || lo[d] || hi[d];
-  }
-  if (!any) {
-    return;
   }
   float* dst = F + p * slot_len + fld_off(G, m, i, j, k);
   float acc = *dst;
@@ -656,10 +722,14 @@ int bnd_fill_ghosts(Ctx* c, int id, int mb, int me)
   if (c->comm) {
     PSC_TRY(comm_halo_exchange(c, id, mb, me, false));
   }
-  size_t n = (size_t)c->gd.n_patches * (me - mb) * c->gd.fld_len;
+  BandGeom B = make_band(c->g, true);
+  size_t n = (size_t)c->gd.n_patches * (me - mb) * (B.n2 + B.n1 + B.n0);
+  if (n == 0) {
+    return 0;
+  }
   KernelScope ks(c, "fill_ghosts");
-  k_fill_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(id), c->fld_slot_len(id), mb,
-                                                      me, c->d_nei_slot);
+  k_fill_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id),
+                                                      mb, me, c->d_nei_slot);
   c->n_launches++;
   return check_launch(c, "fill_ghosts");
 }
@@ -670,9 +740,13 @@ int bnd_add_ghosts(Ctx* c, int id, int mb, int me)
   if (c->comm) {
     PSC_TRY(comm_halo_exchange(c, id, mb, me, true));
   }
-  size_t n = (size_t)c->gd.n_patches * (me - mb) * c->gd.n_cells;
+  BandGeom B = make_band(c->g, false);
+  size_t n = (size_t)c->gd.n_patches * (me - mb) * (B.n2 + B.n1 + B.n0);
+  if (n == 0) {
+    return 0;
+  }
   KernelScope ks(c, "add_ghosts");
-  k_add_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(id), c->fld_slot_len(id), mb,
+  k_add_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id), mb,
                                                      me, c->d_nei_slot, c->d_add_order);
   c->n_launches++;
   return check_launch(c, "add_ghosts");

@@ -1,0 +1,338 @@
+// psc_b200: fused particle boundary exchange + counting sort (the fast path of step()).
+//
+// Precondition: the store was ordered by (patch, cell) before push_mprts ran, and
+// cell_off still describes those pre-push cell runs.  Every particle then sits in the
+// run of its *source* cell s and has moved by at most one cell per direction, so its
+// target cell differs from s by an offset delta in {-1,0,1}^3 (27 classes), possibly
+// through a patch boundary (wrap / neighbour patch / reflection).
+//
+// The reference result we must reproduce is BndParticles (bnd_particles_impl.hxx:93-218,
+// ddc_particles.hxx:421-468) followed by SortCountsort2 (psc_sort_impl.hxx:65-124):
+// inside a target cell the particles are ordered
+//     [stayers of the patch | arrivals by the receiver's direction loop], each block in
+//     the sender's original order = (source cell ascending, index ascending).
+// Three kernels and one scan produce exactly that order with no key array and a single
+// read+write of the particle data:
+//   k_fs_count    one warp per source cell: classify every particle (pm::bnd_classify
+//                 arithmetic), count per delta class -> cnt[class][cell]
+//   k_fs_offsets  one thread per target cell: walk its <= 27 (route, source cell)
+//                 contributions in the reference order, turn cnt into the offset of
+//                 each (source cell, delta) group inside the target cell, emit the
+//                 target cell's population
+//   scan          new cell offsets (these are next step's cell_off and patch offsets)
+//   k_fs_scatter  one warp per source cell: re-classify, rank inside the (cell, delta)
+//                 group by ballot, write the particle (with the boundary fix-ups) to
+//                 new_cell_off[target] + group offset + rank
+// If any particle breaks the precondition (moved more than one cell, leaves for another
+// rank) a flag is raised and the caller falls back to bnd_particles() + sort_mprts();
+// the source store is never modified here.
+#include "fs_classify.cuh"
+
+#include <algorithm>
+
+namespace psc_b200
+{
+
+namespace
+{
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int FS_WARPS = 8;
+constexpr int FS_CELLS = 32; // source cells per CTA
+
+// One CTA = FS_CELLS consecutive source cells, each warp takes FS_CELLS / FS_WARPS of
+// them.  Counters are staged in shared memory and written as planes cnt[class][cell] so
+// that k_fs_offsets (one thread per target cell) reads and rewrites them coalesced.
+__global__ void __launch_bounds__(FS_WARPS * 32)
+  k_fs_count(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
+             const float4* __restrict__ xi4, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags)
+{
+  __shared__ uint32_t cnt_s[FS_CELLS][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t g0 = blockIdx.x * FS_CELLS;
+  for (int k = 0; k < FS_CELLS / FS_WARPS; k++) {
+    const int cl = warp * (FS_CELLS / FS_WARPS) + k;
+    const uint32_t g = g0 + cl;
+    uint32_t mycount = 0;
+    if (g < nct) {
+      const int p = g / G.n_cells;
+      const int s = g - p * G.n_cells;
+      const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1],
+                s2 = s / (G.ldims[0] * G.ldims[1]);
+      const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+      for (uint32_t base = begin; base < end; base += 32) {
+        uint32_t i = base + lane;
+        bool act = i < end;
+        int cls = CLS_NONE;
+        if (act) {
+          float4 X = xi4[i];
+          float x[3] = {X.x, X.y, X.z}, u[3] = {0.f, 0.f, 0.f};
+          int q, c;
+          cls = fs_classify(G, T, p, s0, s1, s2, x, u, q, c);
+        }
+        unsigned rem = __ballot_sync(FULL, act);
+        unsigned grp = __ballot_sync(FULL, cls == CLS_CENTER);
+        if (lane == CLS_CENTER) {
+          mycount += __popc(grp);
+        }
+        rem &= ~grp;
+        while (rem) {
+          int v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
+          grp = __ballot_sync(FULL, cls == v);
+          if (lane == v) {
+            mycount += __popc(grp);
+          }
+          rem &= ~grp;
+        }
+      }
+      if (mycount) {
+        if (lane == CLS_BAD) {
+          atomicExch(&flags[0], 1u);
+        } else if (lane == CLS_DROP) {
+          atomicAdd(&flags[1], mycount);
+        }
+      }
+    }
+    cnt_s[cl][lane] = mycount;
+  }
+  __syncthreads();
+  if (g0 + lane < nct) {
+    for (int plane = warp; plane < 27; plane += FS_WARPS) {
+      cnt[(size_t)plane * nct + g0 + lane] = cnt_s[lane][plane];
+    }
+  }
+}
+
+// contributions of one route (travel direction t, sender patch ps) to target cell c, in
+// ascending source-cell order = descending delta.  All counters are loaded before the
+// first one is rewritten, so the (up to 27) loads are in flight together instead of
+// forming a load -> store -> load chain (the array is updated in place).
+__device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_t* __restrict__ cnt,
+                                         int ps, int c0, int c1, int c2, int t0, int t1, int t2,
+                                         uint32_t& total)
+{
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  const size_t pbase = (size_t)ps * G.n_cells;
+  uint32_t n[27];
+  unsigned ok = 0;
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    // k ascending = delta descending
+    const int e2 = 1 - k / 9, e1 = 1 - (k / 3) % 3, e0 = 1 - k % 3;
+    int z = c2 - e2 + t2 * ld2, y = c1 - e1 + t1 * ld1, x = c0 - e0 + t0 * ld0;
+    bool v = !(t2 != 0 && e2 != t2) && (unsigned)z < (unsigned)ld2 && !(t1 != 0 && e1 != t1) &&
+             (unsigned)y < (unsigned)ld1 && !(t0 != 0 && e0 != t0) && (unsigned)x < (unsigned)ld0;
+    n[k] = 0;
+    if (v) {
+      ok |= 1u << k;
+      n[k] = cnt[(size_t)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct + pbase +
+                 (size_t)((z * ld1 + y) * ld0 + x)];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    const int e2 = 1 - k / 9, e1 = 1 - (k / 3) % 3, e0 = 1 - k % 3;
+    if ((ok >> k) & 1) {
+      int z = c2 - e2 + t2 * ld2, y = c1 - e1 + t1 * ld1, x = c0 - e0 + t0 * ld0;
+      cnt[(size_t)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct + pbase +
+          (size_t)((z * ld1 + y) * ld0 + x)] = total;
+      total += n[k];
+    }
+  }
+}
+
+// per target cell: offsets of its contributions in the reference's order; cnt is
+// rewritten in place (every (source cell, delta) entry has exactly one target).
+// Class order: stayers first, then the receiver's direction loop dir' ascending; the
+// sender sits in direction dir' from q and travelled in direction t = -dir'.  A particle
+// that crossed the lower (upper) patch face lands in the first (last) cell, so only
+// cells on a patch face have routes other than "stay".
+__global__ void k_fs_offsets(GridDev G, const int* __restrict__ nei_patch, uint32_t nct,
+                             uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
+{
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nct) {
+    return;
+  }
+  const int q = g / G.n_cells;
+  const int c = g - q * G.n_cells;
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  const int c0 = c % ld0, c1 = (c / ld0) % ld1, c2 = c / (ld0 * ld1);
+  uint32_t total = 0;
+  fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
+  const bool lo0 = c0 == 0, hi0 = c0 == ld0 - 1, lo1 = c1 == 0, hi1 = c1 == ld1 - 1, lo2 = c2 == 0,
+             hi2 = c2 == ld2 - 1;
+  if (lo0 | hi0 | lo1 | hi1 | lo2 | hi2) {
+    // dir' ascending <=> t descending, z slowest
+    for (int t2 = 1; t2 >= -1; t2--) {
+      if ((t2 == 1 && !lo2) || (t2 == -1 && !hi2)) {
+        continue;
+      }
+      for (int t1 = 1; t1 >= -1; t1--) {
+        if ((t1 == 1 && !lo1) || (t1 == -1 && !hi1)) {
+          continue;
+        }
+        for (int t0 = 1; t0 >= -1; t0--) {
+          if ((t0 == 1 && !lo0) || (t0 == -1 && !hi0) || (t0 == 0 && t1 == 0 && t2 == 0)) {
+            continue;
+          }
+          int dip = ((-t2 + 1) * 3 + (-t1 + 1)) * 3 + (-t0 + 1);
+          int ps = nei_patch[q * 27 + dip];
+          if (ps >= 0) {
+            fs_route(G, nct, cnt, ps, c0, c1, c2, t0, t1, t2, total);
+          }
+        }
+      }
+    }
+  }
+  new_cnt[g] = total;
+}
+
+__global__ void __launch_bounds__(FS_WARPS * 32)
+  k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
+               const uint32_t* __restrict__ new_cell_off, const uint32_t* __restrict__ pre,
+               const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
+               float4* __restrict__ xo, float4* __restrict__ po)
+{
+  __shared__ uint32_t pre_s[FS_CELLS][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t g0 = blockIdx.x * FS_CELLS;
+  for (int plane = warp; plane < 32; plane += FS_WARPS) {
+    pre_s[lane][plane] = (plane < 27 && g0 + lane < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + lane]) : 0u;
+  }
+  __syncthreads();
+  for (int k = 0; k < FS_CELLS / FS_WARPS; k++) {
+    const int cl = warp * (FS_CELLS / FS_WARPS) + k;
+    const uint32_t g = g0 + cl;
+    if (g >= nct) {
+      break;
+    }
+    const int p = g / G.n_cells;
+    const int s = g - p * G.n_cells;
+    const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+    const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+    // lane k carries the running offset of class k inside its target cell
+    uint32_t run = pre_s[cl][lane];
+    for (uint32_t base = begin; base < end; base += 32) {
+      uint32_t i = base + lane;
+      bool act = i < end;
+      int cls = CLS_NONE;
+      float4 X, U;
+      uint32_t tbase = 0;
+      if (act) {
+        X = xi4[i];
+        U = pxi4[i];
+        float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
+        int q = 0, c = 0;
+        cls = fs_classify(G, T, p, s0, s1, s2, x, u, q, c);
+        if (cls < 27) {
+          tbase = __ldg(&new_cell_off[(size_t)q * G.n_cells + c]);
+          X = make_float4(x[0], x[1], x[2], X.w);
+          U = make_float4(u[0], u[1], u[2], U.w);
+        }
+      }
+      unsigned rem = __ballot_sync(FULL, act);
+      uint32_t dst = 0;
+      int v = CLS_CENTER;
+      for (;;) {
+        unsigned grp = __ballot_sync(FULL, cls == v);
+        uint32_t r0 = __shfl_sync(FULL, run, v);
+        if (cls == v) {
+          dst = tbase + r0 + __popc(grp & lt);
+        }
+        if (lane == v) {
+          run += __popc(grp);
+        }
+        rem &= ~grp;
+        if (!rem) {
+          break;
+        }
+        v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
+      }
+      if (act && cls < 27) {
+        xo[dst] = X;
+        po[dst] = U;
+      }
+    }
+  }
+}
+
+__global__ void k_patch_offsets(const uint32_t* __restrict__ cell_off, int n_patches, int n_cells,
+                                uint32_t* __restrict__ off)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p <= n_patches) {
+    off[p] = cell_off[(size_t)p * n_cells];
+  }
+}
+
+} // namespace
+
+int fused_bnd_sort(Ctx* c)
+{
+  const GridDev& G = c->gd;
+  if (!c->pushed_from_sorted || c->comm) {
+    PSC_TRY(bnd_particles(c));
+    return sort_mprts(c);
+  }
+  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+  const int np = G.n_patches;
+  PSC_TRY(c->scr[9].reserve((size_t)nct * 27 * sizeof(uint32_t)));
+  PSC_TRY(c->scr[10].reserve(((size_t)nct + 1) * sizeof(uint32_t)));
+  PSC_TRY(c->scr[11].reserve((np + 1 + 4) * sizeof(uint32_t)));
+  uint32_t* cnt = c->scr[9].as<uint32_t>();
+  uint32_t* new_cnt = c->scr[10].as<uint32_t>();
+  uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, n_drop, -, -, new patch offsets...]
+  uint32_t* d_new_off = flags + 4;
+  FsTables T{c->d_patch_bnd, c->d_nei_patch};
+  if (!c->counts_valid) { // else: the push kernel already filled cnt and flags
+    PSC_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), c->stream));
+    KernelScope ks(c, "fsort_count");
+    k_fs_count<<<div_up(nct, FS_CELLS), FS_WARPS * 32, 0, c->stream>>>(G, T, nct, c->d_cell_off,
+                                                                      c->xi(), cnt, flags);
+    c->n_launches++;
+  }
+  c->counts_valid = false;
+  {
+    KernelScope ks(c, "fsort_offsets");
+    k_fs_offsets<<<div_up(nct, 128), 128, 0, c->stream>>>(G, c->d_nei_patch, nct, cnt, new_cnt);
+  }
+  {
+    KernelScope ks(c, "fsort_scan");
+    PSC_TRY(scan_exclusive<uint32_t>(c, LoadArr<uint32_t>{new_cnt}, nct, c->d_cell_off_alt, c->scr[2]));
+  }
+  {
+    KernelScope ks(c, "fsort_scatter");
+    k_fs_scatter<<<div_up(nct, FS_CELLS), FS_WARPS * 32, 0, c->stream>>>(
+      G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt());
+    k_patch_offsets<<<div_up(np + 1, 128), 128, 0, c->stream>>>(c->d_cell_off_alt, np, G.n_cells,
+                                                               d_new_off);
+  }
+  c->n_launches += 3 + 4; // + scan
+  std::vector<uint32_t> h(np + 1 + 4);
+  PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                               c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  PSC_TRY(check_launch(c, "fused_bnd_sort"));
+  if (h[0]) {
+    // precondition broken for some particle: the source store is intact, take the
+    // general path
+    c->n_fused_fallback++;
+    PSC_TRY(bnd_particles(c));
+    return sort_mprts(c);
+  }
+  c->cur ^= 1;
+  std::swap(c->d_cell_off, c->d_cell_off_alt);
+  for (int p = 0; p <= np; p++) {
+    c->h_off[p] = h[4 + p];
+  }
+  c->n_prts = c->h_off[np];
+  c->n_dropped += h[1];
+  c->sorted = true;
+  c->pushed_from_sorted = false;
+  c->n_fused++;
+  return prts_upload_off(c);
+}
+
+} // namespace psc_b200

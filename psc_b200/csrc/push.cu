@@ -5,20 +5,26 @@
 // with Current1vbVar1 (yz) / Current1vbSplit (xyz, yz); the per-particle arithmetic is
 // pic_math.cuh.  How (ours, not PSC's cuda_push_mprts_yz.cxx):
 //
-//  k_push_tiled   the store is ordered by (patch, cell).  One CTA owns a tile of cells
-//                 of one patch; it stages the E/B tile (+1 node halo, +1 guard) into
-//                 shared memory -- with cp.async.bulk (TMA bulk copies, one per
-//                 contiguous x-row, completion on an mbarrier) or plain LDG/STS --,
-//                 keeps a J tile of the same shape in shared memory, and walks the
-//                 tile's particle runs warp by warp with 128-bit loads/stores.
-//                 Deposits of the first trajectory segment are pre-reduced across the
-//                 warp: lanes are grouped by target cell (sorted particles => 1-2
-//                 groups per warp) and each group's 8/12 values are summed with a
-//                 transposing shuffle butterfly (9/16 SHFL instead of 40/60), then a
-//                 few lanes issue one shared-memory atomic each.  Extra segments of
-//                 cell-crossing particles (a few %) use per-lane shared atomics.  The
-//                 tile (halo included) is flushed with global red.add, so no
-//                 checkerboard passes are needed.
+//  k_push_tiled   the store is ordered by (patch, cell).  One CTA owns a tile of cells of
+//                 one patch (8x8x8 in 3D, 16x16 in yz; compile-time geometry whenever the
+//                 patch is a multiple of it).  It stages the E/B tile (+halo) into shared
+//                 memory with cp.async.bulk (TMA bulk copies, one per contiguous row,
+//                 completion on an mbarrier) -- or LDG/STS for odd geometries --, keeps a
+//                 J tile of the same shape in shared memory, and walks the tile's particle
+//                 runs warp by warp with 128-bit loads/stores, the next chunk prefetched
+//                 while the current one is computed.
+//                   * particles that stay in their cell (one trajectory segment, ~95 %):
+//                     lanes are grouped by target cell (sorted store => 1-2 groups per
+//                     warp) and each group's 8/12 deposit values are summed with a
+//                     transposing shuffle butterfly (9/16 SHFL instead of 40/60); a few
+//                     lanes then issue one shared-memory atomic each
+//                   * particles that cross a cell face are parked in a per-warp shared
+//                     queue and split/deposited 32 at a time, so the divergent
+//                     Villasenor-Buneman walk runs with full warps
+//                 The J tile (halo included) is flushed with global red.add, so no
+//                 checkerboard passes are needed.  Optionally the kernel also counts, per
+//                 source cell, where its particles went (27 direction classes): the input
+//                 of the fused boundary-exchange + sort pass (fused_sort.cu).
 //  k_push_general any particle order: one thread per particle, fields through the
 //                 read-only path, J with global red.add.  Used when the store is not
 //                 sorted (same results, same particle order).
@@ -26,7 +32,7 @@
 // This file is compiled twice: -fmad=false (namespace exact: particle update is
 // bit-identical to PSC's x86-64 build, which has no FMA) and with FMA contraction
 // (namespace fast, within a few ULP).
-#include "dev_util.cuh"
+#include "fs_classify.cuh"
 
 #include <algorithm>
 
@@ -42,15 +48,46 @@ namespace PUSH_VARIANT
 {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int QCAP = 64; // crossing-particle queue entries per warp
 
-struct TileGeom
+// ---------------------------------------------------------------- tile geometry
+// f = shared tile extent in nodes, g = distance of tile node 0 below the tile origin.
+// Deposits touch cells [o-1, o+t] and their +1 neighbours, the gather nodes [o-1, o+t+1]
+// (the extra margin covers float(dx_inv) vs 1/float(dx) disagreeing by one ulp).
+
+struct GeoDyn
 {
-  int t[3];    // cells per tile edge
-  int nt[3];   // tiles per patch edge
-  int f[3];    // shared tile extent (nodes): t + 3 in non-invariant dims, 1 otherwise
-  int g[3];    // 1 in non-invariant dims (origin shift), 0 otherwise
-  int fx_pad;  // row pitch of the shared tile
-  int n_tile_nodes; // f[2]*f[1]*fx_pad
+  int t_[3], nt_[3], f_[3], g_[3];
+  __host__ __device__ int t(int d) const { return t_[d]; }
+  __host__ __device__ int nt(int d) const { return nt_[d]; }
+  __host__ __device__ int f(int d) const { return f_[d]; }
+  __host__ __device__ int g(int d) const { return g_[d]; }
+  __host__ __device__ int sy() const { return f_[0]; }
+  __host__ __device__ int sz() const { return f_[0] * f_[1]; }
+  __host__ __device__ int sm() const { return f_[0] * f_[1] * f_[2]; }
+};
+
+// compile-time geometry; the contiguous direction (x in 3D, y in yz) starts two nodes
+// below the tile origin and is four nodes longer than the tile so that every row is a
+// 16-byte aligned, 16-byte multiple bulk copy
+template <int DIM>
+struct GeoStatic
+{
+  int nt_[3];
+  static constexpr bool XYZ = DIM == pm::DIM_XYZ;
+  __host__ __device__ static constexpr int t(int d) { return XYZ ? 8 : (d == 0 ? 1 : 16); }
+  __host__ __device__ int nt(int d) const { return nt_[d]; }
+  __host__ __device__ static constexpr int f(int d)
+  {
+    return XYZ ? (d == 0 ? 12 : 11) : (d == 0 ? 1 : (d == 1 ? 20 : 19));
+  }
+  __host__ __device__ static constexpr int g(int d)
+  {
+    return XYZ ? (d == 0 ? 2 : 1) : (d == 0 ? 0 : (d == 1 ? 2 : 1));
+  }
+  __host__ __device__ static constexpr int sy() { return f(0); }
+  __host__ __device__ static constexpr int sz() { return f(0) * f(1); }
+  __host__ __device__ static constexpr int sm() { return f(0) * f(1) * f(2); }
 };
 
 // ---------------------------------------------------------------- field accessors
@@ -65,14 +102,15 @@ struct FldGlobal
   }
 };
 
+template <typename GEO>
 struct FldTile
 {
-  const float* s; // EM tile, component-major
-  int o0, o1, o2; // global index of tile node 0
-  int sy, sz, sm;
+  const float* s; // EM tile, component-major; s points at node (n0, n1, n2)
+  const GEO& geo;
+  int n0, n1, n2;
   __device__ __forceinline__ float operator()(int m, int i, int j, int k) const
   {
-    return s[(m - pm::EX) * sm + (k - o2) * sz + (j - o1) * sy + (i - o0)];
+    return s[(m - pm::EX) * geo.sm() + (k - n2) * geo.sz() + (j - n1) * geo.sy() + (i - n0)];
   }
 };
 
@@ -128,11 +166,16 @@ struct Walker<pm::DIM_YZ, pm::DEPOSIT_VAR1>
 
 // leaf value n -> (component, offset) as a linear offset for strides (sy, sz, sm)
 template <int DIM>
-__device__ __forceinline__ int leaf_lin(int n, int sy, int sz, int sm)
+__device__ __forceinline__ constexpr int leaf_lin(int n, int sy, int sz, int sm)
 {
-  int m, ox, oy, oz;
-  pm::leaf_slot<DIM>(n, m, ox, oy, oz);
-  return m * sm + oz * sz + oy * sy + ox;
+  // value order of pm::split_leaf / Var1Walker::cell_values (pic_math.cuh)
+  if (DIM == pm::DIM_XYZ) {
+    return n < 4 ? ((n >> 1) * sz + (n & 1) * sy)
+                 : (n < 8 ? (sm + ((n - 4) & 1) * sz + ((n - 4) >> 1))
+                          : (2 * sm + (((n - 8) >> 1) * sy) + ((n - 8) & 1)));
+  }
+  return n < 4 ? ((n >> 1) * sz + (n & 1) * sy)
+               : (n < 6 ? (sm + (n - 4) * sz) : (2 * sm + (n - 6) * sy));
 }
 
 template <int DIM>
@@ -153,14 +196,12 @@ __device__ __forceinline__ void leaf_to_global(const GridDev& G, float* F, const
   if (!ok) {
     return;
   }
-  long base = fld_off(G, 0, ci[0], ci[1], ci[2]);
+  float* base = F + fld_off(G, 0, ci[0], ci[1], ci[2]);
   int sy = G.im[0], sz = G.im[0] * G.im[1];
-  long sm = G.fld_len;
+  int sm = (int)G.fld_len;
 #pragma unroll
   for (int n = 0; n < NV; n++) {
-    int m, ox, oy, oz;
-    pm::leaf_slot<DIM>(n, m, ox, oy, oz);
-    atomicAdd(F + base + m * sm + oz * sz + oy * sy + ox, val[n]);
+    atomicAdd(base + leaf_lin<DIM>(n, sy, sz, sm), val[n]);
   }
 }
 
@@ -200,7 +241,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------- tiled kernel
 
 // mbarrier / bulk-copy PTX (sm_90+): one thread arms the barrier with the byte count,
-// issues one cp.async.bulk per contiguous row, everybody waits on the phase.
+// one warp issues a cp.async.bulk per contiguous row and polls the phase.
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -291,42 +332,81 @@ __device__ __forceinline__ int slot_of_lane(int lane)
   return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 }
 
-template <int DIM, int DEPOSIT, bool WARP_REDUCE, bool TMA>
-__global__ void __launch_bounds__(512)
-  k_push_tiled(GridDev G, TileGeom T, const uint32_t* __restrict__ cell_off,
-               float4* __restrict__ xi4, float4* __restrict__ pxi4, float* __restrict__ flds,
-               long slot_len)
+struct PushArgs
+{
+  const uint32_t* cell_off;
+  float4* xi4;
+  float4* pxi4;
+  float* flds;
+  long slot_len;
+  // counting hook (COUNT): cnt[class][cell] planes, flags[0] = precondition broken,
+  // flags[1] = dropped particles
+  uint32_t* cnt;
+  uint32_t* flags;
+  uint32_t nct;
+  FsTables tab;
+};
+
+// per-lane deposit of one leaf into the shared J tile (or global when outside it)
+template <int DIM, typename GEO>
+__device__ __forceinline__ void leaf_deposit(const GridDev& G, const GEO& geo, float* sJ, float* F,
+                                             int n0, int n1, int n2, const int ci[3],
+                                             const float* val)
+{
+  constexpr int NV = pm::LeafShape<DIM>::NV;
+  int r0 = ci[0] - n0, r1 = ci[1] - n1, r2 = ci[2] - n2;
+  bool in_tile = (DIM == pm::DIM_YZ || (unsigned)r0 < (unsigned)(geo.f(0) - 1)) &&
+                 (unsigned)r1 < (unsigned)(geo.f(1) - 1) && (unsigned)r2 < (unsigned)(geo.f(2) - 1);
+  if (in_tile) {
+    float* b = sJ + r2 * geo.sz() + r1 * geo.sy() + r0;
+#pragma unroll
+    for (int n = 0; n < NV; n++) {
+      atomicAdd(b + leaf_lin<DIM>(n, geo.sy(), geo.sz(), geo.sm()), val[n]);
+    }
+  } else {
+    leaf_to_global<DIM>(G, F, ci, val);
+  }
+}
+
+template <int DIM, int DEPOSIT, typename GEO, bool WARP_REDUCE, bool TMA, bool COUNT, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, PushArgs A)
 {
   constexpr int NV = pm::LeafShape<DIM>::NV;
   constexpr int NVP = (DIM == pm::DIM_XYZ) ? 16 : 8;
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
-  float* sEM = smem;                      // [6][f2][f1][fx_pad]
-  float* sJ = smem + 6 * T.n_tile_nodes;  // [3][f2][f1][fx_pad]
+  const int nodes = geo.sm();
+  float* sEM = smem;             // [6][f2][f1][f0]
+  float* sJ = smem + 6 * nodes;  // [3][f2][f1][f0]
+  float4* sQ = reinterpret_cast<float4*>(smem + ((9 * nodes + 3) & ~3)); // [warps][QCAP][2]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  const int tiles_per_patch = T.nt[0] * T.nt[1] * T.nt[2];
+  const unsigned lt = (1u << lane) - 1u;
+  const int tiles_per_patch = geo.nt(0) * geo.nt(1) * geo.nt(2);
   const int p = blockIdx.x / tiles_per_patch;
   int tt = blockIdx.x - p * tiles_per_patch;
   int o[3], e[3];
-  o[0] = (tt % T.nt[0]) * T.t[0];
-  o[1] = ((tt / T.nt[0]) % T.nt[1]) * T.t[1];
-  o[2] = (tt / (T.nt[0] * T.nt[1])) * T.t[2];
+  o[0] = (tt % geo.nt(0)) * geo.t(0);
+  o[1] = ((tt / geo.nt(0)) % geo.nt(1)) * geo.t(1);
+  o[2] = (tt / (geo.nt(0) * geo.nt(1))) * geo.t(2);
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    e[d] = min(T.t[d], G.ldims[d] - o[d]);
+    e[d] = min(geo.t(d), G.ldims[d] - o[d]);
   }
-  float* F = flds + p * slot_len;
-  const int sy = T.fx_pad, sz = T.fx_pad * T.f[1], sm = T.n_tile_nodes;
+  float* F = A.flds + p * A.slot_len;
   // global index of tile node 0
-  const int n0 = o[0] - T.g[0], n1 = o[1] - T.g[1], n2 = o[2] - T.g[2];
+  const int n0 = o[0] - geo.g(0), n1 = o[1] - geo.g(1), n2 = o[2] - geo.g(2);
 
   // ---- stage E/B, zero J
   if (TMA) {
-    // rows are contiguous in x: one bulk copy per (comp, z, y) row.  Source address and
-    // size must be 16-byte multiples: the host only selects this path when they are.
-    const int rows = 6 * T.f[2] * T.f[1];
-    const unsigned row_bytes = (unsigned)T.fx_pad * 4u;
+    // rows are contiguous in the first non-invariant direction: one bulk copy per row.
+    // The host selects this path only when every row start and size is a 16-byte multiple
+    // and lies inside the patch array.
+    constexpr bool XYZ = DIM == pm::DIM_XYZ;
+    const int row_len = XYZ ? geo.f(0) : geo.f(1);
+    const int rows_per_comp = XYZ ? geo.f(1) * geo.f(2) : geo.f(2);
+    const int rows = 6 * rows_per_comp;
+    const unsigned row_bytes = (unsigned)row_len * 4u;
     if (tid == 0) {
       mbar_init(&bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,48 +418,87 @@ __global__ void __launch_bounds__(512)
       }
       __syncwarp();
       for (int r = lane; r < rows; r += 32) {
-        int m = r / (T.f[2] * T.f[1]);
-        int rem = r - m * (T.f[2] * T.f[1]);
-        int kz = rem / T.f[1], ky = rem - kz * T.f[1];
+        int m = r / rows_per_comp;
+        int rem = r - m * rows_per_comp;
+        int kz = XYZ ? rem / geo.f(1) : rem;
+        int ky = XYZ ? rem - kz * geo.f(1) : 0;
         const float* src = F + fld_off(G, pm::EX + m, n0, n1 + ky, n2 + kz);
-        bulk_g2s(sEM + m * sm + kz * sz + ky * sy, src, row_bytes, &bar);
+        bulk_g2s(sEM + m * nodes + kz * geo.sz() + ky * geo.sy(), src, row_bytes, &bar);
       }
     }
-    for (int idx = tid; idx < 3 * T.n_tile_nodes; idx += blockDim.x) {
+    for (int idx = tid; idx < 3 * nodes; idx += blockDim.x) {
       sJ[idx] = 0.f;
     }
-    mbar_wait(&bar, 0);
+    // one warp polls the mbarrier (512 spinning threads cost 10 % of the issue slots,
+    // profiles/r01_v1_push_tiled_ncu.txt); the block barrier publishes the tile
+    if (warp == 0) {
+      mbar_wait(&bar, 0);
+    }
     __syncthreads();
   } else {
-    for (int idx = tid; idx < 6 * T.n_tile_nodes; idx += blockDim.x) {
-      int m = idx / T.n_tile_nodes;
-      int rem = idx - m * T.n_tile_nodes;
-      int kz = rem / sz;
-      rem -= kz * sz;
-      int ky = rem / sy, kx = rem - ky * sy;
+    for (int idx = tid; idx < 6 * nodes; idx += blockDim.x) {
+      int m = idx / nodes;
+      int rem = idx - m * nodes;
+      int kz = rem / geo.sz();
+      rem -= kz * geo.sz();
+      int ky = rem / geo.sy(), kx = rem - ky * geo.sy();
       int gi = n0 + kx, gj = n1 + ky, gk = n2 + kz;
       float v = 0.f;
-      if (kx < T.f[0] && gi < G.ldims[0] + G.ibn[0] && gj < G.ldims[1] + G.ibn[1] &&
-          gk < G.ldims[2] + G.ibn[2]) {
+      if (gi < G.ldims[0] + G.ibn[0] && gj < G.ldims[1] + G.ibn[1] && gk < G.ldims[2] + G.ibn[2]) {
         v = __ldg(F + fld_off(G, pm::EX + m, gi, gj, gk));
       }
       sEM[idx] = v;
     }
-    for (int idx = tid; idx < 3 * T.n_tile_nodes; idx += blockDim.x) {
+    for (int idx = tid; idx < 3 * nodes; idx += blockDim.x) {
       sJ[idx] = 0.f;
     }
     __syncthreads();
   }
 
-  FldTile EM{sEM, n0, n1, n2, sy, sz, sm};
+  FldTile<GEO> EM{sEM, geo, n0, n1, n2};
   const int my_slot = slot_of_lane<NVP>(lane);
-  const int my_lin = (my_slot < NV) ? leaf_lin<DIM>(my_slot, sy, sz, sm) : 0;
+  const int my_lin = (my_slot < NV) ? leaf_lin<DIM>(my_slot, geo.sy(), geo.sz(), geo.sm()) : 0;
   const bool writer = (my_slot < NV) && ((lane & (NVP == 16 ? 1 : 3)) == 0);
+  float4* myQ = sQ + (size_t)warp * QCAP * 2;
+  int qn = 0; // queued crossing particles of this warp (warp-uniform)
+
+  // split + deposit `cnt` queued trajectories (entries [qn - cnt, qn)), one per lane
+  auto drain = [&](int cnt) {
+    const bool a2 = lane < cnt;
+    Walker<DIM, DEPOSIT> w;
+    float val[NVP];
+    int ci[3] = {0, 0, 0};
+    bool more = false;
+    float qw = 0.f;
+    if (a2) {
+      float4 A0 = myQ[2 * (qn - cnt + lane)], A1 = myQ[2 * (qn - cnt + lane) + 1];
+      pm::Trajectory t;
+      t.xm[0] = A0.x, t.xm[1] = A0.y, t.xm[2] = A0.z;
+      t.xp[0] = A1.x, t.xp[1] = A1.y, t.xp[2] = A1.z;
+      t.v[0] = A1.w, t.v[1] = 0.f, t.v[2] = 0.f;
+      qw = A0.w;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        t.lg[d] = pm::fint(t.xm[d]);
+        t.lf[d] = pm::fint(t.xp[d]);
+      }
+      more = w.first(G.pc, t, qw, ci, val);
+      leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+    }
+    while (__any_sync(FULL, more)) {
+      if (more) {
+        more = w.next(G.pc, qw, ci, val);
+        leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+      }
+    }
+    qn -= cnt;
+    __syncwarp();
+  };
 
   // ---- particle runs: contiguous cells along the first non-invariant dim
   const int n_rows = (DIM == pm::DIM_XYZ) ? e[1] * e[2] : e[2];
   const int run_cells = (DIM == pm::DIM_XYZ) ? e[0] : e[1];
-  const uint32_t* coff = cell_off + (size_t)p * G.n_cells;
+  const uint32_t* coff = A.cell_off + (size_t)p * G.n_cells;
   for (int row = warp; row < n_rows; row += n_warps) {
     int c0;
     if (DIM == pm::DIM_XYZ) {
@@ -389,47 +508,106 @@ __global__ void __launch_bounds__(512)
       c0 = (o[2] + row) * G.ldims[1] + o[1];
     }
     const uint32_t begin = __ldg(&coff[c0]), end = __ldg(&coff[c0 + run_cells]);
+    float4 Xn = make_float4(0.f, 0.f, 0.f, 0.f), Un = Xn;
+    if (begin + lane < end) {
+      Xn = A.xi4[begin + lane];
+      Un = A.pxi4[begin + lane];
+    }
     for (uint32_t base = begin; base < end; base += 32) {
       const uint32_t i = base + lane;
       const bool act = i < end;
-      Walker<DIM, DEPOSIT> w;
+      const float4 X = Xn, U = Un;
+      if (i + 32 < end) { // prefetch the next chunk while this one is computed
+        Xn = A.xi4[i + 32];
+        Un = A.pxi4[i + 32];
+      }
+      if (qn > QCAP - 32) {
+        drain(32);
+      }
       float val[NVP];
       int ci[3] = {0, 0, 0};
-      bool more = false;
-      float qw = 0.f;
+      bool cross = false;
+      pm::Trajectory t;
+      float xo[3] = {X.x, X.y, X.z};
       if (act) {
-        float4 X = xi4[i], U = pxi4[i];
         float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
-        qw = U.w;
-        pm::Trajectory t;
         pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-        xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-        pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
-        more = w.first(G.pc, t, qw, ci, val);
+        A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+        A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+        cross = (DIM == pm::DIM_XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
+        if (!cross) {
+          // single segment: the leaf is the whole trajectory
+          Walker<DIM, DEPOSIT> w;
+          w.first(G.pc, t, U.w, ci, val);
+        }
+        if (COUNT) {
+          // source cell from the pre-push position, class from the pushed one
+          int s0 = pm::cell_position(G.pc, xo[0], 0), s1 = pm::cell_position(G.pc, xo[1], 1),
+              s2 = pm::cell_position(G.pc, xo[2], 2);
+          int q, c;
+          float uu[3] = {u[0], u[1], u[2]};
+          int cls = fs_classify(G, A.tab, p, s0, s1, s2, x, uu, q, c);
+          int s = (s2 * G.ldims[1] + s1) * G.ldims[0] + s0;
+          xo[0] = __int_as_float(s * 32 + cls); // key, reused below
+        }
       }
-      // tile-relative leaf cell; in_tile: all NV targets lie inside the shared tile
+      if (COUNT) {
+        // aggregate equal (source cell, class) keys across the warp: one red per group
+        int key = act ? __float_as_int(xo[0]) : -1;
+        unsigned rem = __ballot_sync(FULL, act);
+        while (rem) {
+          int kl = __shfl_sync(FULL, key, __ffs(rem) - 1);
+          unsigned grp = __ballot_sync(FULL, key == kl);
+          if (lane == __ffs(grp) - 1) {
+            int cls = kl & 31;
+            uint32_t n = __popc(grp);
+            if (cls < FS_PLANES) {
+              atomicAdd(&A.cnt[(size_t)cls * A.nct + (size_t)p * G.n_cells + (kl >> 5)], n);
+            } else if (cls == CLS_BAD) {
+              atomicExch(&A.flags[0], 1u);
+            } else {
+              atomicAdd(&A.flags[1], n);
+            }
+          }
+          rem &= ~grp;
+        }
+      }
+      // park cell-crossing particles
+      {
+        unsigned cm = __ballot_sync(FULL, cross);
+        if (cm) {
+          if (cross) {
+            int slot = qn + __popc(cm & lt);
+            myQ[2 * slot] = make_float4(t.xm[0], t.xm[1], t.xm[2], U.w);
+            myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], t.v[0]);
+          }
+          qn += __popc(cm);
+          __syncwarp();
+        }
+      }
+      // single-segment particles: deposit
+      const bool dep = act && !cross;
       int r0 = ci[0] - n0, r1 = ci[1] - n1, r2 = ci[2] - n2;
-      bool in_tile = (DIM == pm::DIM_YZ || (unsigned)r0 < (unsigned)(T.f[0] - 1)) &&
-                     (unsigned)r1 < (unsigned)(T.f[1] - 1) && (unsigned)r2 < (unsigned)(T.f[2] - 1);
-      int key = r2 * sz + r1 * sy + r0;
-      if (act && !in_tile) {
+      bool in_tile = (DIM == pm::DIM_YZ || (unsigned)r0 < (unsigned)(geo.f(0) - 1)) &&
+                     (unsigned)r1 < (unsigned)(geo.f(1) - 1) && (unsigned)r2 < (unsigned)(geo.f(2) - 1);
+      int key = r2 * geo.sz() + r1 * geo.sy() + r0;
+      if (dep && !in_tile) {
         leaf_to_global<DIM>(G, F, ci, val);
       }
       if (WARP_REDUCE) {
-        unsigned rem = __ballot_sync(FULL, act && in_tile);
+        unsigned rem = __ballot_sync(FULL, dep && in_tile);
         int iter = 0;
         while (rem) {
           if (iter == 2 || __popc(rem) < 4) {
             if ((rem >> lane) & 1) {
 #pragma unroll
               for (int n = 0; n < NV; n++) {
-                atomicAdd(&sJ[key + leaf_lin<DIM>(n, sy, sz, sm)], val[n]);
+                atomicAdd(&sJ[key + leaf_lin<DIM>(n, geo.sy(), geo.sz(), geo.sm())], val[n]);
               }
             }
             break;
           }
-          int leader = __ffs(rem) - 1;
-          int kl = __shfl_sync(FULL, key, leader);
+          int kl = __shfl_sync(FULL, key, __ffs(rem) - 1);
           bool mine = ((rem >> lane) & 1) && key == kl;
           unsigned grp = __ballot_sync(FULL, mine);
           float v[NVP];
@@ -445,46 +623,29 @@ __global__ void __launch_bounds__(512)
           iter++;
         }
       } else {
-        if (act && in_tile) {
+        if (dep && in_tile) {
 #pragma unroll
           for (int n = 0; n < NV; n++) {
-            atomicAdd(&sJ[key + leaf_lin<DIM>(n, sy, sz, sm)], val[n]);
-          }
-        }
-      }
-      // further segments of cell-crossing particles
-      while (__any_sync(FULL, more)) {
-        if (more) {
-          more = w.next(G.pc, qw, ci, val);
-          r0 = ci[0] - n0;
-          r1 = ci[1] - n1;
-          r2 = ci[2] - n2;
-          in_tile = (DIM == pm::DIM_YZ || (unsigned)r0 < (unsigned)(T.f[0] - 1)) &&
-                    (unsigned)r1 < (unsigned)(T.f[1] - 1) && (unsigned)r2 < (unsigned)(T.f[2] - 1);
-          if (in_tile) {
-            key = r2 * sz + r1 * sy + r0;
-#pragma unroll
-            for (int n = 0; n < NV; n++) {
-              atomicAdd(&sJ[key + leaf_lin<DIM>(n, sy, sz, sm)], val[n]);
-            }
-          } else {
-            leaf_to_global<DIM>(G, F, ci, val);
+            atomicAdd(&sJ[key + leaf_lin<DIM>(n, geo.sy(), geo.sz(), geo.sm())], val[n]);
           }
         }
       }
     }
   }
+  while (qn > 0) {
+    drain(min(qn, 32));
+  }
   __syncthreads();
 
   // ---- flush the J tile (halo included) with global reductions
-  for (int idx = tid; idx < 3 * T.n_tile_nodes; idx += blockDim.x) {
+  for (int idx = tid; idx < 3 * nodes; idx += blockDim.x) {
     float v = sJ[idx];
     if (v != 0.f) {
-      int m = idx / T.n_tile_nodes;
-      int rem = idx - m * T.n_tile_nodes;
-      int kz = rem / sz;
-      rem -= kz * sz;
-      int ky = rem / sy, kx = rem - ky * sy;
+      int m = idx / nodes;
+      int rem = idx - m * nodes;
+      int kz = rem / geo.sz();
+      rem -= kz * geo.sz();
+      int ky = rem / geo.sy(), kx = rem - ky * geo.sy();
       int gi = n0 + kx, gj = n1 + ky, gk = n2 + kz;
       if (gi < G.ldims[0] + G.ibn[0] && gj < G.ldims[1] + G.ibn[1] && gk < G.ldims[2] + G.ibn[2]) {
         atomicAdd(F + fld_off(G, m, gi, gj, gk), v);
@@ -495,36 +656,66 @@ __global__ void __launch_bounds__(512)
 
 // ---------------------------------------------------------------- host side
 
-template <int DIM, int DEPOSIT>
-static int launch_tiled(Ctx* c, const TileGeom& T, bool tma, size_t smem_bytes)
+template <int DIM, int DEPOSIT, typename GEO, bool TUNE>
+static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const PushArgs& A)
 {
   const GridDev& G = c->gd;
-  int tiles = T.nt[0] * T.nt[1] * T.nt[2] * G.n_patches;
-  float* F = c->fld(0);
-  long slot_len = c->fld_slot_len(0);
+  int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
   int threads = std::max(32, std::min(512, c->opt_threads)) & ~31;
-#define PSC_LAUNCH(WR, TM)                                                                        \
+  // register budget variants (launch bounds) of the production configuration
+  int lb = 0; // 0: (512, 2)  1: (512, 1)  2: (256, 3)  3: (256, 4)
+  if (TUNE && c->opt_warp_reduce) {
+    if (threads <= 256) {
+      lb = c->opt_min_blocks >= 4 ? 3 : 2;
+    } else {
+      lb = c->opt_min_blocks == 1 ? 1 : 0;
+    }
+  }
+  size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
+                      (size_t)(threads / 32) * QCAP * 2 * sizeof(float4);
+  if (smem_bytes > 220 * 1024) {
+    return -1;
+  }
+#define PSC_LAUNCH(WR, TM, CN, MT, MB)                                                            \
   do {                                                                                            \
-    auto kern = k_push_tiled<DIM, DEPOSIT, WR, TM>;                                               \
+    auto kern = k_push_tiled<DIM, DEPOSIT, GEO, WR, TM, CN, MT, MB>;                              \
     PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                       (int)smem_bytes));                                          \
-    kern<<<tiles, threads, smem_bytes, c->stream>>>(G, T, c->d_cell_off, c->xi(), c->pxi(), F,    \
-                                                    slot_len);                                    \
+    kern<<<tiles, threads, smem_bytes, c->stream>>>(G, geo, A);                                   \
   } while (0)
-  if (c->opt_warp_reduce) {
+#define PSC_LAUNCH_LB(WR, TM, CN)                                                                 \
+  do {                                                                                            \
+    if (TUNE && lb == 1) {                                                                        \
+      PSC_LAUNCH(WR, TM, CN, 512, 1);                                                             \
+    } else if (TUNE && lb == 2) {                                                                 \
+      PSC_LAUNCH(WR, TM, CN, 256, 3);                                                             \
+    } else if (TUNE && lb == 3) {                                                                 \
+      PSC_LAUNCH(WR, TM, CN, 256, 4);                                                             \
+    } else {                                                                                      \
+      PSC_LAUNCH(WR, TM, CN, 512, 2);                                                             \
+    }                                                                                             \
+  } while (0)
+  if (!c->opt_warp_reduce) {
     if (tma) {
-      PSC_LAUNCH(true, true);
+      PSC_LAUNCH(false, true, false, 512, 2);
     } else {
-      PSC_LAUNCH(true, false);
+      PSC_LAUNCH(false, false, false, 512, 2);
+    }
+  } else if (count) {
+    if (tma) {
+      PSC_LAUNCH_LB(true, true, true);
+    } else {
+      PSC_LAUNCH_LB(true, false, true);
     }
   } else {
     if (tma) {
-      PSC_LAUNCH(false, true);
+      PSC_LAUNCH_LB(true, true, false);
     } else {
-      PSC_LAUNCH(false, false);
+      PSC_LAUNCH_LB(true, false, false);
     }
   }
 #undef PSC_LAUNCH
+#undef PSC_LAUNCH_LB
   return 0;
 }
 
@@ -532,50 +723,67 @@ template <int DIM, int DEPOSIT>
 static int push_dim(Ctx* c)
 {
   const GridDev& G = c->gd;
+  c->counts_valid = false;
   if (c->n_prts == 0) {
     return 0;
   }
   if (c->sorted && c->opt_tiled) {
-    TileGeom T{};
-    int def[3] = {DIM == pm::DIM_XYZ ? 8 : 1, DIM == pm::DIM_XYZ ? 8 : 16, DIM == pm::DIM_XYZ ? 8 : 16};
+    PushArgs A{};
+    A.cell_off = c->d_cell_off;
+    A.xi4 = c->xi();
+    A.pxi4 = c->pxi();
+    A.flds = c->fld(0);
+    A.slot_len = c->fld_slot_len(0);
+    A.nct = (uint32_t)G.n_cells * G.n_patches;
+    A.tab = FsTables{c->d_patch_bnd, c->d_nei_patch};
+    bool count = c->want_counts && c->opt_warp_reduce && !c->comm;
+    if (count) {
+      PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(uint32_t)));
+      PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));
+      A.cnt = c->scr[9].as<uint32_t>();
+      A.flags = c->scr[11].as<uint32_t>();
+      PSC_CUDA_TRY(cudaMemsetAsync(A.cnt, 0, (size_t)A.nct * FS_PLANES * sizeof(uint32_t), c->stream));
+      PSC_CUDA_TRY(cudaMemsetAsync(A.flags, 0, 4 * sizeof(uint32_t), c->stream));
+    }
+    const bool xyz = DIM == pm::DIM_XYZ;
+    bool custom_tile = c->opt_tile[0] > 0 || c->opt_tile[1] > 0 || c->opt_tile[2] > 0;
+    GeoStatic<DIM> gs{};
+    bool stat = !custom_tile;
     for (int d = 0; d < 3; d++) {
-      bool inv = (DIM == pm::DIM_YZ && d == 0);
-      int t = c->opt_tile[d] > 0 ? c->opt_tile[d] : def[d];
-      T.t[d] = inv ? 1 : std::min(t, G.ldims[d]);
-      T.nt[d] = (G.ldims[d] + T.t[d] - 1) / T.t[d];
-      T.f[d] = inv ? 1 : T.t[d] + 3;
-      T.g[d] = inv ? 0 : 1;
+      bool inv = (!xyz && d == 0);
+      gs.nt_[d] = inv ? 1 : G.ldims[d] / gs.t(d);
+      stat = stat && (inv || (G.ibn[d] == 2 && G.ldims[d] % gs.t(d) == 0));
     }
-    // TMA rows: the contiguous dim is x (xyz) -- pad the pitch to 4 floats; the row
-    // start o-1+ibn = o+1 has to be a multiple of 4 floats as well, which no tile
-    // origin satisfies in general => the bulk-copy path is taken only when every
-    // row start is 16-byte aligned (checked here), else LDG/STS staging.
-    T.fx_pad = T.f[0];
-    bool tma = false;
-    if (c->opt_tma && DIM == pm::DIM_XYZ && G.ibn[0] == 2) {
-      // bulk copies need 16-byte aligned row starts and sizes: start the shared tile
-      // two nodes left of the tile origin (row start = o + ibn - 2 = o floats into the
-      // row) and round the pitch up to 4 floats
-      int pitch = (T.t[0] + 4 + 3) & ~3;
-      bool ok = (G.im[0] % 4 == 0) && (T.t[0] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0);
-      // all rows of the padded tile must stay inside the patch array
-      ok = ok && ((T.nt[0] - 1) * T.t[0] + pitch <= G.im[0]) &&
-           ((T.nt[1] - 1) * T.t[1] - 1 + G.ibn[1] + T.f[1] <= G.im[1]) &&
-           ((T.nt[2] - 1) * T.t[2] - 1 + G.ibn[2] + T.f[2] <= G.im[2]);
-      if (ok) {
-        tma = true;
-        T.g[0] = 2;
-        T.f[0] = pitch;
-        T.fx_pad = pitch;
-      }
-    }
-    T.n_tile_nodes = T.f[2] * T.f[1] * T.fx_pad;
-    size_t smem_bytes = (size_t)9 * T.n_tile_nodes * sizeof(float);
-    if (smem_bytes <= 200 * 1024) {
+    int rc = -1;
+    if (stat) {
+      // bulk copies: contiguous rows (x in 3D, y in yz) must be 16-byte aligned
+      int cd = xyz ? 0 : 1;
+      bool tma = c->opt_tma && (G.im[cd] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0) &&
+                 (G.fld_len % 4 == 0);
       KernelScope ks(c, tma ? "push_tiled_tma" : "push_tiled");
-      PSC_TRY((launch_tiled<DIM, DEPOSIT>(c, T, tma, smem_bytes)));
+      rc = launch_tiled<DIM, DEPOSIT, GeoStatic<DIM>, true>(c, gs, tma, count, A);
+    }
+    if (rc == -1) {
+      GeoDyn gd{};
+      int def[3] = {xyz ? 8 : 1, xyz ? 8 : 16, xyz ? 8 : 16};
+      for (int d = 0; d < 3; d++) {
+        bool inv = (!xyz && d == 0);
+        int t = c->opt_tile[d] > 0 ? c->opt_tile[d] : def[d];
+        gd.t_[d] = inv ? 1 : std::min(t, G.ldims[d]);
+        gd.nt_[d] = (G.ldims[d] + gd.t_[d] - 1) / gd.t_[d];
+        gd.f_[d] = inv ? 1 : gd.t_[d] + 3;
+        gd.g_[d] = inv ? 0 : 1;
+      }
+      KernelScope ks(c, "push_tiled_dyn");
+      rc = launch_tiled<DIM, DEPOSIT, GeoDyn, false>(c, gd, false, count, A);
+    }
+    if (rc == 0) {
       c->n_launches++;
+      c->counts_valid = count;
       return check_launch(c, "push_tiled");
+    }
+    if (rc > 0) {
+      return rc;
     }
   }
   {
@@ -606,6 +814,7 @@ int PUSH_CAT(push_mprts_, PUSH_VARIANT)(Ctx* c)
   // (the fused boundary+sort pass of step() picks the store up from here)
   c->pushed_from_sorted = c->sorted && rc == 0;
   c->sorted = false;
+  c->want_counts = false;
   return rc;
 }
 

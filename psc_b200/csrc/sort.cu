@@ -231,13 +231,4 @@ int sort_mprts(Ctx* c)
   return 0;
 }
 
-// boundary exchange + sort of a store that was cell-ordered before the push
-int fused_bnd_sort(Ctx* c)
-{
-  PSC_TRY(bnd_particles(c));
-  PSC_TRY(sort_mprts(c));
-  c->n_fused++;
-  return 0;
-}
-
 } // namespace psc_b200
