@@ -22,11 +22,6 @@
 namespace psc_b200
 {
 
-int comm_exchange_particles(Ctx* c, const float4* xi_src, const float4* pxi_src,
-                            const uint32_t* d_src_idx, const uint32_t* d_keys, uint32_t n_remote,
-                            uint32_t key_remote_base, std::vector<uint32_t>& n_recv_by_patch,
-                            float4** xi_recv, float4** pxi_recv);
-
 namespace
 {
 
@@ -267,7 +262,7 @@ int bnd_particles(Ctx* c)
   if (multi) {
     PSC_TRY(comm_exchange_particles(c, c->xi(), c->pxi(), l_src ? l_src + n_local_arr : nullptr,
                                     l_key ? l_key + n_local_arr : nullptr, n_remote,
-                                    key_remote_base, n_recv, &xi_recv, &pxi_recv));
+                                    key_remote_base, false, n_recv, &xi_recv, &pxi_recv));
   }
 
   std::vector<uint32_t> new_off(np + 1, 0), arr_base(np, 0);

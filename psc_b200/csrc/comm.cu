@@ -437,15 +437,31 @@ int comm_allreduce_sum(Ctx* c, double* v, int n)
 namespace
 {
 
-__global__ void k_pack_prts(uint32_t n, const uint32_t* __restrict__ src_idx,
+// gather the leaving particles into {xi4, pxi4} records; with `fixup` the boundary
+// arithmetic (bnd_particles_impl.hxx:93-218) is applied here because the source store
+// still holds the raw pushed positions
+__global__ void k_pack_prts(GridDev G, uint32_t n, const uint32_t* __restrict__ src_idx,
+                            const uint32_t* __restrict__ keys, uint32_t key_remote_base,
+                            const pm::PatchBnd* __restrict__ pbs, bool fixup,
                             const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
                             float4* __restrict__ out)
 {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) {
     uint32_t i = src_idx[j];
-    out[2 * (size_t)j] = xi4[i];
-    out[2 * (size_t)j + 1] = pxi4[i];
+    float4 X = xi4[i], U = pxi4[i];
+    if (fixup) {
+      int p = ((keys[j] - key_remote_base) >> 5) % G.n_patches;
+      float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
+      int dir[3];
+      bool drop;
+      pm::PatchBnd pb = pbs[p];
+      pm::bnd_classify(G.pc, pb, x, u, dir, drop);
+      X = make_float4(x[0], x[1], x[2], X.w);
+      U = make_float4(u[0], u[1], u[2], U.w);
+    }
+    out[2 * (size_t)j] = X;
+    out[2 * (size_t)j + 1] = U;
   }
 }
 
@@ -476,8 +492,9 @@ __global__ void k_unpack_prts(const Seg* __restrict__ segs, int n_segs, const fl
 // patch, sender direction) -- ddc_particles.hxx:456-468 -- and the count per patch.
 int comm_exchange_particles(Ctx* c, const float4* xi_src, const float4* pxi_src,
                             const uint32_t* d_src_idx, const uint32_t* d_keys, uint32_t n_remote,
-                            uint32_t key_remote_base, std::vector<uint32_t>& n_recv_by_patch,
-                            float4** xi_recv, float4** pxi_recv)
+                            uint32_t key_remote_base, bool fixup,
+                            std::vector<uint32_t>& n_recv_by_patch, float4** xi_recv,
+                            float4** pxi_recv)
 {
   Comm* cm = c->comm;
   const GridHost& g = c->g;
@@ -587,8 +604,9 @@ int comm_exchange_particles(Ctx* c, const float4* xi_src, const float4* pxi_src,
   PSC_TRY(cm->prt_send.reserve(std::max<size_t>(n_remote, 1) * 32));
   PSC_TRY(cm->prt_recv.reserve(std::max<size_t>(n_recv, 1) * 32));
   if (n_remote) {
-    k_pack_prts<<<div_up(n_remote, 256), 256, 0, c->stream>>>(n_remote, d_src_idx, xi_src, pxi_src,
-                                                             cm->prt_send.as<float4>());
+    k_pack_prts<<<div_up(n_remote, 256), 256, 0, c->stream>>>(
+      c->gd, n_remote, d_src_idx, d_keys, key_remote_base, c->d_patch_bnd, fixup, xi_src, pxi_src,
+      cm->prt_send.as<float4>());
     c->n_launches++;
   }
   PSC_NCCL_TRY(g_nccl.GroupStart());

@@ -95,8 +95,8 @@ struct Ctx
   int opt_warp_reduce = 1; // warp-level pre-reduction of deposits in the tiled push
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with cp.async.bulk (TMA) instead of LDG/STS
-  int opt_threads = 512;   // CTA size of the tiled push
-  int opt_min_blocks = 2;  // resident CTAs per SM the tiled push is compiled for
+  int opt_threads = 256;   // CTA size of the tiled push
+  int opt_min_blocks = 3;  // resident CTAs per SM the tiled push is compiled for
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
@@ -150,6 +150,9 @@ struct Ctx
 
   // ---- multi-GPU
   Comm* comm = nullptr;
+  DevBuf rf_cells;      // cells from which particles can leave for another rank
+  uint32_t n_rf_cells = 0;
+  bool rf_built = false;
 
   float4* xi() { return xi4[cur]; }
   float4* pxi() { return pxi4[cur]; }
@@ -216,6 +219,13 @@ int comm_unique_id(void* id128);
 int comm_init(Ctx* c, const void* id128);
 void comm_destroy(Ctx* c);
 int comm_halo_exchange(Ctx* c, int id, int mb, int me, bool add);
+// ships particles leaving for other ranks; `fixup`: apply the boundary fix-ups while
+// packing (the fused pass leaves the source store untouched)
+int comm_exchange_particles(Ctx* c, const float4* xi_src, const float4* pxi_src,
+                            const uint32_t* d_src_idx, const uint32_t* d_keys, uint32_t n_remote,
+                            uint32_t key_remote_base, bool fixup,
+                            std::vector<uint32_t>& n_recv_by_patch, float4** xi_recv,
+                            float4** pxi_recv);
 int comm_allreduce_max(Ctx* c, double* v, int n);
 int comm_allreduce_sum(Ctx* c, double* v, int n);
 

@@ -9,7 +9,7 @@
 namespace psc_b200
 {
 
-constexpr int CLS_CENTER = 13, CLS_DROP = 27, CLS_BAD = 28, CLS_NONE = 31;
+constexpr int CLS_CENTER = 13, CLS_DROP = 27, CLS_BAD = 28, CLS_REMOTE = 29, CLS_NONE = 31;
 constexpr int FS_PLANES = 27; // cnt[class][cell], class = ((dz+1)*3 + dy+1)*3 + dx+1
 
 struct FsTables
@@ -19,7 +19,8 @@ struct FsTables
 };
 
 // class of a pushed particle that started in cell (s0,s1,s2) of patch p; on return x/u
-// carry the boundary fix-ups, (q, c) is the target patch and cell
+// carry the boundary fix-ups, (q, c) is the target patch and cell (for CLS_REMOTE:
+// q = -2 - rank, c = direction index)
 __device__ __forceinline__ int fs_classify(const GridDev& G, const FsTables& T, int p, int s0, int s1,
                                            int s2, float x[3], float u[3], int& q, int& c)
 {
@@ -45,7 +46,10 @@ __device__ __forceinline__ int fs_classify(const GridDev& G, const FsTables& T, 
         return CLS_DROP;
       }
       if (nq < 0) {
-        return CLS_BAD; // other rank: general path
+        // leaves for rank -2 - nq: shipped by the NCCL exchange (q = nq, c = direction)
+        q = nq;
+        c = pm::dir2idx(dir);
+        return CLS_REMOTE;
       }
       q = nq;
     }

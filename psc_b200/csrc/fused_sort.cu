@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
           atomicExch(&flags[0], 1u);
         } else if (lane == CLS_DROP) {
           atomicAdd(&flags[1], mycount);
+        } else if (lane == CLS_REMOTE) {
+          atomicAdd(&flags[2], mycount);
         }
       }
     }
@@ -267,23 +269,173 @@ __global__ void k_patch_offsets(const uint32_t* __restrict__ cell_off, int n_pat
   }
 }
 
+// ---- multi-rank: particles leaving for another rank (CLS_REMOTE) can only start in
+// cells on a patch face that touches a remote patch.  One warp per such cell appends
+// them to a list (group key = (rank * n_patches + patch) * 32 + direction, index); the
+// list is then sorted by (group, index) = the reference's send order
+// (ddc_particles.hxx:360-409).
+__global__ void __launch_bounds__(FS_WARPS * 32)
+  k_fs_collect_remote(GridDev G, FsTables T, uint32_t n_rf, const uint32_t* __restrict__ rf_cells,
+                      const uint32_t* __restrict__ cell_off, const float4* __restrict__ xi4,
+                      uint32_t* __restrict__ rkey, uint32_t* __restrict__ ridx,
+                      uint32_t* __restrict__ counter, uint32_t cap)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t w = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
+  if (w >= n_rf) {
+    return;
+  }
+  const uint32_t g = rf_cells[w];
+  const int p = g / G.n_cells;
+  const int s = g - p * G.n_cells;
+  const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+  const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+  for (uint32_t base = begin; base < end; base += 32) {
+    uint32_t i = base + lane;
+    bool rem = false;
+    uint32_t key = 0;
+    if (i < end) {
+      float4 X = xi4[i];
+      float x[3] = {X.x, X.y, X.z}, u[3] = {0.f, 0.f, 0.f};
+      int q, c;
+      if (fs_classify(G, T, p, s0, s1, s2, x, u, q, c) == CLS_REMOTE) {
+        rem = true;
+        key = ((uint32_t)(-2 - q) * G.n_patches + p) * 32u + (uint32_t)c;
+      }
+    }
+    unsigned m = __ballot_sync(FULL, rem);
+    if (m) {
+      uint32_t b = 0;
+      if (lane == __ffs(m) - 1) {
+        b = atomicAdd(counter, (uint32_t)__popc(m));
+      }
+      b = __shfl_sync(FULL, b, __ffs(m) - 1);
+      if (rem) {
+        uint32_t slot = b + __popc(m & lt);
+        if (slot < cap) {
+          rkey[slot] = key;
+          ridx[slot] = i;
+        }
+      }
+    }
+  }
+}
+
+// received particles: target cell key, and one more particle for that cell
+__global__ void k_fs_recv_keys(GridDev G, uint32_t n, const uint32_t* __restrict__ recv_off,
+                               const float4* __restrict__ xr, uint32_t* __restrict__ keys,
+                               uint32_t* __restrict__ new_cnt, uint32_t* __restrict__ flags)
+{
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) {
+    return;
+  }
+  int q = patch_of(recv_off, G.n_patches, j);
+  float4 X = xr[j];
+  float x[3] = {X.x, X.y, X.z};
+  int ci = pm::cell_index(G.pc, G.ldims, x);
+  if (ci < 0) {
+    atomicExch(&flags[0], 1u);
+    ci = 0;
+  }
+  uint32_t key = (uint32_t)q * G.n_cells + ci;
+  keys[j] = key;
+  atomicAdd(&new_cnt[key], 1u);
+}
+
+// received particles fill the tail of their target cell in list order
+// (ddc_particles.hxx:456-468: behind every local arrival)
+__global__ void k_fs_place_remote(uint32_t n, const uint32_t* __restrict__ skey,
+                                  const uint32_t* __restrict__ sidx,
+                                  const uint32_t* __restrict__ new_cell_off,
+                                  const float4* __restrict__ xr, const float4* __restrict__ pr,
+                                  float4* __restrict__ xo, float4* __restrict__ po)
+{
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) {
+    return;
+  }
+  uint32_t key = skey[j];
+  // first index behind this key's run
+  uint32_t lo = j, hi = n; // skey[lo] == key, skey[hi] > key (hi = n: none)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (skey[mid] == key) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  uint32_t dst = new_cell_off[key + 1] - (hi - j);
+  uint32_t r = sidx[j];
+  xo[dst] = xr[r];
+  po[dst] = pr[r];
+}
+
 } // namespace
+
+// cells from which a particle can leave for another rank
+static int build_remote_cells(Ctx* c)
+{
+  const GridHost& g = c->g;
+  std::vector<uint32_t> cells;
+  for (int p = 0; p < g.n_patches; p++) {
+    for (int di = 0; di < 27; di++) {
+      if (di == 13 || c->h_nei_patch[p * 27 + di] >= -1) {
+        continue;
+      }
+      int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+      int lo[3], hi[3];
+      for (int d = 0; d < 3; d++) {
+        lo[d] = dir[d] > 0 ? g.ldims[d] - 1 : 0;
+        hi[d] = dir[d] < 0 ? 1 : g.ldims[d];
+      }
+      for (int k = lo[2]; k < hi[2]; k++) {
+        for (int j = lo[1]; j < hi[1]; j++) {
+          for (int i = lo[0]; i < hi[0]; i++) {
+            cells.push_back((uint32_t)p * g.n_cells + (uint32_t)((k * g.ldims[1] + j) * g.ldims[0] + i));
+          }
+        }
+      }
+    }
+  }
+  std::sort(cells.begin(), cells.end());
+  cells.erase(std::unique(cells.begin(), cells.end()), cells.end());
+  c->n_rf_cells = (uint32_t)cells.size();
+  PSC_TRY(c->rf_cells.reserve(std::max<size_t>(cells.size(), 4) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMemcpy(c->rf_cells.p, cells.data(), cells.size() * sizeof(uint32_t),
+                          cudaMemcpyHostToDevice));
+  c->rf_built = true;
+  return 0;
+}
+
+static int fused_fallback(Ctx* c)
+{
+  // precondition broken for some particle: the source store is intact, take the general path
+  c->n_fused_fallback++;
+  c->counts_valid = false;
+  PSC_TRY(bnd_particles(c));
+  return sort_mprts(c);
+}
 
 int fused_bnd_sort(Ctx* c)
 {
   const GridDev& G = c->gd;
-  if (!c->pushed_from_sorted || c->comm) {
+  if (!c->pushed_from_sorted) {
+    c->counts_valid = false;
     PSC_TRY(bnd_particles(c));
     return sort_mprts(c);
   }
   const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
   const int np = G.n_patches;
-  PSC_TRY(c->scr[9].reserve((size_t)nct * 27 * sizeof(uint32_t)));
+  const bool multi = c->comm != nullptr;
+  PSC_TRY(c->scr[9].reserve((size_t)nct * FS_PLANES * sizeof(uint32_t)));
   PSC_TRY(c->scr[10].reserve(((size_t)nct + 1) * sizeof(uint32_t)));
   PSC_TRY(c->scr[11].reserve((np + 1 + 4) * sizeof(uint32_t)));
   uint32_t* cnt = c->scr[9].as<uint32_t>();
   uint32_t* new_cnt = c->scr[10].as<uint32_t>();
-  uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, n_drop, -, -, new patch offsets...]
+  uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, dropped, remote, counter, new patch offsets...]
   uint32_t* d_new_off = flags + 4;
   FsTables T{c->d_patch_bnd, c->d_nei_patch};
   if (!c->counts_valid) { // else: the push kernel already filled cnt and flags
@@ -297,6 +449,80 @@ int fused_bnd_sort(Ctx* c)
   {
     KernelScope ks(c, "fsort_offsets");
     k_fs_offsets<<<div_up(nct, 128), 128, 0, c->stream>>>(G, c->d_nei_patch, nct, cnt, new_cnt);
+    c->n_launches++;
+  }
+  uint32_t n_expected = c->n_prts;
+  // ---- multi-rank: ship the leavers, merge the arrivals into the target cells' tails
+  uint32_t n_recv_tot = 0;
+  float4 *xr = nullptr, *pr = nullptr;
+  uint32_t *skey = nullptr, *sidx = nullptr;
+  if (multi) {
+    uint32_t h4[4];
+    PSC_CUDA_TRY(cudaMemcpyAsync(h4, flags, sizeof(h4), cudaMemcpyDeviceToHost, c->stream));
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // every rank must reach the exchange below, also when it falls back later
+    const bool bad = h4[0] != 0;
+    const uint32_t n_rem = bad ? 0 : h4[2];
+    if (bad) {
+      return fused_fallback(c);
+    }
+    if (!c->rf_built) {
+      PSC_TRY(build_remote_cells(c));
+    }
+    uint32_t *gk = nullptr, *gi = nullptr;
+    if (n_rem) {
+      KernelScope ks(c, "fsort_remote_collect");
+      PSC_TRY(c->scr[7].reserve(4 * (size_t)n_rem * sizeof(uint32_t)));
+      uint32_t* a = c->scr[7].as<uint32_t>();
+      uint32_t *k0 = a, *v0 = a + n_rem, *k1 = a + 2 * (size_t)n_rem, *v1 = a + 3 * (size_t)n_rem;
+      // pass 1 sorts by index (keys = index, values = group), pass 2 by group
+      k_fs_collect_remote<<<div_up(c->n_rf_cells, FS_WARPS), FS_WARPS * 32, 0, c->stream>>>(
+        G, T, c->n_rf_cells, c->rf_cells.as<uint32_t>(), c->d_cell_off, c->xi(), v0, k0, flags + 3,
+        n_rem);
+      c->n_launches++;
+      bool in_alt = false;
+      PSC_TRY(sort_pairs(c, k0, v0, k1, v1, n_rem, 32, false, &in_alt));
+      uint32_t *ik = in_alt ? k1 : k0, *iv = in_alt ? v1 : v0; // (index, group) by index
+      uint32_t *ok = in_alt ? k0 : k1, *ov = in_alt ? v0 : v1;
+      size_t key_space = (size_t)c->g.n_ranks * np * 32;
+      int bits = 1;
+      while ((size_t(1) << bits) < key_space) {
+        bits++;
+      }
+      // keys = group (iv), values = index (ik)
+      PSC_TRY(sort_pairs(c, iv, ik, ov, ok, n_rem, bits, false, &in_alt));
+      gk = in_alt ? ov : iv;
+      gi = in_alt ? ok : ik;
+    }
+    std::vector<uint32_t> n_recv(np, 0);
+    PSC_TRY(comm_exchange_particles(c, c->xi(), c->pxi(), gi, gk, n_rem, 0, true, n_recv, &xr, &pr));
+    std::vector<uint32_t> roff(np + 1, 0);
+    for (int p = 0; p < np; p++) {
+      roff[p + 1] = roff[p] + n_recv[p];
+    }
+    n_recv_tot = roff[np];
+    n_expected = c->n_prts - n_rem - h4[1] + n_recv_tot;
+    if (n_recv_tot) {
+      KernelScope ks(c, "fsort_remote_merge");
+      PSC_TRY(c->scr[6].reserve((np + 1 + 4 * (size_t)n_recv_tot) * sizeof(uint32_t)));
+      uint32_t* d_roff = c->scr[6].as<uint32_t>();
+      uint32_t *k0 = d_roff + np + 1, *v0 = k0 + n_recv_tot, *k1 = v0 + n_recv_tot, *v1 = k1 + n_recv_tot;
+      PSC_CUDA_TRY(cudaMemcpyAsync(d_roff, roff.data(), (np + 1) * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, c->stream));
+      k_fs_recv_keys<<<div_up(n_recv_tot, 256), 256, 0, c->stream>>>(G, n_recv_tot, d_roff, xr, k0,
+                                                                    new_cnt, flags);
+      c->n_launches++;
+      int bits = 1;
+      while ((size_t(1) << bits) < nct) {
+        bits++;
+      }
+      bool in_alt = false;
+      PSC_TRY(sort_pairs(c, k0, v0, k1, v1, n_recv_tot, bits, true, &in_alt));
+      skey = in_alt ? k1 : k0;
+      sidx = in_alt ? v1 : v0;
+      PSC_CUDA_TRY(cudaStreamSynchronize(c->stream)); // roff is a host temporary
+    }
+    PSC_TRY(prts_reserve(c, n_expected));
   }
   {
     KernelScope ks(c, "fsort_scan");
@@ -306,21 +532,25 @@ int fused_bnd_sort(Ctx* c)
     KernelScope ks(c, "fsort_scatter");
     k_fs_scatter<<<div_up(nct, FS_CELLS), FS_WARPS * 32, 0, c->stream>>>(
       G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt());
+    if (n_recv_tot) {
+      k_fs_place_remote<<<div_up(n_recv_tot, 256), 256, 0, c->stream>>>(
+        n_recv_tot, skey, sidx, c->d_cell_off_alt, xr, pr, c->xi_alt(), c->pxi_alt());
+      c->n_launches++;
+    }
     k_patch_offsets<<<div_up(np + 1, 128), 128, 0, c->stream>>>(c->d_cell_off_alt, np, G.n_cells,
                                                                d_new_off);
   }
-  c->n_launches += 3 + 4; // + scan
+  c->n_launches += 2;
   std::vector<uint32_t> h(np + 1 + 4);
   PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                c->stream));
   PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
   PSC_TRY(check_launch(c, "fused_bnd_sort"));
   if (h[0]) {
-    // precondition broken for some particle: the source store is intact, take the
-    // general path
-    c->n_fused_fallback++;
-    PSC_TRY(bnd_particles(c));
-    return sort_mprts(c);
+    if (multi) {
+      return fail("fused boundary+sort: a received particle lies outside its patch");
+    }
+    return fused_fallback(c);
   }
   c->cur ^= 1;
   std::swap(c->d_cell_off, c->d_cell_off_alt);
@@ -328,6 +558,9 @@ int fused_bnd_sort(Ctx* c)
     c->h_off[p] = h[4 + p];
   }
   c->n_prts = c->h_off[np];
+  if (multi && c->n_prts != n_expected) {
+    return fail("fused boundary+sort: particle count mismatch after the exchange");
+  }
   c->n_dropped += h[1];
   c->sorted = true;
   c->pushed_from_sorted = false;

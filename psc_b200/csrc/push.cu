@@ -565,8 +565,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
               atomicAdd(&A.cnt[(size_t)cls * A.nct + (size_t)p * G.n_cells + (kl >> 5)], n);
             } else if (cls == CLS_BAD) {
               atomicExch(&A.flags[0], 1u);
-            } else {
+            } else if (cls == CLS_DROP) {
               atomicAdd(&A.flags[1], n);
+            } else {
+              atomicAdd(&A.flags[2], n); // leaves for another rank
             }
           }
           rem &= ~grp;
@@ -736,7 +738,7 @@ static int push_dim(Ctx* c)
     A.slot_len = c->fld_slot_len(0);
     A.nct = (uint32_t)G.n_cells * G.n_patches;
     A.tab = FsTables{c->d_patch_bnd, c->d_nei_patch};
-    bool count = c->want_counts && c->opt_warp_reduce && !c->comm;
+    bool count = c->want_counts && c->opt_warp_reduce;
     if (count) {
       PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(uint32_t)));
       PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));

@@ -1,0 +1,143 @@
+"""Multi-GPU parity check, one process per GPU (NCCL):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29533 tests/multi_gpu_check.py
+
+Every rank owns a contiguous range of the global patch list.  Rank 0 gathers the other
+ranks' particles and fields and compares them with the CPU oracle run on the whole
+domain with the same rank map (remote arrivals are appended behind local ones:
+ddc_particles.hxx:456-468).  Run by tests/test_gpu_multi.py when >= 2 GPUs are visible
+and by hand under `gpurun --gpus 2`."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle_lib as ol  # noqa: E402
+import psc_b200 as pb  # noqa: E402
+from gen import random_fields, thermal_plasma  # noqa: E402
+
+KINDS = ((-1., 1.), (1., 100.))
+
+
+def gather_obj(obj, rank, world):
+    out = [None] * world if rank == 0 else None
+    dist.gather_object(obj, out, dst=0)
+    return out
+
+
+def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None):
+    og = ol.Grid(dt=0.35, kinds=KINDS, nicell=8, **gkw)
+    npg = og.n_patches
+    if n_by_rank is None:
+        per, remn = divmod(npg, world)
+        n_by_rank = [per + (r < remn) for r in range(world)]
+    starts = np.concatenate([[0], np.cumsum(n_by_rank)])
+    rank_of_patch = np.repeat(np.arange(world), n_by_rank).astype(np.int32)
+    flds = random_fields(og, seed=3, amp_e=0.02, amp_b=0.05)
+    ol.fill_ghosts(og, flds, 3, 9)
+    prts, off = thermal_plasma(og, ppc=6, seed=4, vth=(0.5, 0.05), margin=0.02)
+
+    g = og.g
+    grid = pb.Grid(gdims=tuple(g.gdims), length=tuple(g.length), np=tuple(g.np), dt=g.dt, kinds=og.kinds,
+                   fnqs=g.fnqs, eta=g.eta, bc_fld_lo=list(g.bc_fld_lo), bc_fld_hi=list(g.bc_fld_hi),
+                   bc_prt_lo=list(g.bc_prt_lo), bc_prt_hi=list(g.bc_prt_hi), rank=rank, n_ranks=world,
+                   n_patches_by_rank=n_by_rank, device=local_rank)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(pb.Grid.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
+    p0, p1 = starts[rank], starts[rank + 1]
+    assert grid.n_patches() == p1 - p0 and grid.patch_begin() == p0
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    mprts.set(prts[off[p0]:off[p1]], np.diff(off[p0:p1 + 1]))
+    mflds.upload(flds[p0:p1])
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=fused)
+
+    # reference: the oracle's step with the same rank map
+    rf, rp, ro = flds.copy(), prts.copy(), off.copy()
+    L, G = ol.lib(), og.byref()
+    for _ in range(n_steps):
+        L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None)
+        L.po_push_mprts(G, ol.ptr(rf), ol.ptr(rp), ol.ptr(ro))
+        rp, ro, _ = ol.bnd_particles(og, rp, ro, rank_of_patch=rank_of_patch)
+        L.po_bndf_add_ghosts_J(G, ol.ptr(rf))
+        L.po_add_ghosts(G, ol.ptr(rf), 9, 0, 3)
+        L.po_fill_ghosts(G, ol.ptr(rf), 9, 0, 3)
+        L.po_push_H(G, ol.ptr(rf), .5)
+        L.po_bndf_fill_ghosts_H(G, ol.ptr(rf))
+        L.po_fill_ghosts(G, ol.ptr(rf), 9, 6, 9)
+        L.po_push_E(G, ol.ptr(rf), 1.)
+        L.po_bndf_fill_ghosts_E(G, ol.ptr(rf))
+        L.po_fill_ghosts(G, ol.ptr(rf), 9, 3, 6)
+        L.po_push_H(G, ol.ptr(rf), .5)
+        L.po_bndf_fill_ghosts_H(G, ol.ptr(rf))
+        L.po_fill_ghosts(G, ol.ptr(rf), 9, 6, 9)
+        psc.step()
+    if fused:
+        L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None)  # the fused step already did the next sort
+    gp, go = mprts.get()
+    gf = mflds.download()
+    en = pb.energies(grid)
+    stats = dict(fused=grid.get_stat("fused_steps"), fallbacks=grid.get_stat("fused_fallbacks"))
+    res = gather_obj((gp, go, gf, stats), rank, world)
+    ok = True
+    if rank == 0:
+        counts = np.concatenate([np.diff(r[1]) for r in res])
+        ref_counts = np.diff(ro)
+        all_p = np.concatenate([r[0] for r in res])
+        all_f = np.concatenate([r[2] for r in res])
+        same_counts = np.array_equal(counts, ref_counts)
+        ferr = np.abs(all_f - rf).max() / np.abs(rf).max()
+        perr = uerr = float("nan")
+        if same_counts:
+            perr = float(np.abs(all_p["x"] - rp["x"]).max())
+            uerr = float(np.abs(all_p["u"] - rp["u"]).max())
+        ref_e = ol.energies(og, rf, rp, ro)
+        eerr = float(np.abs(en - ref_e).max() / np.abs(ref_e).max())
+        ok = same_counts and ferr < 3e-5 and perr < 1e-4 and uerr < 1e-5 and eerr < 1e-4
+        print("%-28s fused=%d  counts %s  fld rel %.2e  x abs %.2e  u abs %.2e  energies rel %.2e  %s  %s" % (
+            name, fused, "same" if same_counts else "DIFFER", ferr, perr, uerr, eerr,
+            [r[3] for r in res], "ok" if ok else "FAIL"), flush=True)
+    grid.close()
+    return ok
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cases = {
+        "xyz_periodic_slabs": dict(gdims=(16, 16, 32), length=(16., 16., 32.), np_=(2, 2, 4)),
+        "yz_periodic": dict(gdims=(1, 32, 64), length=(1., 32., 64.), np_=(1, 2, 4)),
+        "xyz_wall_z": dict(gdims=(16, 16, 32), length=(16., 16., 32.), np_=(2, 2, 4),
+                           bc_fld_lo=[1, 1, 2], bc_fld_hi=[1, 1, 2], bc_prt_lo=[1, 1, 0], bc_prt_hi=[1, 1, 0]),
+    }
+    ok = True
+    for name, kw in cases.items():
+        for fused in (False, True):
+            ok = run_case(name, kw, rank, world, local_rank, fused) and ok
+    # uneven patch distribution (what the balancer produces)
+    npg = 16
+    uneven = [npg - 3 * (world - 1)] + [3] * (world - 1)
+    ok = run_case("xyz_uneven_ranks", cases["xyz_periodic_slabs"], rank, world, local_rank, True,
+                  n_by_rank=uneven) and ok
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if flag.item() else "FAIL", flush=True)
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
