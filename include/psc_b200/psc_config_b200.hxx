@@ -1,0 +1,793 @@
+// psc_b200 -- the PscConfig plugin surface of psc-code/psc over the psc_b200 C ABI.
+//
+// PSC's plugin API is compile-time duck typing: `template <typename PscConfig> struct Psc`
+// pulls its operator types out of PscConfig (src/include/psc.hxx:100-119) and a case deck
+// picks a config next to PscConfig1vbecCuda (src/psc_config.hxx:99-146,170-180).  This
+// header provides that set of types for the B200 backend:
+//
+//     template <typename Dim> using PscConfig1vbecB200 = psc_b200::PscConfig<Dim, Grid_t>;
+//
+//   Mparticles     MparticlesB200       ~ MparticlesSimple  (particles_simple.hxx:123-247)
+//   MfieldsState   MfieldsStateB200     ~ MfieldsStateFromMfields (fields3d.hxx:415-464)
+//   Mfields        MfieldsB200          ~ Mfields<float>    (fields3d.hxx:321-382)
+//   PushParticles  PushParticlesB200    ~ PushParticlesVb   (push_particles_1vb.hxx:27-84)
+//   Sort           SortB200             ~ SortCountsort2    (psc_sort_impl.hxx:65-124)
+//   BndParticles   BndParticlesB200     ~ BndParticlesCommon (bnd_particles_impl.hxx:234-247)
+//   Bnd            BndB200              ~ Bnd_              (psc_bnd_impl.hxx:105-158)
+//   BndFields      BndFieldsB200        ~ BndFields_        (psc_bnd_fields_impl.hxx:27-188)
+//   PushFields     PushFieldsB200       ~ PushFields        (psc_push_fields_impl.hxx:134-178)
+//   Marder         MarderB200           ~ MarderCommon      (marder_impl.hxx:197-264)
+//   Checks         ChecksB200           ~ Checks_           (checks_impl.hxx:33-215)
+//   Balance        BalanceB200          ~ Balance_          (psc_balance_impl.hxx:770-1026)
+//
+// Every method is one call into libpsc_b200.so (include/psc_b200.h); nothing is computed
+// on the host and there is no CPU fallback.  Error behaviour is PSC's: a failed call
+// prints the library's error text and abort()s (libpsc/bits.hxx:35-40,
+// cuda/cuda_bits.h:32-40) -- no exceptions, no error codes.
+//
+// The types are templates over the grid type so that this header compiles both inside a
+// PSC tree (GridT = Grid_t, src/include/grid.hxx:68-160) and stand-alone in this
+// repository's tests (tests/cxx/mini_grid.hxx, a struct with the same member names).
+// What is read from GridT:
+//   domain.gdims/np/length/corner/dx, ldims, ibn, dt, norm.fnqs/eta, kinds[k].q/.m,
+//   bc.fld_lo/fld_hi/prt_lo/prt_hi, patches[p].xb, n_patches()
+#pragma once
+
+#include "../psc_b200.h"
+
+#include <array>
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+namespace psc_b200
+{
+
+// LOG_ERROR + abort, like cudaCheck (cuda/cuda_bits.h:32-40)
+inline void check(int rc, const char* what)
+{
+  if (rc != 0) {
+    std::fprintf(stderr, "psc_b200: %s failed: %s\n", what, psc_b200_last_error());
+    std::abort();
+  }
+}
+#define PSC_B200_CHECK(call) ::psc_b200::check((call), #call)
+
+// ParticleSimple<float> (particle_simple.hxx:10-42) as stored on the wire
+struct Particle
+{
+  using real_t = float;
+  float x[3];
+  float u[3];
+  int kind;
+  float qni_wni;
+};
+static_assert(sizeof(Particle) == 32, "AoS record must be 32 bytes");
+
+// ----------------------------------------------------------------------
+// Context: one psc_b200_ctx per (rank, Grid_t).  PSC constructs Mparticles(grid) and
+// MfieldsState(grid) separately (psc_bubble_yz.cxx:290-291); both attach to the context
+// of their grid, which is created on first use and lives as long as one of them does.
+
+template <typename GridT>
+class Context
+{
+public:
+  static std::shared_ptr<Context> get(const GridT& grid, int deposit = PSC_B200_DEPOSIT_DEFAULT)
+  {
+    auto& reg = registry();
+    auto it = reg.find(&grid);
+    if (it != reg.end()) {
+      if (auto sp = it->second.lock()) {
+        return sp;
+      }
+    }
+    auto sp = std::shared_ptr<Context>(new Context(grid, deposit));
+    reg[&grid] = sp;
+    return sp;
+  }
+
+  ~Context()
+  {
+    psc_b200_destroy(ctx_);
+    registry().erase(grid_);
+  }
+
+  psc_b200_ctx* ctx() const { return ctx_; }
+  const GridT& grid() const { return *grid_; }
+
+  // multi-GPU: rank / n_ranks / patch counts of the decomposition, set before the first
+  // container is constructed (defaults: one rank owning every patch)
+  struct Decomposition
+  {
+    int rank = 0, n_ranks = 1, device = -1;
+    std::vector<int> n_patches_by_rank; // empty = uniform
+    unsigned long long max_n_prts = 0;
+  };
+  static Decomposition& decomposition()
+  {
+    static Decomposition d;
+    return d;
+  }
+
+private:
+  Context(const GridT& grid, int deposit) : grid_(&grid)
+  {
+    psc_b200_grid_desc d;
+    std::memset(&d, 0, sizeof(d));
+    for (int i = 0; i < 3; i++) {
+      d.gdims[i] = grid.domain.gdims[i];
+      d.np[i] = grid.domain.np[i];
+      d.length[i] = grid.domain.length[i];
+      d.corner[i] = grid.domain.corner[i];
+      d.bc_fld_lo[i] = grid.bc.fld_lo[i];
+      d.bc_fld_hi[i] = grid.bc.fld_hi[i];
+      d.bc_prt_lo[i] = grid.bc.prt_lo[i];
+      d.bc_prt_hi[i] = grid.bc.prt_hi[i];
+    }
+    d.dt = grid.dt;
+    d.fnqs = grid.norm.fnqs;
+    d.eta = grid.norm.eta;
+    d.n_kinds = (int)grid.kinds.size();
+    assert(d.n_kinds <= PSC_B200_MAX_KINDS);
+    for (int k = 0; k < d.n_kinds; k++) {
+      d.q[k] = grid.kinds[k].q;
+      d.m[k] = grid.kinds[k].m;
+    }
+    d.deposit = deposit;
+    const auto& dec = decomposition();
+    d.rank = dec.rank;
+    d.n_ranks = dec.n_ranks;
+    d.device = dec.device;
+    d.n_patches_by_rank = dec.n_patches_by_rank.empty() ? nullptr : dec.n_patches_by_rank.data();
+    d.max_n_prts = dec.max_n_prts;
+    PSC_B200_CHECK(psc_b200_create(&d, &ctx_));
+    assert(psc_b200_n_patches(ctx_) == grid.n_patches());
+  }
+
+  static std::map<const GridT*, std::weak_ptr<Context>>& registry()
+  {
+    static std::map<const GridT*, std::weak_ptr<Context>> r;
+    return r;
+  }
+
+  const GridT* grid_;
+  psc_b200_ctx* ctx_ = nullptr;
+};
+
+// ----------------------------------------------------------------------
+// InjectorB200: injector()[p](psc::particle::Inject) -- buffered, flushed when the
+// injector goes out of scope (cuda/injector_buffered.hxx:62-66); patches must be
+// visited in ascending order like there.  The conversion to the stored record is
+// InjectorSimple::Patch::operator() (injector_simple.hxx:20-37):
+//   x = Real3(new.x) - Real3(patch.xb)  (both narrowed to float first), qni_wni = w*q(kind)
+
+template <typename Mparticles>
+class InjectorB200
+{
+public:
+  class Patch
+  {
+  public:
+    Patch(InjectorB200& inj, int p) : inj_(inj), p_(p) {}
+
+    template <typename Inject>
+    void operator()(const Inject& new_prt)
+    {
+      const auto& grid = inj_.mprts_.grid();
+      const auto& patch = grid.patches[p_];
+      Particle prt;
+      for (int d = 0; d < 3; d++) {
+        prt.x[d] = float(new_prt.x[d]) - float(patch.xb[d]);
+        prt.u[d] = float(new_prt.u[d]);
+      }
+      prt.kind = new_prt.kind;
+      prt.qni_wni = float(new_prt.w * grid.kinds[new_prt.kind].q);
+      inj_.push_back(p_, prt);
+    }
+
+    // already-converted record (MparticlesSimple::push_back)
+    void raw(const Particle& prt) { inj_.push_back(p_, prt); }
+
+  private:
+    InjectorB200& inj_;
+    int p_;
+  };
+
+  explicit InjectorB200(Mparticles& mprts) : mprts_(mprts), n_by_patch_(mprts.n_patches(), 0) {}
+  InjectorB200(const InjectorB200&) = delete;
+  InjectorB200(InjectorB200&& o)
+    : mprts_(o.mprts_), buf_(std::move(o.buf_)), n_by_patch_(std::move(o.n_by_patch_)), last_(o.last_)
+  {
+    o.buf_.clear();
+    o.n_by_patch_.assign(mprts_.n_patches(), 0);
+  }
+
+  ~InjectorB200() { flush(); }
+
+  void reserve(int n_prts_total) { buf_.reserve(n_prts_total); }
+
+  Patch operator[](int p) { return Patch(*this, p); }
+
+  void flush()
+  {
+    if (buf_.empty()) {
+      return;
+    }
+    PSC_B200_CHECK(psc_b200_mprts_inject(mprts_.ctx(), buf_.data(), n_by_patch_.data()));
+    buf_.clear();
+    n_by_patch_.assign(mprts_.n_patches(), 0);
+    last_ = 0;
+  }
+
+private:
+  void push_back(int p, const Particle& prt)
+  {
+    assert(p >= last_ && "InjectorB200: patches must be injected in ascending order");
+    last_ = p;
+    buf_.push_back(prt);
+    n_by_patch_[p]++;
+  }
+
+  Mparticles& mprts_;
+  std::vector<Particle> buf_;
+  std::vector<uint32_t> n_by_patch_;
+  int last_ = 0;
+};
+
+// ----------------------------------------------------------------------
+// ConstAccessorB200: accessor()[p] -> range of particle proxies with PSC's accessor
+// vocabulary (const_accessor_simple.hxx:47-81).  A device->host copy of the whole store
+// (the reference's CUDA backend does the same, cuda_mparticles.cu get_particles).
+
+template <typename Mparticles>
+class ConstAccessorB200
+{
+public:
+  using GridT = typename Mparticles::Grid;
+
+  struct Proxy
+  {
+    const Particle& prt;
+    const GridT& grid;
+    int p;
+    std::array<float, 3> x() const { return {prt.x[0], prt.x[1], prt.x[2]}; }
+    std::array<float, 3> u() const { return {prt.u[0], prt.u[1], prt.u[2]}; }
+    float qni_wni() const { return prt.qni_wni; }
+    int kind() const { return prt.kind; }
+    float q() const { return float(grid.kinds[prt.kind].q); }
+    float m() const { return float(grid.kinds[prt.kind].m); }
+    float w() const { return prt.qni_wni / q(); }
+    // global position (const_accessor_simple.hxx:69-75)
+    std::array<double, 3> position() const
+    {
+      const auto& patch = grid.patches[p];
+      return {patch.xb[0] + prt.x[0], patch.xb[1] + prt.x[1], patch.xb[2] + prt.x[2]};
+    }
+  };
+
+  struct Patch
+  {
+    const ConstAccessorB200& acc;
+    int p;
+    struct iterator
+    {
+      const Patch& patch;
+      uint32_t n;
+      Proxy operator*() const { return {patch.acc.data_[n], patch.acc.mprts_.grid(), patch.p}; }
+      iterator& operator++()
+      {
+        ++n;
+        return *this;
+      }
+      bool operator!=(const iterator& o) const { return n != o.n; }
+    };
+    iterator begin() const { return {*this, acc.off_[p]}; }
+    iterator end() const { return {*this, acc.off_[p + 1]}; }
+    uint32_t size() const { return acc.off_[p + 1] - acc.off_[p]; }
+    Proxy operator[](uint32_t n) const { return {acc.data_[acc.off_[p] + n], acc.mprts_.grid(), p}; }
+  };
+
+  explicit ConstAccessorB200(Mparticles& mprts)
+    : mprts_(mprts), data_(mprts.size()), off_(mprts.n_patches() + 1)
+  {
+    PSC_B200_CHECK(psc_b200_mprts_get(mprts.ctx(), data_.data(), off_.data()));
+  }
+
+  Patch operator[](int p) const { return {*this, p}; }
+  const std::vector<Particle>& data() const { return data_; }
+  const std::vector<uint32_t>& offsets() const { return off_; }
+
+private:
+  Mparticles& mprts_;
+  std::vector<Particle> data_;
+  std::vector<uint32_t> off_;
+};
+
+// ----------------------------------------------------------------------
+// MparticlesB200
+
+template <typename GridT>
+class MparticlesB200
+{
+public:
+  using Grid = GridT;
+  using real_t = float;
+  using Particle = psc_b200::Particle;
+  using is_cuda = std::true_type; // device-resident: deck code takes its is_cuda branches
+
+  explicit MparticlesB200(const GridT& grid) : cx_(Context<GridT>::get(grid)) {}
+
+  const GridT& grid() const { return cx_->grid(); }
+  psc_b200_ctx* ctx() const { return cx_->ctx(); }
+  int n_patches() const { return psc_b200_n_patches(ctx()); }
+
+  // MparticlesBase::size / sizeByPatch (particles.hxx:19-33)
+  int size() const
+  {
+    uint64_t n;
+    PSC_B200_CHECK(psc_b200_mprts_size(ctx(), &n));
+    return (int)n;
+  }
+  std::vector<unsigned int> sizeByPatch() const
+  {
+    std::vector<unsigned int> n(n_patches());
+    PSC_B200_CHECK(psc_b200_mprts_size_by_patch(ctx(), n.data()));
+    return n;
+  }
+
+  // MparticlesBase::reset (Balance hands over the new grid, psc_balance_impl.hxx:893-909)
+  void reset(const GridT& grid) { cx_ = Context<GridT>::get(grid); }
+
+  InjectorB200<MparticlesB200> injector() { return InjectorB200<MparticlesB200>(*this); }
+  ConstAccessorB200<MparticlesB200> accessor() { return ConstAccessorB200<MparticlesB200>(*this); }
+
+  // bulk host interface (get_as<MparticlesSingle> / put_as, particles.hxx:35-54)
+  void set(const std::vector<Particle>& prts, const std::vector<uint32_t>& n_by_patch)
+  {
+    assert((int)n_by_patch.size() == n_patches());
+    PSC_B200_CHECK(psc_b200_mprts_set(ctx(), prts.data(), n_by_patch.data()));
+  }
+  void get(std::vector<Particle>& prts, std::vector<uint32_t>& off) const
+  {
+    prts.resize(size());
+    off.resize(n_patches() + 1);
+    PSC_B200_CHECK(psc_b200_mprts_get(ctx(), prts.data(), off.data()));
+  }
+
+private:
+  std::shared_ptr<Context<GridT>> cx_;
+};
+
+// ----------------------------------------------------------------------
+// MfieldsB200 / MfieldsStateB200: PSC's layout float [p][m][iz][iy][ix]
+// (fields3d.hxx:29-32,284-291); ib = -ibn, im = ldims + 2 ibn
+
+template <typename GridT>
+class MfieldsB200
+{
+public:
+  using Grid = GridT;
+  using real_t = float;
+
+  // scratch container with n_comps components, ghosts = grid.ibn
+  MfieldsB200(const GridT& grid, int n_comps) : cx_(Context<GridT>::get(grid)), n_comps_(n_comps)
+  {
+    PSC_B200_CHECK(psc_b200_mflds_create(ctx(), n_comps, &id_));
+    init_dims();
+  }
+
+  const GridT& grid() const { return cx_->grid(); }
+  psc_b200_ctx* ctx() const { return cx_->ctx(); }
+  int id() const { return id_; }
+  int n_comps() const { return n_comps_; }
+  int n_patches() const { return psc_b200_n_patches(ctx()); }
+  std::array<int, 3> ibn() const { return ibn_; }
+  std::array<int, 3> ib() const { return {-ibn_[0], -ibn_[1], -ibn_[2]}; }
+  std::array<int, 3> im() const { return im_; }
+  size_t patch_len() const { return (size_t)im_[0] * im_[1] * im_[2]; }
+
+  void zero(int mb, int me) { PSC_B200_CHECK(psc_b200_mflds_zero(ctx(), id_, mb, me)); }
+  void zero() { zero(0, n_comps_); }
+
+  // hostMirror + copy of setup_fields_cuda.hxx: components [mb, me) of every patch
+  std::vector<float> download(int mb, int me) const
+  {
+    std::vector<float> h((size_t)n_patches() * (me - mb) * patch_len());
+    PSC_B200_CHECK(psc_b200_mflds_download(ctx(), id_, mb, me, h.data()));
+    return h;
+  }
+  void upload(int mb, int me, const std::vector<float>& h)
+  {
+    assert(h.size() == (size_t)n_patches() * (me - mb) * patch_len());
+    PSC_B200_CHECK(psc_b200_mflds_upload(ctx(), id_, mb, me, h.data()));
+  }
+  // offset of (m, i, j, k) of patch p inside a download(mb, me) buffer
+  size_t index(int p, int m_rel, int n_m, int i, int j, int k) const
+  {
+    return ((((size_t)p * n_m + m_rel) * im_[2] + (k + ibn_[2])) * im_[1] + (j + ibn_[1])) * im_[0] +
+           (i + ibn_[0]);
+  }
+
+protected:
+  struct state_tag
+  {};
+  MfieldsB200(const GridT& grid, state_tag)
+    : cx_(Context<GridT>::get(grid)), n_comps_(PSC_B200_NR_FIELDS), id_(0)
+  {
+    init_dims();
+  }
+  void init_dims()
+  {
+    int ld[3], ibn[3];
+    PSC_B200_CHECK(psc_b200_get_ldims(ctx(), ld, ibn));
+    for (int d = 0; d < 3; d++) {
+      ibn_[d] = ibn[d];
+      im_[d] = ld[d] + 2 * ibn[d];
+    }
+  }
+
+  std::shared_ptr<Context<GridT>> cx_;
+  int n_comps_;
+  int id_ = -1;
+  std::array<int, 3> ibn_, im_;
+};
+
+template <typename GridT>
+class MfieldsStateB200 : public MfieldsB200<GridT>
+{
+public:
+  using Base = MfieldsB200<GridT>;
+  explicit MfieldsStateB200(const GridT& grid) : Base(grid, typename Base::state_tag{}) {}
+  void reset(const GridT& grid) { *this = MfieldsStateB200(grid); }
+
+  // setupFields (setup_fields.hxx:19-45): init(m, x[3]) evaluated at each component's
+  // Yee position (centering.hxx; bits/discretization.txt:4-12), ghosts included.
+  template <typename F>
+  void setup(F&& init)
+  {
+    const auto& g = this->grid();
+    // component m: staggered (+1/2) in dimension d?  E_d: own dim; H_d: the two others
+    static const int stag[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 1}, {1, 1, 0}};
+    auto ibn = this->ibn();
+    auto im = this->im();
+    std::vector<float> h((size_t)this->n_patches() * 6 * this->patch_len());
+    for (int p = 0; p < this->n_patches(); p++) {
+      const auto& patch = g.patches[p];
+      for (int m = 0; m < 6; m++) {
+        for (int k = -ibn[2]; k < im[2] - ibn[2]; k++) {
+          for (int j = -ibn[1]; j < im[1] - ibn[1]; j++) {
+            for (int i = -ibn[0]; i < im[0] - ibn[0]; i++) {
+              int idx[3] = {i, j, k};
+              double x[3];
+              for (int d = 0; d < 3; d++) {
+                x[d] = patch.xb[d] + (idx[d] + .5 * stag[m][d]) * g.domain.dx[d];
+              }
+              h[this->index(p, m, 6, i, j, k)] = float(init(PSC_B200_EX + m, x));
+            }
+          }
+        }
+      }
+    }
+    this->upload(PSC_B200_EX, PSC_B200_EX + 6, h);
+  }
+};
+
+// ----------------------------------------------------------------------
+// operators
+
+template <typename GridT>
+struct PushParticlesB200
+{
+  using Mparticles = MparticlesB200<GridT>;
+  using MfieldsState = MfieldsStateB200<GridT>;
+  // push_particles_1vb.hxx:27-84
+  void push_mprts(Mparticles& mprts, MfieldsState& mflds)
+  {
+    assert(mprts.ctx() == mflds.ctx());
+    PSC_B200_CHECK(psc_b200_push_mprts(mprts.ctx()));
+  }
+};
+
+template <typename GridT>
+struct SortB200
+{
+  // psc_sort_impl.hxx:65-124
+  void operator()(MparticlesB200<GridT>& mprts) { PSC_B200_CHECK(psc_b200_sort(mprts.ctx())); }
+};
+
+template <typename GridT>
+struct BndParticlesB200
+{
+  explicit BndParticlesB200(const GridT&) {}
+  // bnd_particles_impl.hxx:234-247; rebuilds nothing here: the neighbour tables live in
+  // the context and follow the grid (balance bumps them, psc_balance_impl.hxx:1018)
+  void operator()(MparticlesB200<GridT>& mprts) { PSC_B200_CHECK(psc_b200_bnd_particles(mprts.ctx())); }
+};
+
+template <typename GridT>
+struct BndB200
+{
+  // psc_bnd_impl.hxx:105-158
+  void add_ghosts(MfieldsB200<GridT>& mflds, int mb, int me)
+  {
+    PSC_B200_CHECK(psc_b200_bnd_add_ghosts(mflds.ctx(), mflds.id(), mb, me));
+  }
+  void fill_ghosts(MfieldsB200<GridT>& mflds, int mb, int me)
+  {
+    PSC_B200_CHECK(psc_b200_bnd_fill_ghosts(mflds.ctx(), mflds.id(), mb, me));
+  }
+};
+
+template <typename GridT>
+struct BndFieldsB200
+{
+  using MfieldsState = MfieldsStateB200<GridT>;
+  // psc_bnd_fields_impl.hxx:27-188
+  void fill_ghosts_E(MfieldsState& mflds) { PSC_B200_CHECK(psc_b200_bndf_fill_ghosts_E(mflds.ctx())); }
+  void fill_ghosts_H(MfieldsState& mflds) { PSC_B200_CHECK(psc_b200_bndf_fill_ghosts_H(mflds.ctx())); }
+  void add_ghosts_J(MfieldsState& mflds) { PSC_B200_CHECK(psc_b200_bndf_add_ghosts_J(mflds.ctx())); }
+};
+
+template <typename GridT>
+struct PushFieldsB200
+{
+  using MfieldsState = MfieldsStateB200<GridT>;
+  // psc_push_fields_impl.hxx:134-178; the Dim tag is what the context was created for
+  template <typename Dim>
+  void push_E(MfieldsState& mflds, double dt_fac, Dim)
+  {
+    PSC_B200_CHECK(psc_b200_push_E(mflds.ctx(), dt_fac));
+  }
+  template <typename Dim>
+  void push_H(MfieldsState& mflds, double dt_fac, Dim)
+  {
+    PSC_B200_CHECK(psc_b200_push_H(mflds.ctx(), dt_fac));
+  }
+  void push_E(MfieldsState& mflds, double dt_fac) { PSC_B200_CHECK(psc_b200_push_E(mflds.ctx(), dt_fac)); }
+  void push_H(MfieldsState& mflds, double dt_fac) { PSC_B200_CHECK(psc_b200_push_H(mflds.ctx(), dt_fac)); }
+};
+
+template <typename GridT>
+struct MarderB200
+{
+  using MfieldsState = MfieldsStateB200<GridT>;
+  using Mparticles = MparticlesB200<GridT>;
+  // marder_impl.hxx:150-264
+  MarderB200(const GridT&, double diffusion, int loop, bool /*dump*/) : diffusion_(diffusion), loop_(loop)
+  {}
+  void correct_gauss(MfieldsState& mflds, Mparticles&)
+  {
+    PSC_B200_CHECK(psc_b200_marder(mflds.ctx(), diffusion_, loop_));
+  }
+  void operator()(MfieldsState& mflds, Mparticles& mprts) { correct_gauss(mflds, mprts); }
+
+  double diffusion_;
+  int loop_;
+};
+
+// ChecksParams (checks_params.hxx): the cadence/threshold fields the step loop reads
+struct ChecksParamsB200
+{
+  int continuity_every_step = 0;
+  double continuity_threshold = 1e-13;
+  bool continuity_verbose = false;
+  int gauss_every_step = 0;
+  double gauss_threshold = 1e-13;
+  bool gauss_verbose = false;
+};
+
+template <typename GridT>
+struct ChecksB200
+{
+  using MfieldsState = MfieldsStateB200<GridT>;
+  using Mparticles = MparticlesB200<GridT>;
+
+  // checks_impl.hxx:33-132
+  struct Continuity
+  {
+    int every_step;
+    double threshold;
+    double last_max_err = 0.;
+    bool armed = false;
+    bool should_do_check(int timestep) const { return every_step > 0 && timestep % every_step == 0; }
+    void before_particle_push(Mparticles& mprts, int timestep)
+    {
+      armed = should_do_check(timestep);
+      if (armed) {
+        PSC_B200_CHECK(psc_b200_check_continuity_begin(mprts.ctx()));
+      }
+    }
+    void after_particle_push(Mparticles& mprts, MfieldsState&)
+    {
+      if (armed) {
+        PSC_B200_CHECK(psc_b200_check_continuity_end(mprts.ctx(), &last_max_err));
+        assert(last_max_err < threshold); // checks_impl.hxx:128
+        armed = false;
+      }
+    }
+  };
+  // checks_impl.hxx:137-215
+  struct Gauss
+  {
+    int every_step;
+    double threshold;
+    double last_max_err = 0.;
+    bool should_do_check(int timestep) const { return every_step > 0 && timestep % every_step == 0; }
+    void operator()(Mparticles& mprts, MfieldsState&, int timestep)
+    {
+      if (should_do_check(timestep)) {
+        PSC_B200_CHECK(psc_b200_check_gauss(mprts.ctx(), &last_max_err));
+        assert(last_max_err < threshold); // checks_impl.hxx:211
+      }
+    }
+  };
+
+  ChecksB200(const GridT&, const ChecksParamsB200& prm)
+    : continuity{prm.continuity_every_step, prm.continuity_threshold},
+      gauss{prm.gauss_every_step, prm.gauss_threshold}
+  {}
+
+  Continuity continuity;
+  Gauss gauss;
+};
+
+template <typename GridT>
+struct BalanceB200
+{
+  // psc_balance_impl.hxx:770-1026: redistributes patches over the ranks by
+  // load = n_prts + factor_fields * n_cells; returns whether anything moved
+  explicit BalanceB200(double factor_fields = 1.) : factor_fields_(factor_fields) {}
+  bool operator()(MparticlesB200<GridT>& mprts)
+  {
+    int changed = 0;
+    PSC_B200_CHECK(psc_b200_balance(mprts.ctx(), factor_fields_, &changed));
+    return changed != 0;
+  }
+  double factor_fields_;
+};
+
+// DiagEnergies (DiagEnergiesField.h:19-42, DiagEnergiesParticle.h:15-40)
+template <typename GridT>
+inline std::array<double, 8> energies(MparticlesB200<GridT>& mprts)
+{
+  std::array<double, 8> out;
+  PSC_B200_CHECK(psc_b200_energies(mprts.ctx(), out.data()));
+  return out;
+}
+
+// ----------------------------------------------------------------------
+// the config bundle (src/psc_config.hxx:99-146)
+
+template <typename _Dim, typename GridT>
+struct PscConfig
+{
+  using Dim = _Dim;
+  using Grid = GridT;
+  using Mparticles = MparticlesB200<GridT>;
+  using MfieldsState = MfieldsStateB200<GridT>;
+  using Mfields = MfieldsB200<GridT>;
+  using PushParticles = PushParticlesB200<GridT>;
+  using Sort = SortB200<GridT>;
+  using PushFields = PushFieldsB200<GridT>;
+  using BndParticles = BndParticlesB200<GridT>;
+  using Bnd = BndB200<GridT>;
+  using BndFields = BndFieldsB200<GridT>;
+  using Balance = BalanceB200<GridT>;
+  using Checks = ChecksB200<GridT>;
+  using Marder = MarderB200<GridT>;
+};
+
+// ----------------------------------------------------------------------
+// Step: the operator sequence of Psc::step (src/include/psc.hxx:321-486) over a config,
+// with PscParams' cadence (psc.hxx:66-83).  `fused` routes the same sequence through the
+// single entry point psc_b200_step, which lets the library fuse the particle boundary
+// exchange with the following sort (same results).
+
+struct PscParamsB200
+{
+  int sort_interval = 0;
+  int marder_interval = 0;
+  double marder_diffusion = 0.9;
+  int marder_loop = 3;
+  bool fused = true;
+};
+
+template <typename Config>
+class Step
+{
+public:
+  using GridT = typename Config::Grid;
+  using Mparticles = typename Config::Mparticles;
+  using MfieldsState = typename Config::MfieldsState;
+
+  Step(const GridT& grid, MfieldsState& mflds, Mparticles& mprts, const PscParamsB200& p,
+       const ChecksParamsB200& cp = {})
+    : p_(p), mflds_(mflds), mprts_(mprts), bndp_(grid), marder_(grid, p.marder_diffusion, p.marder_loop, false),
+      checks_(grid, cp)
+  {}
+
+  // psc.hxx:220-238 initialize(): ghost fills before the first step
+  void initialize()
+  {
+    bndf_.fill_ghosts_H(mflds_);
+    bnd_.fill_ghosts(mflds_, PSC_B200_HX, PSC_B200_HX + 3);
+    bnd_.fill_ghosts(mflds_, PSC_B200_JXI, PSC_B200_JXI + 3);
+    bndf_.fill_ghosts_E(mflds_);
+    bnd_.fill_ghosts(mflds_, PSC_B200_EX, PSC_B200_EX + 3);
+  }
+
+  void operator()()
+  {
+    const int t = ++timestep_;
+    const bool do_sort = p_.sort_interval > 0 && t % p_.sort_interval == 0;
+    const bool do_marder = p_.marder_interval > 0 && t % p_.marder_interval == 0;
+    if (p_.fused) {
+      psc_b200_step_params sp;
+      sp.sort = do_sort;
+      sp.marder_loop = do_marder ? p_.marder_loop : 0;
+      sp.marder_diffusion = p_.marder_diffusion;
+      sp.push_fields = 1;
+      sp.checks = checks_.continuity.should_do_check(t) || checks_.gauss.should_do_check(t);
+      PSC_B200_CHECK(psc_b200_step(mprts_.ctx(), &sp));
+      if (sp.checks) {
+        PSC_B200_CHECK(psc_b200_last_checks(mprts_.ctx(), &checks_.continuity.last_max_err,
+                                            &checks_.gauss.last_max_err));
+      }
+      return;
+    }
+    typename Config::Dim dim{};
+    if (do_sort) {
+      sort_(mprts_); // psc.hxx:356-361
+    }
+    checks_.continuity.before_particle_push(mprts_, t); // :379-384
+    pushp_.push_mprts(mprts_, mflds_);                  // :389
+    bndp_(mprts_);                                      // :412
+    bndf_.add_ghosts_J(mflds_);                         // :417
+    bnd_.add_ghosts(mflds_, PSC_B200_JXI, PSC_B200_JXI + 3);  // :418
+    bnd_.fill_ghosts(mflds_, PSC_B200_JXI, PSC_B200_JXI + 3); // :419
+    pushf_.push_H(mflds_, .5, dim);                     // :426
+    bndf_.fill_ghosts_H(mflds_);                        // :428
+    bnd_.fill_ghosts(mflds_, PSC_B200_HX, PSC_B200_HX + 3); // :432
+    pushf_.push_E(mflds_, 1., dim);                     // :439
+    bndf_.fill_ghosts_E(mflds_);                        // :441
+    bnd_.fill_ghosts(mflds_, PSC_B200_EX, PSC_B200_EX + 3); // :445
+    if (do_marder) {
+      marder_(mflds_, mprts_); // :448-455
+    }
+    pushf_.push_H(mflds_, .5, dim);                     // :461
+    bndf_.fill_ghosts_H(mflds_);                        // :463
+    bnd_.fill_ghosts(mflds_, PSC_B200_HX, PSC_B200_HX + 3); // :467
+    checks_.continuity.after_particle_push(mprts_, mflds_); // :471-476
+    checks_.gauss(mprts_, mflds_, t);                   // :479-483
+  }
+
+  int timestep() const { return timestep_; }
+  typename Config::Checks& checks() { return checks_; }
+
+private:
+  PscParamsB200 p_;
+  MfieldsState& mflds_;
+  Mparticles& mprts_;
+  typename Config::Sort sort_;
+  typename Config::PushParticles pushp_;
+  typename Config::PushFields pushf_;
+  typename Config::Bnd bnd_;
+  typename Config::BndFields bndf_;
+  typename Config::BndParticles bndp_;
+  typename Config::Marder marder_;
+  typename Config::Checks checks_;
+  int timestep_ = 0;
+};
+
+} // namespace psc_b200
+
+// inside a PSC tree (grid.hxx included first): the name a deck uses
+#ifdef PSC_B200_WITH_PSC_GRID
+template <typename Dim>
+using PscConfig1vbecB200 = psc_b200::PscConfig<Dim, Grid_t>;
+#endif
