@@ -48,7 +48,7 @@ namespace PUSH_VARIANT
 {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int QCAP = 64; // crossing-particle queue entries per warp
+constexpr int QCAP = 56; // crossing-particle queue entries per warp
 
 // ---------------------------------------------------------------- tile geometry
 // f = shared tile extent in nodes, g = distance of tile node 0 below the tile origin.
@@ -277,6 +277,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
+// Ampere-style async copy: 16 bytes per lane, global -> shared, bypassing L1 and registers
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+
 // sum N values across the warp with a transposing butterfly; afterwards every lane
 // holds in v[0] the warp total of value slot_of_lane<N>(lane)
 template <int N>
@@ -339,11 +362,13 @@ struct PushArgs
   float4* pxi4;
   float* flds;
   long slot_len;
-  // counting hook (COUNT): cnt[class][cell] planes, flags[0] = precondition broken,
-  // flags[1] = dropped particles
+  // counting hook (COUNT): cnt[class][cell] planes (every entry is written exactly once,
+  // no memset needed), flags[0] = precondition broken, flags[1] = dropped particles,
+  // flags[2] = particles leaving for another rank
   uint32_t* cnt;
   uint32_t* flags;
   uint32_t nct;
+  int same_dxi; // 1/float(dx) == float(dx_inv) bitwise: the pusher's cell = the indexer's cell
   FsTables tab;
 };
 
@@ -368,20 +393,34 @@ __device__ __forceinline__ void leaf_deposit(const GridDev& G, const GEO& geo, f
   }
 }
 
-template <int DIM, int DEPOSIT, typename GEO, bool WARP_REDUCE, bool TMA, bool COUNT, int MAXT, int MINB>
+// The store is ordered by (patch, cell), so a warp that walks a row of cells sees the
+// particles of one cell after the other.  Work is issued in chunks of 32 consecutive
+// particles (full lanes, coalesced 128-bit loads/stores) regardless of where the cell
+// boundaries fall; the deposit of the particles that stay in their cell (one trajectory
+// segment, ~95 %) is accumulated per lane in registers and summed across the warp once
+// per CELL (transposing shuffle butterfly, then one shared-memory atomic per value), not
+// once per chunk.  A chunk that straddles a cell boundary is visited in one pass per
+// cell; the cell a pass belongs to is warp-uniform, so the source cell of every particle
+// is known without computing it, and so is its destination class (COUNT) in the common
+// case.  Particles that leave their cell are parked in a per-warp shared queue and
+// split/deposited 32 at a time, so the divergent Villasenor-Buneman walk runs with full
+// warps.
+template <int DIM, int DEPOSIT, typename GEO, bool TMA, bool COUNT, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, PushArgs A)
 {
   constexpr int NV = pm::LeafShape<DIM>::NV;
   constexpr int NVP = (DIM == pm::DIM_XYZ) ? 16 : 8;
+  constexpr bool XYZ = DIM == pm::DIM_XYZ;
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   const int nodes = geo.sm();
   float* sEM = smem;             // [6][f2][f1][f0]
   float* sJ = smem + 6 * nodes;  // [3][f2][f1][f0]
   float4* sQ = reinterpret_cast<float4*>(smem + ((9 * nodes + 3) & ~3)); // [warps][QCAP][2]
+  float4* sP = sQ + (size_t)(blockDim.x >> 5) * QCAP * 2;                // [warps][2][32] next chunk
+  __shared__ int row_ctr; // rows are handed out dynamically (balances the warps)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
   const int tiles_per_patch = geo.nt(0) * geo.nt(1) * geo.nt(2);
   const int p = blockIdx.x / tiles_per_patch;
   int tt = blockIdx.x - p * tiles_per_patch;
@@ -397,12 +436,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   // global index of tile node 0
   const int n0 = o[0] - geo.g(0), n1 = o[1] - geo.g(1), n2 = o[2] - geo.g(2);
 
+  if (tid == 0) {
+    row_ctr = n_warps;
+  }
   // ---- stage E/B, zero J
   if (TMA) {
     // rows are contiguous in the first non-invariant direction: one bulk copy per row.
     // The host selects this path only when every row start and size is a 16-byte multiple
     // and lies inside the patch array.
-    constexpr bool XYZ = DIM == pm::DIM_XYZ;
     const int row_len = XYZ ? geo.f(0) : geo.f(1);
     const int rows_per_comp = XYZ ? geo.f(1) * geo.f(2) : geo.f(2);
     const int rows = 6 * rows_per_comp;
@@ -456,11 +497,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
 
   FldTile<GEO> EM{sEM, geo, n0, n1, n2};
-  const int my_slot = slot_of_lane<NVP>(lane);
-  const int my_lin = (my_slot < NV) ? leaf_lin<DIM>(my_slot, geo.sy(), geo.sz(), geo.sm()) : 0;
-  const bool writer = (my_slot < NV) && ((lane & (NVP == 16 ? 1 : 3)) == 0);
   float4* myQ = sQ + (size_t)warp * QCAP * 2;
-  int qn = 0; // queued crossing particles of this warp (warp-uniform)
+  const uint32_t myP = smem_u32(sP + (size_t)warp * 64 + lane);
+  int qn = 0; // queued trajectories of this warp (warp-uniform)
 
   // split + deposit `cnt` queued trajectories (entries [qn - cnt, qn)), one per lane
   auto drain = [&](int cnt) {
@@ -495,91 +534,84 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
     __syncwarp();
   };
 
-  // ---- particle runs: contiguous cells along the first non-invariant dim
-  const int n_rows = (DIM == pm::DIM_XYZ) ? e[1] * e[2] : e[2];
-  const int run_cells = (DIM == pm::DIM_XYZ) ? e[0] : e[1];
+  // ---- particle runs: rows of cells along the first non-invariant dim
+  const int n_rows = XYZ ? e[1] * e[2] : e[2];
+  const int run_cells = XYZ ? e[0] : e[1]; // <= 31 (host)
   const uint32_t* coff = A.cell_off + (size_t)p * G.n_cells;
-  for (int row = warp; row < n_rows; row += n_warps) {
-    int c0;
-    if (DIM == pm::DIM_XYZ) {
+  for (int row = warp; row < n_rows;) {
+    int c0, rs1, rs2; // first cell of the row; row coordinates
+    if (XYZ) {
       int ry = row % e[1], rz = row / e[1];
-      c0 = ((o[2] + rz) * G.ldims[1] + (o[1] + ry)) * G.ldims[0] + o[0];
+      rs1 = o[1] + ry, rs2 = o[2] + rz;
+      c0 = (rs2 * G.ldims[1] + rs1) * G.ldims[0] + o[0];
     } else {
-      c0 = (o[2] + row) * G.ldims[1] + o[1];
+      rs1 = o[1], rs2 = o[2] + row;
+      c0 = rs2 * G.ldims[1] + o[1];
     }
-    const uint32_t begin = __ldg(&coff[c0]), end = __ldg(&coff[c0 + run_cells]);
-    float4 Xn = make_float4(0.f, 0.f, 0.f, 0.f), Un = Xn;
+    // lane j holds the offset of the row's j-th cell boundary
+    const uint32_t myoff = __ldg(&coff[c0 + min(lane, run_cells)]);
+    const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, run_cells);
+    int cur = 0;                                     // cell of the row the passes are at
+    uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
+    float acc[NV];                                   // this lane's share of the cell's deposit
+#pragma unroll
+    for (int n = 0; n < NV; n++) {
+      acc[n] = 0.f;
+    }
+    bool dirty = false;
+    uint32_t mycount = 0; // lane k: particles of the current cell in class k
+
+    // the next chunk travels global -> shared with cp.async while this one is computed
+    // (no registers held across the chunk body)
     if (begin + lane < end) {
-      Xn = A.xi4[begin + lane];
-      Un = A.pxi4[begin + lane];
+      cp_async16(myP, A.xi4 + begin + lane);
+      cp_async16(myP + 32 * sizeof(float4), A.pxi4 + begin + lane);
     }
-    for (uint32_t base = begin; base < end; base += 32) {
+    cp_async_commit();
+    uint32_t base = begin;
+    do {
       const uint32_t i = base + lane;
       const bool act = i < end;
-      const float4 X = Xn, U = Un;
-      if (i + 32 < end) { // prefetch the next chunk while this one is computed
-        Xn = A.xi4[i + 32];
-        Un = A.pxi4[i + 32];
+      cp_async_wait_all();
+      const float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
+      if (i + 32 < end) {
+        cp_async16(myP, A.xi4 + i + 32);
+        cp_async16(myP + 32 * sizeof(float4), A.pxi4 + i + 32);
       }
+      cp_async_commit();
       if (qn > QCAP - 32) {
-        drain(32);
+        drain(min(qn, 32));
       }
-      float val[NVP];
+      float val[NV];
       int ci[3] = {0, 0, 0};
-      bool cross = false;
-      pm::Trajectory t;
-      float xo[3] = {X.x, X.y, X.z};
-      if (act) {
-        float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
-        pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-        A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-        A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
-        cross = (DIM == pm::DIM_XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
-        if (!cross) {
-          // single segment: the leaf is the whole trajectory
-          Walker<DIM, DEPOSIT> w;
-          w.first(G.pc, t, U.w, ci, val);
-        }
-        if (COUNT) {
-          // source cell from the pre-push position, class from the pushed one
-          int s0 = pm::cell_position(G.pc, xo[0], 0), s1 = pm::cell_position(G.pc, xo[1], 1),
-              s2 = pm::cell_position(G.pc, xo[2], 2);
-          int q, c;
-          float uu[3] = {u[0], u[1], u[2]};
-          int cls = fs_classify(G, A.tab, p, s0, s1, s2, x, uu, q, c);
-          int s = (s2 * G.ldims[1] + s1) * G.ldims[0] + s0;
-          xo[0] = __int_as_float(s * 32 + cls); // key, reused below
-        }
-      }
-      if (COUNT) {
-        // aggregate equal (source cell, class) keys across the warp: one red per group
-        int key = act ? __float_as_int(xo[0]) : -1;
-        unsigned rem = __ballot_sync(FULL, act);
-        while (rem) {
-          int kl = __shfl_sync(FULL, key, __ffs(rem) - 1);
-          unsigned grp = __ballot_sync(FULL, key == kl);
-          if (lane == __ffs(grp) - 1) {
-            int cls = kl & 31;
-            uint32_t n = __popc(grp);
-            if (cls < FS_PLANES) {
-              atomicAdd(&A.cnt[(size_t)cls * A.nct + (size_t)p * G.n_cells + (kl >> 5)], n);
-            } else if (cls == CLS_BAD) {
-              atomicExch(&A.flags[0], 1u);
-            } else if (cls == CLS_DROP) {
-              atomicAdd(&A.flags[1], n);
-            } else {
-              atomicAdd(&A.flags[2], n); // leaves for another rank
+      int pos[3] = {0, 0, 0};
+      bool single = false; // one trajectory segment, leaf in (ci, val)
+      {
+        bool cross = false;
+        pm::Trajectory t;
+        if (act) {
+          float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
+          pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
+          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+          cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
+          single = !cross;
+          if (single) {
+            Walker<DIM, DEPOSIT> w;
+            w.first(G.pc, t, U.w, ci, val);
+          }
+          if (COUNT) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+              pos[d] = A.same_dxi ? t.lf[d] : pm::cell_position(G.pc, x[d], d);
             }
           }
-          rem &= ~grp;
         }
-      }
-      // park cell-crossing particles
-      {
-        unsigned cm = __ballot_sync(FULL, cross);
+        // park cell-crossing particles for the split/deposit walk
+        const unsigned cm = __ballot_sync(FULL, cross);
         if (cm) {
           if (cross) {
-            int slot = qn + __popc(cm & lt);
+            const int slot = qn + __popc(cm & ((1u << lane) - 1u));
             myQ[2 * slot] = make_float4(t.xm[0], t.xm[1], t.xm[2], U.w);
             myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], t.v[0]);
           }
@@ -587,52 +619,103 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
           __syncwarp();
         }
       }
-      // single-segment particles: deposit
-      const bool dep = act && !cross;
-      int r0 = ci[0] - n0, r1 = ci[1] - n1, r2 = ci[2] - n2;
-      bool in_tile = (DIM == pm::DIM_YZ || (unsigned)r0 < (unsigned)(geo.f(0) - 1)) &&
-                     (unsigned)r1 < (unsigned)(geo.f(1) - 1) && (unsigned)r2 < (unsigned)(geo.f(2) - 1);
-      int key = r2 * geo.sz() + r1 * geo.sy() + r0;
-      if (dep && !in_tile) {
-        leaf_to_global<DIM>(G, F, ci, val);
-      }
-      if (WARP_REDUCE) {
-        unsigned rem = __ballot_sync(FULL, dep && in_tile);
-        int iter = 0;
-        while (rem) {
-          if (iter == 2 || __popc(rem) < 4) {
-            if ((rem >> lane) & 1) {
+      // ---- one pass per cell that has particles in this chunk
+      for (;;) {
+        const bool mine = act && i >= cb && i < ce;
+        const int s0 = XYZ ? o[0] + cur : 0, s1 = XYZ ? rs1 : rs1 + cur, s2 = rs2;
+        if (mine && single) {
+          if (ci[0] == s0 && ci[1] == s1 && ci[2] == s2) {
 #pragma unroll
-              for (int n = 0; n < NV; n++) {
-                atomicAdd(&sJ[key + leaf_lin<DIM>(n, geo.sy(), geo.sz(), geo.sm())], val[n]);
-              }
+            for (int n = 0; n < NV; n++) {
+              acc[n] += val[n];
             }
-            break;
+            dirty = true;
+          } else {
+            // the leaf is not the run's cell (1/float(dx) and float(dx_inv) disagree at a
+            // cell edge): deposit it on its own
+            leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
           }
-          int kl = __shfl_sync(FULL, key, __ffs(rem) - 1);
-          bool mine = ((rem >> lane) & 1) && key == kl;
-          unsigned grp = __ballot_sync(FULL, mine);
+        }
+        if (COUNT) {
+          int cls = CLS_NONE;
+          if (mine) {
+            const int d0 = pos[0] - s0, d1 = pos[1] - s1, d2 = pos[2] - s2;
+            const bool ok = (unsigned)pos[0] < (unsigned)G.ldims[0] && (unsigned)pos[1] < (unsigned)G.ldims[1] &&
+                            (unsigned)pos[2] < (unsigned)G.ldims[2] && (unsigned)(d0 + 1) <= 2u &&
+                            (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
+            if (ok) {
+              cls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
+            } else {
+              // patch boundary: the pushed record is re-read (written by this thread above)
+              const float4 Xr = A.xi4[i], Ur = A.pxi4[i];
+              float xx[3] = {Xr.x, Xr.y, Xr.z}, uu[3] = {Ur.x, Ur.y, Ur.z};
+              int q, c;
+              cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
+            }
+          }
+          unsigned grp = __ballot_sync(FULL, cls == CLS_CENTER);
+          if (lane == CLS_CENTER) {
+            mycount += __popc(grp);
+          }
+          unsigned rem = __ballot_sync(FULL, mine) & ~grp;
+          while (rem) {
+            const int v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
+            grp = __ballot_sync(FULL, cls == v);
+            if (lane == v) {
+              mycount += __popc(grp);
+            }
+            rem &= ~grp;
+          }
+        }
+        if (ce > base + 32) {
+          break; // the cell continues in the next chunk
+        }
+        // ---- the cell is complete: flush its deposit and its class counts
+        if (__any_sync(FULL, dirty)) {
           float v[NVP];
 #pragma unroll
           for (int n = 0; n < NVP; n++) {
-            v[n] = (mine && n < NV) ? val[n] : 0.f;
+            v[n] = n < NV ? acc[n] : 0.f;
           }
           warp_transpose_reduce<NVP>(v, lane);
+          const int my_slot = slot_of_lane<NVP>(lane);
+          const int my_lin = (my_slot < NV) ? leaf_lin<DIM>(my_slot, geo.sy(), geo.sz(), geo.sm()) : 0;
+          const bool writer = (my_slot < NV) && ((lane & (NVP == 16 ? 1 : 3)) == 0);
           if (writer) {
-            atomicAdd(&sJ[kl + my_lin], v[0]);
+            atomicAdd(&sJ[(s2 - n2) * geo.sz() + (s1 - n1) * geo.sy() + (s0 - n0) + my_lin], v[0]);
           }
-          rem &= ~grp;
-          iter++;
-        }
-      } else {
-        if (dep && in_tile) {
 #pragma unroll
           for (int n = 0; n < NV; n++) {
-            atomicAdd(&sJ[key + leaf_lin<DIM>(n, geo.sy(), geo.sz(), geo.sm())], val[n]);
+            acc[n] = 0.f;
           }
+          dirty = false;
         }
+        if (COUNT) {
+          if (lane < FS_PLANES) {
+            A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur)] = mycount;
+          } else if (mycount) {
+            if (lane == CLS_BAD) {
+              atomicExch(&A.flags[0], 1u);
+            } else if (lane == CLS_DROP) {
+              atomicAdd(&A.flags[1], mycount);
+            } else if (lane == CLS_REMOTE) {
+              atomicAdd(&A.flags[2], mycount);
+            }
+          }
+          mycount = 0;
+        }
+        if (++cur == run_cells) {
+          break;
+        }
+        cb = ce;
+        ce = __shfl_sync(FULL, myoff, cur + 1);
       }
+      base += 32;
+    } while (base < end);
+    if (lane == 0) {
+      row = atomicAdd(&row_ctr, 1);
     }
+    row = __shfl_sync(FULL, row, 0);
   }
   while (qn > 0) {
     drain(min(qn, 32));
@@ -664,60 +747,65 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
   const GridDev& G = c->gd;
   int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
   int threads = std::max(32, std::min(512, c->opt_threads)) & ~31;
-  // register budget variants (launch bounds) of the production configuration
-  int lb = 0; // 0: (512, 2)  1: (512, 1)  2: (256, 3)  3: (256, 4)
-  if (TUNE && c->opt_warp_reduce) {
-    if (threads <= 256) {
-      lb = c->opt_min_blocks >= 4 ? 3 : 2;
-    } else {
-      lb = c->opt_min_blocks == 1 ? 1 : 0;
-    }
+  if (geo.t(DIM == pm::DIM_XYZ ? 0 : 1) > 31) {
+    return -1; // a row's cell boundaries are held one per lane
+  }
+  // register budget variants (launch bounds); odd geometries get the roomy one only
+  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)
+  if (TUNE) {
+    lb = threads > 256 ? 2 : (c->opt_min_blocks == 2 ? 1 : 0);
+  } else {
+    threads = std::min(threads, 256);
   }
   size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
-                      (size_t)(threads / 32) * QCAP * 2 * sizeof(float4);
+                      (size_t)(threads / 32) * (QCAP * 2 + 64) * sizeof(float4);
   if (smem_bytes > 220 * 1024) {
     return -1;
   }
-#define PSC_LAUNCH(WR, TM, CN, MT, MB)                                                            \
+#define PSC_LAUNCH(TM, CN, MT, MB)                                                                \
   do {                                                                                            \
-    auto kern = k_push_tiled<DIM, DEPOSIT, GEO, WR, TM, CN, MT, MB>;                              \
+    auto kern = k_push_tiled<DIM, DEPOSIT, GEO, TM, CN, MT, MB>;                                  \
     PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                       (int)smem_bytes));                                          \
     kern<<<tiles, threads, smem_bytes, c->stream>>>(G, geo, A);                                   \
   } while (0)
-#define PSC_LAUNCH_LB(WR, TM, CN)                                                                 \
+#ifdef PUSH_PROBE
+  PSC_LAUNCH(true, true, 256, 3);
+#else
+#define PSC_LAUNCH_LB(TM, CN)                                                                     \
   do {                                                                                            \
-    if (TUNE && lb == 1) {                                                                        \
-      PSC_LAUNCH(WR, TM, CN, 512, 1);                                                             \
-    } else if (TUNE && lb == 2) {                                                                 \
-      PSC_LAUNCH(WR, TM, CN, 256, 3);                                                             \
-    } else if (TUNE && lb == 3) {                                                                 \
-      PSC_LAUNCH(WR, TM, CN, 256, 4);                                                             \
+    if constexpr (TUNE) {                                                                         \
+      if (lb == 0) {                                                                              \
+        PSC_LAUNCH(TM, CN, 256, 3);                                                               \
+      } else if (lb == 2) {                                                                       \
+        PSC_LAUNCH(TM, CN, 512, 1);                                                               \
+      } else {                                                                                    \
+        PSC_LAUNCH(TM, CN, 256, 2);                                                               \
+      }                                                                                           \
     } else {                                                                                      \
-      PSC_LAUNCH(WR, TM, CN, 512, 2);                                                             \
+      PSC_LAUNCH(TM, CN, 256, 2);                                                                 \
     }                                                                                             \
   } while (0)
-  if (!c->opt_warp_reduce) {
+  if (count) {
     if (tma) {
-      PSC_LAUNCH(false, true, false, 512, 2);
+      if constexpr (TUNE) {
+        PSC_LAUNCH_LB(true, true);
+      }
     } else {
-      PSC_LAUNCH(false, false, false, 512, 2);
-    }
-  } else if (count) {
-    if (tma) {
-      PSC_LAUNCH_LB(true, true, true);
-    } else {
-      PSC_LAUNCH_LB(true, false, true);
+      PSC_LAUNCH_LB(false, true);
     }
   } else {
     if (tma) {
-      PSC_LAUNCH_LB(true, true, false);
+      if constexpr (TUNE) {
+        PSC_LAUNCH_LB(true, false);
+      }
     } else {
-      PSC_LAUNCH_LB(true, false, false);
+      PSC_LAUNCH_LB(false, false);
     }
   }
-#undef PSC_LAUNCH
 #undef PSC_LAUNCH_LB
+#endif
+#undef PSC_LAUNCH
   return 0;
 }
 
@@ -738,13 +826,17 @@ static int push_dim(Ctx* c)
     A.slot_len = c->fld_slot_len(0);
     A.nct = (uint32_t)G.n_cells * G.n_patches;
     A.tab = FsTables{c->d_patch_bnd, c->d_nei_patch};
-    bool count = c->want_counts && c->opt_warp_reduce;
+    A.same_dxi = 1;
+    for (int d = 0; d < 3; d++) {
+      A.same_dxi = A.same_dxi && G.pc.dxi[d] == G.pc.dxi_idx[d];
+    }
+    bool count = c->want_counts;
     if (count) {
+      // the kernel writes every cnt[class][cell] entry exactly once: no memset
       PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(uint32_t)));
       PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));
       A.cnt = c->scr[9].as<uint32_t>();
       A.flags = c->scr[11].as<uint32_t>();
-      PSC_CUDA_TRY(cudaMemsetAsync(A.cnt, 0, (size_t)A.nct * FS_PLANES * sizeof(uint32_t), c->stream));
       PSC_CUDA_TRY(cudaMemsetAsync(A.flags, 0, 4 * sizeof(uint32_t), c->stream));
     }
     const bool xyz = DIM == pm::DIM_XYZ;
@@ -805,6 +897,9 @@ int PUSH_CAT(push_mprts_, PUSH_VARIANT)(Ctx* c)
   // push_particles_1vb.hxx:48: J = 0 on every patch
   PSC_TRY(flds_zero(c, 0, pm::JXI, pm::JXI + 3));
   int rc;
+#ifdef PUSH_PROBE
+  rc = push_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
+#else
   if (c->gd.dim == pm::DIM_XYZ) {
     rc = push_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
   } else if (c->gd.deposit == pm::DEPOSIT_VAR1) {
@@ -812,6 +907,7 @@ int PUSH_CAT(push_mprts_, PUSH_VARIANT)(Ctx* c)
   } else {
     rc = push_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c);
   }
+#endif
   // particles have moved: cell order and cell offsets no longer describe the store
   // (the fused boundary+sort pass of step() picks the store up from here)
   c->pushed_from_sorted = c->sorted && rc == 0;
