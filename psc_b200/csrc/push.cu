@@ -751,9 +751,9 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
     return -1; // a row's cell boundaries are held one per lane
   }
   // register budget variants (launch bounds); odd geometries get the roomy one only
-  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)
+  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)  3: (224, 3)  4: (192, 3)
   if (TUNE) {
-    lb = threads > 256 ? 2 : (c->opt_min_blocks == 2 ? 1 : 0);
+    lb = threads > 256 ? 2 : (threads == 224 ? 3 : (threads == 192 ? 4 : (c->opt_min_blocks == 2 ? 1 : 0)));
   } else {
     threads = std::min(threads, 256);
   }
@@ -770,7 +770,7 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
     kern<<<tiles, threads, smem_bytes, c->stream>>>(G, geo, A);                                   \
   } while (0)
 #ifdef PUSH_PROBE
-  PSC_LAUNCH(true, true, 256, 3);
+  PSC_LAUNCH(true, true, PUSH_PROBE_T, PUSH_PROBE_B);
 #else
 #define PSC_LAUNCH_LB(TM, CN)                                                                     \
   do {                                                                                            \
@@ -779,6 +779,10 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
         PSC_LAUNCH(TM, CN, 256, 3);                                                               \
       } else if (lb == 2) {                                                                       \
         PSC_LAUNCH(TM, CN, 512, 1);                                                               \
+      } else if (lb == 3) {                                                                       \
+        PSC_LAUNCH(TM, CN, 224, 3);                                                               \
+      } else if (lb == 4) {                                                                       \
+        PSC_LAUNCH(TM, CN, 192, 3);                                                               \
       } else {                                                                                    \
         PSC_LAUNCH(TM, CN, 256, 2);                                                               \
       }                                                                                           \
