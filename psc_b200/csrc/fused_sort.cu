@@ -190,41 +190,72 @@ __global__ void k_fs_offsets(GridDev G, const int* __restrict__ nei_patch, uint3
   new_cnt[g] = total;
 }
 
-__global__ void __launch_bounds__(FS_WARPS * 32)
+// Scatter: one warp walks SC_CPW consecutive source cells.  Like the push kernel it
+// issues full 32-particle chunks regardless of cell boundaries (coalesced 128-bit loads,
+// the next chunk in flight through cp.async while this one is ranked) and visits a chunk
+// once per cell it touches; lane k carries the running offset of class k of the current
+// cell inside its target cell.
+constexpr int SC_WARPS = 8;
+constexpr int SC_CPW = 8;                 // cells per warp
+constexpr int SC_CELLS = SC_WARPS * SC_CPW; // source cells per CTA
+
+__device__ __forceinline__ void fs_cp_async16(uint32_t dst, const void* src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
   k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
                const uint32_t* __restrict__ new_cell_off, const uint32_t* __restrict__ pre,
                const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
                float4* __restrict__ xo, float4* __restrict__ po)
 {
-  __shared__ uint32_t pre_s[FS_CELLS][33];
+  __shared__ uint32_t pre_s[SC_CELLS][33];
+  __shared__ float4 stage_s[SC_WARPS][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t g0 = blockIdx.x * FS_CELLS;
-  for (int plane = warp; plane < 32; plane += FS_WARPS) {
-    pre_s[lane][plane] = (plane < 27 && g0 + lane < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + lane]) : 0u;
+  const uint32_t g0 = blockIdx.x * SC_CELLS;
+  for (int plane = warp; plane < 32; plane += SC_WARPS) {
+    for (int c = lane; c < SC_CELLS; c += 32) {
+      pre_s[c][plane] = (plane < 27 && g0 + c < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + c]) : 0u;
+    }
   }
   __syncthreads();
-  for (int k = 0; k < FS_CELLS / FS_WARPS; k++) {
-    const int cl = warp * (FS_CELLS / FS_WARPS) + k;
-    const uint32_t g = g0 + cl;
-    if (g >= nct) {
-      break;
+  const uint32_t gw = g0 + warp * SC_CPW; // first cell of this warp
+  if (gw >= nct) {
+    return;
+  }
+  const int n_cells_w = min((uint32_t)SC_CPW, nct - gw);
+  // coordinates of the current cell, advanced incrementally
+  int p = gw / G.n_cells;
+  int s = gw - p * G.n_cells;
+  int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+  const uint32_t myoff = __ldg(&cell_off[gw + min(lane, n_cells_w)]);
+  const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, n_cells_w);
+  int cur = 0;
+  uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
+  uint32_t run = pre_s[warp * SC_CPW][lane];
+  const uint32_t stg = (uint32_t)__cvta_generic_to_shared(&stage_s[warp][0][lane]);
+  if (begin + lane < end) {
+    fs_cp_async16(stg, xi4 + begin + lane);
+    fs_cp_async16(stg + 32 * sizeof(float4), pxi4 + begin + lane);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (uint32_t base = begin; base < end; base += 32) {
+    const uint32_t i = base + lane;
+    const bool act = i < end;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float4 X = stage_s[warp][0][lane], U = stage_s[warp][1][lane];
+    if (i + 32 < end) {
+      fs_cp_async16(stg, xi4 + i + 32);
+      fs_cp_async16(stg + 32 * sizeof(float4), pxi4 + i + 32);
     }
-    const int p = g / G.n_cells;
-    const int s = g - p * G.n_cells;
-    const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
-    const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
-    // lane k carries the running offset of class k inside its target cell
-    uint32_t run = pre_s[cl][lane];
-    for (uint32_t base = begin; base < end; base += 32) {
-      uint32_t i = base + lane;
-      bool act = i < end;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (;;) {
+      const bool mine = act && i >= cb && i < ce;
       int cls = CLS_NONE;
-      float4 X, U;
       uint32_t tbase = 0;
-      if (act) {
-        X = xi4[i];
-        U = pxi4[i];
+      if (mine) {
         float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
         int q = 0, c = 0;
         cls = fs_classify(G, T, p, s0, s1, s2, x, u, q, c);
@@ -234,12 +265,12 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
           U = make_float4(u[0], u[1], u[2], U.w);
         }
       }
-      unsigned rem = __ballot_sync(FULL, act);
+      unsigned rem = __ballot_sync(FULL, mine);
       uint32_t dst = 0;
       int v = CLS_CENTER;
-      for (;;) {
-        unsigned grp = __ballot_sync(FULL, cls == v);
-        uint32_t r0 = __shfl_sync(FULL, run, v);
+      while (rem) {
+        const unsigned grp = __ballot_sync(FULL, cls == v);
+        const uint32_t r0 = __shfl_sync(FULL, run, v);
         if (cls == v) {
           dst = tbase + r0 + __popc(grp & lt);
         }
@@ -247,14 +278,32 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
           run += __popc(grp);
         }
         rem &= ~grp;
-        if (!rem) {
-          break;
+        if (rem) {
+          v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
         }
-        v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
       }
-      if (act && cls < 27) {
+      if (mine && cls < 27) {
         xo[dst] = X;
         po[dst] = U;
+      }
+      if (ce > base + 32) {
+        break; // the cell continues in the next chunk
+      }
+      if (++cur == n_cells_w) {
+        break;
+      }
+      cb = ce;
+      ce = __shfl_sync(FULL, myoff, cur + 1);
+      run = pre_s[warp * SC_CPW + cur][lane];
+      if (++s0 == G.ldims[0]) {
+        s0 = 0;
+        if (++s1 == G.ldims[1]) {
+          s1 = 0;
+          if (++s2 == G.ldims[2]) {
+            s2 = 0;
+            p++;
+          }
+        }
       }
     }
   }
@@ -530,7 +579,7 @@ int fused_bnd_sort(Ctx* c)
   }
   {
     KernelScope ks(c, "fsort_scatter");
-    k_fs_scatter<<<div_up(nct, FS_CELLS), FS_WARPS * 32, 0, c->stream>>>(
+    k_fs_scatter<<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
       G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt());
     if (n_recv_tot) {
       k_fs_place_remote<<<div_up(n_recv_tot, 256), 256, 0, c->stream>>>(
