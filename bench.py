@@ -281,6 +281,17 @@ def run_b200(args, rank, world, local_rank):
                     "algorithmic_bytes_per_particle": B_PUSH,
                     "step_frac": (value / world) * B_STEP / 1e9 / peak,
                     "step_algorithmic_bytes_per_particle": B_STEP}
+    # DRAM bytes of one launch of the dominant kernel from the last `ncu --set full`
+    # capture of this workload (profiles/push_traffic.json, written by tools/summarize_ncu.py)
+    if roofline:
+        try:
+            with open(os.path.join(ROOT, "profiles", "push_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("particles") == n_prts:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
     cpu = None
     if not args.no_cpu:
         cores = os.cpu_count() or 1

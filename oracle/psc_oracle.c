@@ -1295,6 +1295,73 @@ void po_energies(const po_grid* g, const float* flds, const po_prt* prts,
   }
 }
 
+/* ====================================================================== */
+/* balance */
+
+/* best_mapping_recursive (psc_balance_impl.hxx:99-151) */
+static void po_map_rec(const double* load_by_patch, int* n_by_proc, int proc_begin,
+                       int proc_end, int patch_begin, int patch_end)
+{
+  assert(patch_end - patch_begin >= proc_end - proc_begin);
+  if (proc_end == proc_begin + 1) {
+    n_by_proc[proc_begin] = patch_end - patch_begin;
+    return;
+  }
+  int proc_middle = (proc_begin + proc_end) / 2;
+  double load_total = 0.;
+  for (int p = patch_begin; p < patch_end; p++) {
+    load_total += load_by_patch[p];
+  }
+  double load_target =
+    (load_total * (proc_middle - proc_begin)) / (proc_end - proc_begin);
+  double load = 0.;
+  int patch_middle = patch_begin;
+  for (;;) {
+    double prev_load = load;
+    load += load_by_patch[patch_middle];
+    patch_middle++;
+    if (load > load_target) {
+      double above = load - load_target;
+      double below = load_target - prev_load;
+      if (below < above && patch_middle) {
+        patch_middle--;
+        load = prev_load;
+      }
+      break;
+    }
+    if (patch_middle >= patch_end) { /* the reference would read past the end here */
+      break;
+    }
+  }
+  if (patch_middle - patch_begin < proc_middle - proc_begin) {
+    patch_middle = patch_begin + (proc_middle - proc_begin);
+  }
+  if (patch_end - patch_middle < proc_end - proc_middle) {
+    patch_middle = patch_end - (proc_end - proc_middle);
+  }
+  po_map_rec(load_by_patch, n_by_proc, proc_begin, proc_middle, patch_begin, patch_middle);
+  po_map_rec(load_by_patch, n_by_proc, proc_middle, proc_end, patch_middle, patch_end);
+}
+
+/* best_mapping (psc_balance_impl.hxx:153-160); capabilities are all equal in PSC's
+ * non-capability build (this branch, :95-160) */
+void po_best_mapping(int n_ranks, const double* capability, int n_patches,
+                     const double* loads, int* n_patches_by_rank)
+{
+  (void)capability;
+  po_map_rec(loads, n_patches_by_rank, 0, n_ranks, 0, n_patches);
+}
+
+/* get_loads (psc_balance_impl.hxx:223-269) */
+void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,
+                  double* loads)
+{
+  int n_cells = g->ldims[0] * g->ldims[1] * g->ldims[2];
+  for (int p = 0; p < g->n_patches; p++) {
+    loads[p] = (double)(off[p + 1] - off[p]) + factor_fields * n_cells;
+  }
+}
+
 const char* po_describe(void)
 {
   return "plain-C restatement of psc-code/psc 1vb hot path (oracle/psc_oracle.c), "

@@ -173,6 +173,14 @@ void po_marder_correct(const po_grid* g, float* flds, const po_prt* prts,
 void po_energies(const po_grid* g, const float* flds, const po_prt* prts,
                  const unsigned* off, double* out);
 
+/* Balance: best_mapping / best_mapping_recursive (psc_balance_impl.hxx:99-160): 1-D
+ * recursive bisection of the patch list by load, at least one patch per rank;
+ * get_loads (psc_balance_impl.hxx:223-269): load = n_prts + factor_fields * n_cells */
+void po_best_mapping(int n_ranks, const double* capability, int n_patches,
+                     const double* loads, int* n_patches_by_rank);
+void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,
+                  double* loads);
+
 const char* po_describe(void);
 
 #ifdef __cplusplus

@@ -122,6 +122,13 @@ class Grid:
         check(load().psc_b200_nccl_unique_id(buf))
         return bytes(buf)
 
+    def balance(self, factor_fields=1.0):
+        """Balance::operator() (psc_balance_impl.hxx:770-1026): redistributes whole patches
+        over the ranks by load = n_prts + factor_fields * n_cells; True if anything moved"""
+        ch = C.c_int()
+        check(self.lib.psc_b200_balance(self.ctx, float(factor_fields), C.byref(ch)))
+        return bool(ch.value)
+
     def close(self):
         if self.ctx:
             self.lib.psc_b200_destroy(self.ctx)

@@ -725,14 +725,147 @@ std::vector<int> best_mapping(const std::vector<double>& capability,
   return out;
 }
 
+// Balance_::operator() (psc_balance_impl.hxx:770-1026): loads -> best_mapping -> new
+// contiguous patch ranges -> whole patches (particles + every field array) move to
+// their new owner.  The reference round-trips everything through the host and MPI
+// (communicate_ctx, :353-760); here every rank knows all per-patch particle counts
+// after one all-reduce, so the moves are direct device-to-device ncclSend/ncclRecv with
+// no headers: both sides walk the global patch list in ascending order.
 int balance(Ctx* c, double factor_fields, int* changed)
 {
   *changed = 0;
-  (void)factor_fields;
-  if (c->g.n_ranks == 1) {
+  const GridHost g = c->g; // the old decomposition (copy)
+  if (g.n_ranks == 1) {
     return 0; // one rank owns every patch: nothing to redistribute
   }
-  return fail("balance across ranks: not implemented in this build");
+  if (!c->comm) {
+    return fail("balance: psc_b200_nccl_init has not been called");
+  }
+  Comm* cm = c->comm;
+  const int NG = g.n_patches_global, me = g.rank;
+  // get_loads (:223-269) and the particle count of every global patch
+  std::vector<double> v(2 * (size_t)NG, 0.);
+  for (int p = 0; p < g.n_patches; p++) {
+    double n = (double)(c->h_off[p + 1] - c->h_off[p]);
+    v[g.patch_begin + p] = n + factor_fields * g.n_cells;
+    v[NG + g.patch_begin + p] = n;
+  }
+  PSC_TRY(comm_allreduce_sum(c, v.data(), 2 * NG));
+  std::vector<double> loads(v.begin(), v.begin() + NG);
+  std::vector<int> new_n = best_mapping(std::vector<double>(g.n_ranks, 1.), loads);
+  std::vector<int> new_off(g.n_ranks + 1, 0);
+  for (int r = 0; r < g.n_ranks; r++) {
+    new_off[r + 1] = new_off[r] + new_n[r];
+  }
+  if (new_off == g.patch_off_by_rank) {
+    return 0;
+  }
+  *changed = 1;
+  auto owner = [](const std::vector<int>& off, int gp) {
+    return (int)(std::upper_bound(off.begin(), off.end(), gp) - off.begin()) - 1;
+  };
+  const int nb = new_off[me], nnp = new_off[me + 1] - new_off[me];
+  std::vector<uint32_t> noff(nnp + 1, 0);
+  for (int k = 0; k < nnp; k++) {
+    noff[k + 1] = noff[k] + (uint32_t)v[NG + nb + k];
+  }
+  const uint32_t n_new = noff[nnp];
+  PSC_TRY(prts_reserve(c, std::max<size_t>(n_new, c->n_prts)));
+  float4 *xs = c->xi(), *ps = c->pxi(), *xd = c->xi_alt(), *pd = c->pxi_alt();
+
+  // new decomposition, tables and (zeroed) field arrays
+  std::vector<FieldArr> old_flds = c->flds;
+  c->g.patch_off_by_rank = new_off;
+  c->g.patch_begin = nb;
+  c->g.n_patches = nnp;
+  c->gd.n_patches = nnp;
+  cudaFree(c->d_patch_bnd);
+  cudaFree(c->d_nei_patch);
+  cudaFree(c->d_nei_slot);
+  cudaFree(c->d_add_order);
+  c->d_patch_bnd = nullptr, c->d_nei_patch = nullptr, c->d_nei_slot = nullptr, c->d_add_order = nullptr;
+  PSC_TRY(build_patch_tables(c));
+  c->flds.clear();
+  for (const FieldArr& f : old_flds) {
+    int id;
+    PSC_TRY(flds_create(c, f.n_comps, &id));
+  }
+
+  // move the patches
+  PSC_NCCL_TRY(g_nccl.GroupStart());
+  for (int gp = 0; gp < NG; gp++) {
+    const int ro = owner(g.patch_off_by_rank, gp), rn = owner(new_off, gp);
+    if (ro != me && rn != me) {
+      continue;
+    }
+    const size_t n = (size_t)v[NG + gp];
+    const int po = gp - g.patch_begin, pn = gp - nb; // old / new local index
+    if (ro == me && rn == me) {
+      if (n) {
+        PSC_CUDA_TRY(cudaMemcpyAsync(xd + noff[pn], xs + c->h_off[po], n * sizeof(float4),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+        PSC_CUDA_TRY(cudaMemcpyAsync(pd + noff[pn], ps + c->h_off[po], n * sizeof(float4),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+      }
+      for (size_t f = 0; f < old_flds.size(); f++) {
+        size_t len = (size_t)g.fld_len * old_flds[f].n_comps;
+        PSC_CUDA_TRY(cudaMemcpyAsync(c->flds[f].d + pn * len, old_flds[f].d + po * len,
+                                     len * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+      }
+    } else if (ro == me) {
+      if (n) {
+        PSC_NCCL_TRY(g_nccl.Send(xs + c->h_off[po], n * 4, ncclFloat, rn, cm->comm, c->stream));
+        PSC_NCCL_TRY(g_nccl.Send(ps + c->h_off[po], n * 4, ncclFloat, rn, cm->comm, c->stream));
+      }
+      for (size_t f = 0; f < old_flds.size(); f++) {
+        size_t len = (size_t)g.fld_len * old_flds[f].n_comps;
+        PSC_NCCL_TRY(g_nccl.Send(old_flds[f].d + po * len, len, ncclFloat, rn, cm->comm, c->stream));
+      }
+    } else {
+      if (n) {
+        PSC_NCCL_TRY(g_nccl.Recv(xd + noff[pn], n * 4, ncclFloat, ro, cm->comm, c->stream));
+        PSC_NCCL_TRY(g_nccl.Recv(pd + noff[pn], n * 4, ncclFloat, ro, cm->comm, c->stream));
+      }
+      for (size_t f = 0; f < old_flds.size(); f++) {
+        size_t len = (size_t)g.fld_len * old_flds[f].n_comps;
+        PSC_NCCL_TRY(g_nccl.Recv(c->flds[f].d + pn * len, len, ncclFloat, ro, cm->comm, c->stream));
+      }
+    }
+  }
+  PSC_NCCL_TRY(g_nccl.GroupEnd());
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (FieldArr& f : old_flds) {
+    cudaFree(f.d);
+  }
+
+  // the store now lives in the other buffer, in the new patch order
+  c->cur ^= 1;
+  c->n_prts = n_new;
+  c->h_off = noff;
+  cudaFree(c->d_off);
+  cudaFree(c->d_cell_off);
+  cudaFree(c->d_cell_off_alt);
+  const size_t nct = (size_t)g.n_cells * nnp;
+  PSC_CUDA_TRY(cudaMalloc(&c->d_off, (nnp + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_cell_off, (nct + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMalloc(&c->d_cell_off_alt, (nct + 1) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMemset(c->d_cell_off, 0, (nct + 1) * sizeof(uint32_t)));
+  PSC_TRY(prts_upload_off(c));
+  c->sorted = false;
+  c->pushed_from_sorted = false;
+  c->counts_valid = false;
+  c->want_counts = false;
+  c->rf_built = false;
+  // halo plans follow the tables (psc_balance_generation_cnt, bnd_particles_impl.hxx:236-239)
+  for (auto& P : cm->plan) {
+    cudaFree(P.d_send);
+    cudaFree(P.d_recv);
+    cudaFree(P.d_send_boff);
+    cudaFree(P.d_recv_boff);
+    P = HaloPlan{};
+  }
+  // ghost cells of the moved patches are rebuilt by the next fill; proxies start empty
+  return 0;
 }
 
 } // namespace psc_b200

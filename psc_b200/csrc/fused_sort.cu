@@ -204,7 +204,10 @@ __device__ __forceinline__ void fs_cp_async16(uint32_t dst, const void* src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(SC_WARPS * 32)
+#ifndef SC_MINB
+#define SC_MINB 4
+#endif
+__global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
                const uint32_t* __restrict__ new_cell_off, const uint32_t* __restrict__ pre,
                const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
@@ -215,32 +218,33 @@ __global__ void __launch_bounds__(SC_WARPS * 32)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t g0 = blockIdx.x * SC_CELLS;
-  for (int plane = warp; plane < 32; plane += SC_WARPS) {
-    for (int c = lane; c < SC_CELLS; c += 32) {
-      pre_s[c][plane] = (plane < 27 && g0 + c < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + c]) : 0u;
-    }
-  }
-  __syncthreads();
   const uint32_t gw = g0 + warp * SC_CPW; // first cell of this warp
-  if (gw >= nct) {
-    return;
-  }
-  const int n_cells_w = min((uint32_t)SC_CPW, nct - gw);
-  // coordinates of the current cell, advanced incrementally
-  int p = gw / G.n_cells;
-  int s = gw - p * G.n_cells;
-  int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
-  const uint32_t myoff = __ldg(&cell_off[gw + min(lane, n_cells_w)]);
+  const int n_cells_w = gw < nct ? (int)min((uint32_t)SC_CPW, nct - gw) : 0;
+  // the warp's first chunk is requested before anything else waits on memory
+  const uint32_t myoff = n_cells_w ? __ldg(&cell_off[gw + min(lane, n_cells_w)]) : 0u;
   const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, n_cells_w);
-  int cur = 0;
-  uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
-  uint32_t run = pre_s[warp * SC_CPW][lane];
   const uint32_t stg = (uint32_t)__cvta_generic_to_shared(&stage_s[warp][0][lane]);
   if (begin + lane < end) {
     fs_cp_async16(stg, xi4 + begin + lane);
     fs_cp_async16(stg + 32 * sizeof(float4), pxi4 + begin + lane);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int plane = warp; plane < 32; plane += SC_WARPS) {
+    for (int c = lane; c < SC_CELLS; c += 32) {
+      pre_s[c][plane] = (plane < 27 && g0 + c < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + c]) : 0u;
+    }
+  }
+  __syncthreads();
+  if (n_cells_w == 0) {
+    return;
+  }
+  // coordinates of the current cell, advanced incrementally
+  int p = gw / G.n_cells;
+  int s = gw - p * G.n_cells;
+  int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+  int cur = 0;
+  uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
+  uint32_t run = pre_s[warp * SC_CPW][lane];
   for (uint32_t base = begin; base < end; base += 32) {
     const uint32_t i = base + lane;
     const bool act = i < end;

@@ -60,6 +60,7 @@ def hostcheck():
         L.hc_push_mprts.argtypes = [P, P, P, P]
         L.hc_bnd_classify.argtypes = [P, P, P, P, P]
         L.hc_grid_info.argtypes = [P, P, P, P, P]
+        L.hc_neighbor_table.argtypes = [P, P, P]
         _hc = L
     return _hc
 

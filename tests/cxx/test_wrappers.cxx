@@ -1,0 +1,155 @@
+// Drives the PscConfig wrapper types (include/psc_b200/psc_config_b200.hxx) the way a
+// PSC case deck + Psc<PscConfig> would (psc_bubble_yz.cxx:117-147,290-340; psc.hxx:321-486):
+// build a grid, construct Mparticles / MfieldsState, set fields with a lambda, inject
+// particles patch by patch, run N steps twice -- once operator by operator, once through
+// the fused entry point -- and dump the final state for the Python test to compare with
+// the CPU oracle (tests/test_gpu_cxx.py).
+//
+//   test_wrappers <out.bin> <xyz|yz> <n_steps> <fused 0|1>
+//
+// Needs a GPU at run time; compiling and linking it is the CPU-side check of the header.
+#include "mini_grid.hxx"
+
+#include <psc_b200/psc_config_b200.hxx>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+
+using Grid = mini::Grid;
+
+template <typename Dim>
+static int run(const std::string& out, bool yz, int n_steps, bool fused)
+{
+  using Config = psc_b200::PscConfig<Dim, Grid>;
+  using Mparticles = typename Config::Mparticles;
+  using MfieldsState = typename Config::MfieldsState;
+
+  const int ppc = 6;
+  Grid grid(yz ? mini::Int3{1, 16, 32} : mini::Int3{16, 8, 16},
+            yz ? mini::Real3{1., 20., 30.} : mini::Real3{16., 8., 16.},
+            yz ? mini::Int3{1, 2, 2} : mini::Int3{2, 1, 2}, yz ? 0.3 : 0.4,
+            {{-1., 1., "e"}, {1., 100., "i"}}, ppc);
+
+  Mparticles mprts{grid};
+  MfieldsState mflds{grid};
+
+  // setupFields with a lambda (psc_bubble_yz.cxx:248-285)
+  mflds.setup([&](int m, double x[3]) {
+    switch (m) {
+      case PSC_B200_EY: return 0.05 * std::sin(0.4 * x[2]);
+      case PSC_B200_EZ: return 0.03 * std::cos(0.3 * x[1]);
+      case PSC_B200_HX: return 0.1;
+      case PSC_B200_HZ: return 0.02 * std::sin(0.2 * x[1] + 0.1 * x[0]);
+      default: return 0.;
+    }
+  });
+
+  // inject patch by patch (setup_particles.hxx:263-331 does the same through injector())
+  {
+    std::mt19937 rng(42);
+    std::uniform_real_distribution<double> uni(0.02, 0.98);
+    std::normal_distribution<double> nrm(0., 1.);
+    auto inj = mprts.injector();
+    for (int p = 0; p < grid.n_patches(); p++) {
+      auto injp = inj[p];
+      const auto& patch = grid.patches[p];
+      for (int k = 0; k < grid.ldims[2]; k++) {
+        for (int j = 0; j < grid.ldims[1]; j++) {
+          for (int i = 0; i < grid.ldims[0]; i++) {
+            for (int n = 0; n < 2 * ppc; n++) {
+              int kind = n & 1;
+              double vth = kind ? 0.02 : 0.2;
+              mini::Inject prt{{patch.xb[0] + (i + (yz ? 0.5 : uni(rng))) * grid.domain.dx[0],
+                                patch.xb[1] + (j + uni(rng)) * grid.domain.dx[1],
+                                patch.xb[2] + (k + uni(rng)) * grid.domain.dx[2]},
+                               {vth * nrm(rng), vth * nrm(rng), vth * nrm(rng)},
+                               1.,
+                               kind};
+              injp(prt);
+            }
+          }
+        }
+      }
+    }
+  } // injector flushes here
+
+  // initial state for the oracle
+  std::vector<psc_b200::Particle> prts0;
+  std::vector<uint32_t> off0;
+  mprts.get(prts0, off0);
+  std::vector<float> flds0 = mflds.download(0, PSC_B200_NR_FIELDS);
+
+  psc_b200::PscParamsB200 prm;
+  prm.sort_interval = 2;
+  prm.marder_interval = 0;
+  prm.fused = fused;
+  psc_b200::ChecksParamsB200 cprm;
+  cprm.continuity_every_step = 1;
+  cprm.continuity_threshold = 1e-4;
+  psc_b200::Step<Config> step(grid, mflds, mprts, prm, cprm);
+  step.initialize();
+  double max_cont = 0.;
+  for (int n = 0; n < n_steps; n++) {
+    step();
+    max_cont = std::fmax(max_cont, step.checks().continuity.last_max_err);
+  }
+
+  // accessor vocabulary (const_accessor_simple.hxx:47-81)
+  double sum_w = 0.;
+  {
+    auto acc = mprts.accessor();
+    for (int p = 0; p < grid.n_patches(); p++) {
+      for (auto prt : acc[p]) {
+        sum_w += prt.w();
+        auto pos = prt.position();
+        if (!(pos[1] >= grid.patches[p].xb[1] - 1e-3 && pos[1] <= grid.patches[p].xe[1] + 1e-3)) {
+          std::fprintf(stderr, "particle outside its patch\n");
+          return 2;
+        }
+      }
+    }
+  }
+
+  std::vector<psc_b200::Particle> prts1;
+  std::vector<uint32_t> off1;
+  mprts.get(prts1, off1);
+  std::vector<float> flds1 = mflds.download(0, PSC_B200_NR_FIELDS);
+  auto en = psc_b200::energies(mprts);
+
+  FILE* f = std::fopen(out.c_str(), "wb");
+  if (!f) {
+    return 3;
+  }
+  auto wr = [&](const void* p, size_t n) { std::fwrite(p, 1, n, f); };
+  int hdr[8] = {grid.n_patches(), (int)prts0.size(), (int)prts1.size(), (int)flds0.size(),
+                grid.domain.gdims[0], grid.domain.gdims[1], grid.domain.gdims[2], n_steps};
+  wr(hdr, sizeof(hdr));
+  wr(off0.data(), off0.size() * 4);
+  wr(prts0.data(), prts0.size() * 32);
+  wr(flds0.data(), flds0.size() * 4);
+  wr(off1.data(), off1.size() * 4);
+  wr(prts1.data(), prts1.size() * 32);
+  wr(flds1.data(), flds1.size() * 4);
+  double tail[10] = {max_cont, sum_w, en[0], en[1], en[2], en[3], en[4], en[5], en[6], en[7]};
+  wr(tail, sizeof(tail));
+  std::fclose(f);
+  std::printf("ok: %zu particles, %d steps, continuity %.3g, sum w %.1f\n", prts1.size(), n_steps,
+              max_cont, sum_w);
+  return 0;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc < 5) {
+    std::fprintf(stderr, "usage: %s out.bin xyz|yz n_steps fused\n", argv[0]);
+    return 1;
+  }
+  bool yz = std::strcmp(argv[2], "yz") == 0;
+  int n_steps = std::atoi(argv[3]);
+  bool fused = std::atoi(argv[4]) != 0;
+  return yz ? run<mini::dim_yz>(argv[1], true, n_steps, fused)
+            : run<mini::dim_xyz>(argv[1], false, n_steps, fused);
+}

@@ -145,3 +145,27 @@ int hc_grid_info(const psc_b200_grid_desc* desc, int* n_patches, int* patch_begi
   return 0;
 }
 }
+
+extern "C" {
+
+// neighbour table of this rank: for every local patch and each of the 27 directions the
+// global neighbour patch (-1 none) and its owner rank -- the host logic the NCCL halo and
+// particle exchanges are planned from (GridHost::neighbor_patch / rank_of_patch)
+int hc_neighbor_table(const psc_b200_grid_desc* desc, int* nei_gp, int* nei_rank)
+{
+  GridHost g;
+  std::string err;
+  if (!grid_setup(*desc, g, err)) {
+    return -1;
+  }
+  for (int p = 0; p < g.n_patches; p++) {
+    for (int di = 0; di < 27; di++) {
+      int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+      int gp = g.neighbor_patch(g.patch_begin + p, dir);
+      nei_gp[p * 27 + di] = gp;
+      nei_rank[p * 27 + di] = gp >= 0 ? g.rank_of_patch(gp) : -1;
+    }
+  }
+  return g.n_patches;
+}
+}

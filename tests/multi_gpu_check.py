@@ -32,7 +32,7 @@ def gather_obj(obj, rank, world):
     return out
 
 
-def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None):
+def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None, balance_step=None):
     og = ol.Grid(dt=0.35, kinds=KINDS, nicell=8, **gkw)
     npg = og.n_patches
     if n_by_rank is None:
@@ -81,6 +81,21 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
         L.po_bndf_fill_ghosts_H(G, ol.ptr(rf))
         L.po_fill_ghosts(G, ol.ptr(rf), 9, 6, 9)
         psc.step()
+        if balance_step is not None and _ == balance_step:
+            # Balance::operator(): loads -> best_mapping -> whole patches move between GPUs
+            loads = (np.diff(ro) + 1.0 * og.n_cells).astype(np.float64)
+            new_n = np.zeros(world, dtype=np.int32)
+            cap = np.ones(world)
+            L.po_best_mapping(world, ol.ptr(cap), npg, ol.ptr(loads), ol.ptr(new_n))
+            changed = grid.balance(1.0)
+            assert changed == (list(new_n) != list(n_by_rank)), (changed, new_n, n_by_rank)
+            assert grid.n_patches() == new_n[rank], (grid.n_patches(), new_n)
+            assert grid.patch_begin() == int(np.sum(new_n[:rank]))
+            n_by_rank = [int(x) for x in new_n]
+            rank_of_patch = np.repeat(np.arange(world), n_by_rank).astype(np.int32)
+            # the operator types re-attach to the new decomposition (psc_balance_generation_cnt)
+            mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+            psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=fused)
     if fused:
         L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None)  # the fused step already did the next sort
     gp, go = mprts.get()
@@ -130,6 +145,10 @@ def main():
     uneven = [npg - 3 * (world - 1)] + [3] * (world - 1)
     ok = run_case("xyz_uneven_ranks", cases["xyz_periodic_slabs"], rank, world, local_rank, True,
                   n_by_rank=uneven) and ok
+    # load balancing: start uneven, rebalance after the first step, keep stepping
+    for fused in (False, True):
+        ok = run_case("xyz_balance_after_step1", cases["xyz_periodic_slabs"], rank, world, local_rank,
+                      fused, n_steps=4, n_by_rank=uneven, balance_step=0) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()

@@ -99,6 +99,8 @@ def lib():
         L.po_gauss.restype = C.c_double
         L.po_marder_correct.argtypes = [G, P, P, P, C.c_double, C.c_int]
         L.po_energies.argtypes = [G, P, P, P, P]
+        L.po_best_mapping.argtypes = [C.c_int, P, C.c_int, P, P]
+        L.po_get_loads.argtypes = [G, P, C.c_double, P]
         L.po_describe.restype = C.c_char_p
         _lib = L
     return _lib

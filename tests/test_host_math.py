@@ -94,3 +94,40 @@ def test_bnd_classify_matches_process_patch(dim, bc):
                     out.append(p2[sel])
     got = np.concatenate(out)
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("n_ranks,n_patches", [(1, 5), (2, 2), (3, 17), (8, 64), (8, 9), (5, 1536)])
+def test_best_mapping_matches_reference_bisection(n_ranks, n_patches):
+    """psc_b200_best_mapping (pure host function of the C ABI) vs the oracle's restatement
+    of best_mapping_recursive (psc_balance_impl.hxx:99-160); the reference's own test
+    (test_balance.cxx:234-253) only prints the mapping, so this is pinned by restatement"""
+    import psc_b200
+    L = psc_b200.load()
+    rng = np.random.default_rng(n_ranks * 1000 + n_patches)
+    for trial in range(20):
+        loads = rng.uniform(0.1, 100., size=n_patches) ** (1 + trial % 3)
+        cap = np.ones(n_ranks)
+        got = np.zeros(n_ranks, dtype=np.int32)
+        ref = np.zeros(n_ranks, dtype=np.int32)
+        assert L.psc_b200_best_mapping(n_ranks, ol.ptr(cap), n_patches, ol.ptr(loads), ol.ptr(got)) == 0
+        ol.lib().po_best_mapping(n_ranks, ol.ptr(cap), n_patches, ol.ptr(loads), ol.ptr(ref))
+        assert got.tolist() == ref.tolist()
+        assert got.sum() == n_patches and got.min() >= 1
+
+
+def test_best_mapping_known_answer():
+    """equal loads split evenly; one heavy patch gets a rank to itself"""
+    import psc_b200
+    L = psc_b200.load()
+    out = np.zeros(4, dtype=np.int32)
+    cap = np.ones(4)
+    loads = np.ones(8)
+    assert L.psc_b200_best_mapping(4, ol.ptr(cap), 8, ol.ptr(loads), ol.ptr(out)) == 0
+    assert out.tolist() == [2, 2, 2, 2]
+    loads = np.array([1., 1., 1., 100., 1., 1., 1., 1.])
+    assert L.psc_b200_best_mapping(4, ol.ptr(cap), 8, ol.ptr(loads), ol.ptr(out)) == 0
+    assert out.sum() == 8 and out.min() >= 1
+    # the heavy patch (index 3) sits alone or nearly alone on its rank
+    start = np.concatenate([[0], np.cumsum(out)])
+    r = np.searchsorted(start, 3, side="right") - 1
+    assert out[r] <= 2
