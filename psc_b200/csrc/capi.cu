@@ -248,6 +248,7 @@ static void ctx_destroy(Ctx* c)
     cudaFree(c->xi4[b]);
     cudaFree(c->pxi4[b]);
   }
+  lazy_release(c);
   cudaFree(c->d_off);
   cudaFree(c->d_cell_off);
   cudaFree(c->d_cell_off_alt);
@@ -280,8 +281,35 @@ static int push_mprts(Ctx* c)
 // Psc::step (src/include/psc.hxx:321-486) without collisions / injection / output
 static int step(Ctx* c, const psc_b200_step_params* prm)
 {
-  if (prm->sort && !c->sorted) {
+  // lazy path (lazy.cuh): the store stays a set of per-cell segments from step to step;
+  // push + deposit + boundary exchange + sort are one pass over the particles
+  const bool lazy_ok = prm->sort && c->opt_fused_sort && c->opt_lazy && c->opt_tiled && !c->comm &&
+                       !prm->checks && prm->marder_loop <= 0 && c->n_prts > 0;
+  if (!lazy_ok) {
+    PSC_TRY(store_ready(c));
+  }
+  if (prm->sort && !c->sorted && !c->lazy) {
     PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
+  }
+  if (lazy_ok) {
+    PSC_TRY(lazy_prepare(c));
+    PSC_TRY(c->opt_fma ? push_lazy_fast(c) : push_lazy_exact(c)); // :389 (+ :412, :356 of the next step)
+    PSC_TRY(lazy_finish(c));
+    PSC_TRY(bndf_add_ghosts_J(c));                       // :417
+    PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
+    if (prm->push_fields) {
+      PSC_TRY(push_H(c, .5)); // :426
+      PSC_TRY(bndf_fill_ghosts_H(c));
+      PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+      PSC_TRY(push_E(c, 1.)); // :439
+      PSC_TRY(bndf_fill_ghosts_E(c));
+      PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
+      PSC_TRY(push_H(c, .5)); // :461
+      PSC_TRY(bndf_fill_ghosts_H(c));
+      PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+    }
+    return 0;
   }
   if (prm->checks) {
     PSC_TRY(check_continuity_begin(c)); // :379-384
@@ -401,12 +429,12 @@ int psc_b200_get_ldims(const psc_b200_ctx* ctx, int ldims[3], int ibn[3])
 
 int psc_b200_mprts_set(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
 {
-  GUARD(return prts_set(c, prts, n_by_patch);)
+  GUARD(c->lazy = false; return prts_set(c, prts, n_by_patch);)
 }
 
 int psc_b200_mprts_inject(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
 {
-  GUARD(return prts_inject(c, prts, n_by_patch);)
+  GUARD(PSC_TRY(store_ready(c)); return prts_inject(c, prts, n_by_patch);)
 }
 
 int psc_b200_mprts_size(psc_b200_ctx* ctx, uint64_t* n_total)
@@ -421,12 +449,12 @@ int psc_b200_mprts_size_by_patch(psc_b200_ctx* ctx, uint32_t* n_by_patch)
 
 int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts, uint32_t* off)
 {
-  GUARD(return prts_get(c, prts, off);)
+  GUARD(PSC_TRY(store_ready(c)); return prts_get(c, prts, off);)
 }
 
 int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth, uint64_t seed)
 {
-  GUARD(return prts_setup_thermal(c, ppc, vth, seed);)
+  GUARD(c->lazy = false; return prts_setup_thermal(c, ppc, vth, seed);)
 }
 
 int psc_b200_mflds_create(psc_b200_ctx* ctx, int n_comps, int* field_id)
@@ -456,17 +484,17 @@ int psc_b200_mflds_fill(psc_b200_ctx* ctx, int id, int m, float value)
 
 int psc_b200_push_mprts(psc_b200_ctx* ctx)
 {
-  GUARD(return push_mprts(c);)
+  GUARD(PSC_TRY(store_ready(c)); return push_mprts(c);)
 }
 
 int psc_b200_sort(psc_b200_ctx* ctx)
 {
-  GUARD(return sort_mprts(c);)
+  GUARD(PSC_TRY(store_ready(c)); return sort_mprts(c);)
 }
 
 int psc_b200_bnd_particles(psc_b200_ctx* ctx)
 {
-  GUARD(return bnd_particles(c);)
+  GUARD(PSC_TRY(store_ready(c)); return bnd_particles(c);)
 }
 
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
@@ -506,32 +534,32 @@ int psc_b200_push_H(psc_b200_ctx* ctx, double dt_fac)
 
 int psc_b200_marder(psc_b200_ctx* ctx, double diffusion, int loop)
 {
-  GUARD(return marder(c, diffusion, loop);)
+  GUARD(PSC_TRY(store_ready(c)); return marder(c, diffusion, loop);)
 }
 
 int psc_b200_moment_rho_1st_nc(psc_b200_ctx* ctx, int field_id)
 {
-  GUARD(return moment_rho_1st_nc(c, field_id);)
+  GUARD(PSC_TRY(store_ready(c)); return moment_rho_1st_nc(c, field_id);)
 }
 
 int psc_b200_check_continuity_begin(psc_b200_ctx* ctx)
 {
-  GUARD(return check_continuity_begin(c);)
+  GUARD(PSC_TRY(store_ready(c)); return check_continuity_begin(c);)
 }
 
 int psc_b200_check_continuity_end(psc_b200_ctx* ctx, double* max_err)
 {
-  GUARD(return check_continuity_end(c, max_err);)
+  GUARD(PSC_TRY(store_ready(c)); return check_continuity_end(c, max_err);)
 }
 
 int psc_b200_check_gauss(psc_b200_ctx* ctx, double* max_err)
 {
-  GUARD(return check_gauss(c, max_err);)
+  GUARD(PSC_TRY(store_ready(c)); return check_gauss(c, max_err);)
 }
 
 int psc_b200_energies(psc_b200_ctx* ctx, double out[8])
 {
-  GUARD(PSC_TRY(field_energies(c, out)); PSC_TRY(prts_energies(c, out + 6));
+  GUARD(PSC_TRY(store_ready(c)); PSC_TRY(field_energies(c, out)); PSC_TRY(prts_energies(c, out + 6));
         if (c->comm) { PSC_TRY(comm_allreduce_sum(c, out, 8)); } return 0;)
 }
 
@@ -561,7 +589,7 @@ int psc_b200_nccl_init(psc_b200_ctx* ctx, const void* id128)
 
 int psc_b200_balance(psc_b200_ctx* ctx, double factor_fields, int* changed)
 {
-  GUARD(return balance(c, factor_fields, changed);)
+  GUARD(PSC_TRY(store_ready(c)); return balance(c, factor_fields, changed);)
 }
 
 int psc_b200_best_mapping(int n_ranks, const double* capability, int n_patches,
@@ -595,6 +623,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "tile_z") { c->opt_tile[2] = v; }
     else if (n == "profile") { c->opt_profile = v; }
     else if (n == "fused_sort") { c->opt_fused_sort = v; }
+    else if (n == "lazy") { c->opt_lazy = v; }
     else { return fail("unknown option " + n); }
     return 0;)
 }
@@ -610,6 +639,8 @@ int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
     else if (n == "capacity") { *value = (double)c->cap; }
     else if (n == "n_slots") { *value = c->n_slots; }
     else if (n == "fused_steps") { *value = (double)c->n_fused; }
+    else if (n == "lazy_steps") { *value = (double)c->n_lazy; }
+    else if (n == "lazy_movers") { *value = (double)c->lz_mov_used; }
     else if (n == "fused_fallbacks") { *value = (double)c->n_fused_fallback; }
     else { return fail("unknown stat " + n); }
     return 0;)

@@ -100,6 +100,7 @@ struct Ctx
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
+  int opt_lazy = 0;        // step(): never materialise the sort (lazy.cuh); needs fused_sort
 
   // ---- particles
   float4* xi4[2] = {nullptr, nullptr};
@@ -119,6 +120,23 @@ struct Ctx
   uint32_t* d_cell_off_alt = nullptr; // written by the fused boundary+sort pass
   uint64_t n_fused_fallback = 0;
   uint64_t n_dropped = 0;        // absorbed at open/absorbing walls so far
+
+  // ---- lazy store (lazy.cuh): when `lazy` is set, xi4/pxi4[cur] hold per-cell runs
+  // (stayers at the front) delimited by d_vprev, mvx/mvp[cur] the movers grouped by
+  // (cell, class), lz_*[cur] the metadata, and d_cell_off the offsets of the cell-ordered
+  // sequence the store stands for (h_off / n_prts describe that sequence)
+  bool lazy = false;
+  uint64_t n_lazy = 0;           // steps taken on the lazy path
+  float4* mvx[2] = {nullptr, nullptr};
+  float4* mvp[2] = {nullptr, nullptr};
+  size_t mov_cap = 0;
+  uint32_t* lz_ncen[2] = {nullptr, nullptr};
+  uint32_t* lz_mbase[2] = {nullptr, nullptr};
+  uint16_t* lz_pre[2] = {nullptr, nullptr};
+  uint32_t* d_vprev = nullptr;   // run offsets of the lazy store [nct + 1]
+  uint32_t* lz_newpop = nullptr; // [nct + 1]
+  uint32_t* lz_counter = nullptr;
+  uint32_t lz_mov_used = 0;      // movers stored by the last lazy push
 
   // ---- per-patch tables (device)
   pm::PatchBnd* d_patch_bnd = nullptr; // n_patches
@@ -190,6 +208,18 @@ int sort_mprts(Ctx* c);
 int sort_pairs(Ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
                size_t n, int key_bits, bool iota_vals, bool* result_in_alt);
 int fused_bnd_sort(Ctx* c); // boundary exchange + sort of a pushed, previously sorted store
+// lazy store (lazy.cuh)
+int lazy_prepare(Ctx* c);      // allocations + per-step clears; false path when not applicable
+int lazy_finish(Ctx* c);       // after the lazy push: scan populations, rotate the buffers
+int lazy_materialize(Ctx* c);  // lazy store -> cell-ordered store (sorted = true)
+void lazy_release(Ctx* c);
+int push_lazy_exact(Ctx* c);
+int push_lazy_fast(Ctx* c);
+// every operator that reads the particle store directly calls this first
+inline int store_ready(Ctx* c)
+{
+  return c->lazy ? lazy_materialize(c) : 0;
+}
 
 // ---- bndp.cu
 int bnd_particles(Ctx* c);

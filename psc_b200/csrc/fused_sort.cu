@@ -26,7 +26,7 @@
 // If any particle breaks the precondition (moved more than one cell, leaves for another
 // rank) a flag is raised and the caller falls back to bnd_particles() + sort_mprts();
 // the source store is never modified here.
-#include "fs_classify.cuh"
+#include "lazy.cuh"
 
 #include <algorithm>
 
@@ -619,6 +619,220 @@ int fused_bnd_sort(Ctx* c)
   c->pushed_from_sorted = false;
   c->n_fused++;
   return prts_upload_off(c);
+}
+
+// ====================================================================== lazy store
+
+namespace
+{
+
+// lazy store -> cell-ordered store: every cell's segments copied back to back (the read
+// side of k_push_lazy without the push).  One warp per LZ_UNIT consecutive cells.
+constexpr int MZ_WARPS = 8;
+
+__global__ void __launch_bounds__(MZ_WARPS * 32)
+  k_lz_materialize(GridDev G, const int* __restrict__ nei_patch, LzIn in, const uint32_t* __restrict__ v,
+                   float4* __restrict__ xo, float4* __restrict__ po, uint32_t* __restrict__ flags)
+{
+  __shared__ LzSeg tab_s[MZ_WARPS][LZ_TAB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t g0 = (blockIdx.x * MZ_WARPS + warp) * LZ_UNIT;
+  if (g0 >= in.nct) {
+    return;
+  }
+  const int nc = min((uint32_t)LZ_UNIT, in.nct - g0);
+  LzSeg* tab = tab_s[warp];
+  int n_ent = 0;
+  uint32_t vbase = 0;
+  for (int j = 0; j < nc; j++) {
+    const uint32_t g = g0 + j;
+    const int p = g / G.n_cells;
+    const int s = g - p * G.n_cells;
+    const int c0 = s % G.ldims[0], c1 = (s / G.ldims[0]) % G.ldims[1], c2 = s / (G.ldims[0] * G.ldims[1]);
+    uint32_t len, addr, vstart, total;
+    int src, eidx, ne;
+    lz_cell_segments(G, nei_patch, in, p, c0, c1, c2, lane, len, addr, src, vstart, eidx, ne, total);
+    if (len) {
+      tab[n_ent + eidx] = LzSeg{(vbase + vstart) | ((uint32_t)src << 28), addr};
+    }
+    if (lane == 0 && total != v[g + 1] - v[g]) {
+      atomicExch(&flags[0], 1u);
+    }
+    n_ent += ne;
+    vbase += total;
+  }
+  __syncwarp();
+  const uint32_t out0 = v[g0];
+  for (uint32_t i = lane; i < vbase; i += 32) {
+    int src;
+    uint32_t addr;
+    lz_lookup(tab, n_ent, i, src, addr);
+    const float4* sx = src == LZ_SRC_B ? in.bx : (src == LZ_SRC_M ? in.mx : in.rx);
+    const float4* sp = src == LZ_SRC_B ? in.bp : (src == LZ_SRC_M ? in.mp : in.rp);
+    xo[out0 + i] = sx[addr];
+    po[out0 + i] = sp[addr];
+  }
+}
+
+} // namespace
+
+void lazy_release(Ctx* c)
+{
+  for (int b = 0; b < 2; b++) {
+    cudaFree(c->mvx[b]);
+    cudaFree(c->mvp[b]);
+    cudaFree(c->lz_ncen[b]);
+    cudaFree(c->lz_mbase[b]);
+    cudaFree(c->lz_pre[b]);
+    c->mvx[b] = c->mvp[b] = nullptr;
+    c->lz_ncen[b] = c->lz_mbase[b] = nullptr;
+    c->lz_pre[b] = nullptr;
+  }
+  cudaFree(c->d_vprev);
+  cudaFree(c->lz_newpop);
+  cudaFree(c->lz_counter);
+  c->d_vprev = c->lz_newpop = c->lz_counter = nullptr;
+  c->mov_cap = 0;
+  c->lazy = false;
+}
+
+// allocations (first use / growth) and the per-step clears of the lazy push
+int lazy_prepare(Ctx* c)
+{
+  const GridDev& G = c->gd;
+  const size_t nct = (size_t)G.n_cells * G.n_patches;
+  if (!c->lz_newpop) {
+    for (int b = 0; b < 2; b++) {
+      PSC_CUDA_TRY(cudaMalloc(&c->lz_ncen[b], nct * sizeof(uint32_t)));
+      PSC_CUDA_TRY(cudaMalloc(&c->lz_mbase[b], nct * sizeof(uint32_t)));
+      PSC_CUDA_TRY(cudaMalloc(&c->lz_pre[b], nct * LZ_PLANES * sizeof(uint16_t)));
+    }
+    PSC_CUDA_TRY(cudaMalloc(&c->d_vprev, (nct + 1) * sizeof(uint32_t)));
+    PSC_CUDA_TRY(cudaMalloc(&c->lz_newpop, (nct + 1) * sizeof(uint32_t)));
+    PSC_CUDA_TRY(cudaMalloc(&c->lz_counter, 4 * sizeof(uint32_t)));
+  }
+  // mover arrays: every particle of a small store may move, a quarter of a big one; grown
+  // when the last step used more than half
+  size_t want = c->n_prts <= (size_t(1) << 26) ? (size_t)c->n_prts : (size_t)c->n_prts / 4;
+  want = std::max<size_t>(want, 1024);
+  if (c->lz_mov_used > c->mov_cap / 2) {
+    want = std::max(want, std::min<size_t>(c->n_prts, 2 * c->mov_cap));
+  }
+  if (want > c->mov_cap) {
+    want += want / 8;
+    float4 *nx[2], *np[2];
+    for (int b = 0; b < 2; b++) {
+      PSC_CUDA_TRY(cudaMalloc(&nx[b], want * sizeof(float4)));
+      PSC_CUDA_TRY(cudaMalloc(&np[b], want * sizeof(float4)));
+    }
+    if (c->lazy && c->lz_mov_used) { // live movers of the current store
+      PSC_CUDA_TRY(cudaMemcpyAsync(nx[c->cur], c->mvx[c->cur], c->lz_mov_used * sizeof(float4),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+      PSC_CUDA_TRY(cudaMemcpyAsync(np[c->cur], c->mvp[c->cur], c->lz_mov_used * sizeof(float4),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+      PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    for (int b = 0; b < 2; b++) {
+      cudaFree(c->mvx[b]);
+      cudaFree(c->mvp[b]);
+      c->mvx[b] = nx[b];
+      c->mvp[b] = np[b];
+    }
+    c->mov_cap = want;
+  }
+  PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));
+  PSC_CUDA_TRY(cudaMemsetAsync(c->scr[11].p, 0, 4 * sizeof(uint32_t), c->stream));
+  PSC_CUDA_TRY(cudaMemsetAsync(c->lz_newpop, 0, (nct + 1) * sizeof(uint32_t), c->stream));
+  PSC_CUDA_TRY(cudaMemsetAsync(c->lz_counter, 0, 4 * sizeof(uint32_t), c->stream));
+  return 0;
+}
+
+// after k_push_lazy: populations -> offsets of the next cell-ordered sequence; the written
+// buffers become the current store
+int lazy_finish(Ctx* c)
+{
+  const GridDev& G = c->gd;
+  const size_t nct = (size_t)G.n_cells * G.n_patches;
+  const int np = G.n_patches;
+  uint32_t* flags = c->scr[11].as<uint32_t>();
+  {
+    KernelScope ks(c, "lazy_scan");
+    PSC_TRY(scan_exclusive<uint32_t>(c, LoadArr<uint32_t>{c->lz_newpop}, nct, c->d_cell_off_alt, c->scr[2]));
+    k_patch_offsets<<<div_up(np + 1, 128), 128, 0, c->stream>>>(c->d_cell_off_alt, np, G.n_cells, flags + 4);
+    c->n_launches++;
+  }
+  std::vector<uint32_t> h(np + 1 + 4);
+  uint32_t used = 0;
+  PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaMemcpyAsync(&used, c->lz_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  PSC_TRY(check_launch(c, "lazy_finish"));
+  if (h[3]) {
+    return fail("lazy push: mover array overflow (more than a quarter of the particles changed cell in one step)");
+  }
+  if (h[0]) {
+    return fail("lazy push: a particle moved more than one cell in a step (dt exceeds the cell size) or left "
+                "for a patch that is not local; rerun with option lazy = 0");
+  }
+  // rotate: B' -> B, V -> vprev, scan -> V
+  c->cur ^= 1;
+  uint32_t* t = c->d_vprev;
+  c->d_vprev = c->d_cell_off;
+  c->d_cell_off = c->d_cell_off_alt;
+  c->d_cell_off_alt = t;
+  for (int p = 0; p <= np; p++) {
+    c->h_off[p] = h[4 + p];
+  }
+  c->n_prts = c->h_off[np];
+  c->n_dropped += h[1];
+  c->lz_mov_used = used;
+  c->lazy = true;
+  c->sorted = false;
+  c->pushed_from_sorted = false;
+  c->counts_valid = false;
+  c->n_lazy++;
+  return prts_upload_off(c);
+}
+
+int lazy_materialize(Ctx* c)
+{
+  if (!c->lazy) {
+    return 0;
+  }
+  const GridDev& G = c->gd;
+  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+  const int b = c->cur;
+  LzIn in{};
+  in.vprev = c->d_vprev;
+  in.ncen = c->lz_ncen[b];
+  in.mbase = c->lz_mbase[b];
+  in.pre = c->lz_pre[b];
+  in.bx = c->xi4[b], in.bp = c->pxi4[b];
+  in.mx = c->mvx[b], in.mp = c->mvp[b];
+  in.nct = nct;
+  if (c->n_prts > c->cap) {
+    return fail("lazy store: particle capacity exceeded");
+  }
+  uint32_t* flags = c->scr[11].as<uint32_t>();
+  PSC_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), c->stream));
+  {
+    KernelScope ks(c, "lazy_materialize");
+    k_lz_materialize<<<div_up(nct, MZ_WARPS * LZ_UNIT), MZ_WARPS * 32, 0, c->stream>>>(
+      G, c->d_nei_patch, in, c->d_cell_off, c->xi4[b ^ 1], c->pxi4[b ^ 1], flags);
+    c->n_launches++;
+  }
+  uint32_t h = 0;
+  PSC_CUDA_TRY(cudaMemcpyAsync(&h, flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  PSC_TRY(check_launch(c, "lazy_materialize"));
+  if (h) {
+    return fail("lazy store inconsistent: segment lengths do not add up to the cell populations");
+  }
+  c->cur ^= 1;
+  c->lazy = false;
+  c->sorted = true; // ordered by (patch, cell), d_cell_off describes it
+  c->pushed_from_sorted = false;
+  return 0;
 }
 
 } // namespace psc_b200

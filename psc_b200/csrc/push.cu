@@ -32,7 +32,7 @@
 // This file is compiled twice: -fmad=false (namespace exact: particle update is
 // bit-identical to PSC's x86-64 build, which has no FMA) and with FMA contraction
 // (namespace fast, within a few ULP).
-#include "fs_classify.cuh"
+#include "lazy.cuh"
 
 #include <algorithm>
 
@@ -739,6 +739,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
 }
 
+#include "push_lazy.cuh"
+
 // ---------------------------------------------------------------- host side
 
 template <int DIM, int DEPOSIT, typename GEO, bool TUNE>
@@ -751,9 +753,9 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
     return -1; // a row's cell boundaries are held one per lane
   }
   // register budget variants (launch bounds); odd geometries get the roomy one only
-  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)  3: (224, 3)  4: (192, 3)
+  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)  3: (384, 2)  4: (192, 3)
   if (TUNE) {
-    lb = threads > 256 ? 2 : (threads == 224 ? 3 : (threads == 192 ? 4 : (c->opt_min_blocks == 2 ? 1 : 0)));
+    lb = threads > 384 ? 2 : (threads == 384 ? 3 : (threads == 192 ? 4 : (c->opt_min_blocks == 2 ? 1 : 0)));
   } else {
     threads = std::min(threads, 256);
   }
@@ -780,7 +782,7 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
       } else if (lb == 2) {                                                                       \
         PSC_LAUNCH(TM, CN, 512, 1);                                                               \
       } else if (lb == 3) {                                                                       \
-        PSC_LAUNCH(TM, CN, 224, 3);                                                               \
+        PSC_LAUNCH(TM, CN, 384, 2);                                                               \
       } else if (lb == 4) {                                                                       \
         PSC_LAUNCH(TM, CN, 192, 3);                                                               \
       } else {                                                                                    \
@@ -893,7 +895,115 @@ static int push_dim(Ctx* c)
   return check_launch(c, "push_general");
 }
 
+
+// ---- lazy store: push + deposit + (implicit) boundary exchange and sort
+template <int DIM, int DEPOSIT>
+static int push_lazy_dim(Ctx* c)
+{
+  const GridDev& G = c->gd;
+  const bool xyz = DIM == pm::DIM_XYZ;
+  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+  LazyArgs A{};
+  A.v = c->d_cell_off;
+  A.flds = c->fld(0);
+  A.slot_len = c->fld_slot_len(0);
+  A.flags = c->scr[11].as<uint32_t>();
+  A.same_dxi = 1;
+  for (int d = 0; d < 3; d++) {
+    A.same_dxi = A.same_dxi && G.pc.dxi[d] == G.pc.dxi_idx[d];
+  }
+  A.tab = FsTables{c->d_patch_bnd, c->d_nei_patch};
+  const int b = c->cur;
+  A.in.vprev = c->lazy ? c->d_vprev : c->d_cell_off;
+  A.in.ncen = c->lazy ? c->lz_ncen[b] : nullptr;
+  A.in.mbase = c->lz_mbase[b];
+  A.in.pre = c->lz_pre[b];
+  A.in.rstart = nullptr;
+  A.in.rcount = nullptr;
+  A.in.bx = c->xi4[b], A.in.bp = c->pxi4[b];
+  A.in.mx = c->mvx[b], A.in.mp = c->mvp[b];
+  A.in.rx = nullptr, A.in.rp = nullptr;
+  A.in.nct = nct;
+  A.out.bx = c->xi4[b ^ 1], A.out.bp = c->pxi4[b ^ 1];
+  A.out.mx = c->mvx[b ^ 1], A.out.mp = c->mvp[b ^ 1];
+  A.out.ncen = c->lz_ncen[b ^ 1];
+  A.out.mbase = c->lz_mbase[b ^ 1];
+  A.out.pre = c->lz_pre[b ^ 1];
+  A.out.newpop = c->lz_newpop;
+  A.out.mov_counter = c->lz_counter;
+  A.out.mov_cap = (uint32_t)std::min<size_t>(c->mov_cap, 0xffffffffu);
+
+  GeoStatic<DIM> gs{};
+  bool stat = !(c->opt_tile[0] > 0 || c->opt_tile[1] > 0 || c->opt_tile[2] > 0);
+  for (int d = 0; d < 3; d++) {
+    bool inv = (!xyz && d == 0);
+    gs.nt_[d] = inv ? 1 : G.ldims[d] / gs.t(d);
+    stat = stat && (inv || (G.ibn[d] == 2 && G.ldims[d] % gs.t(d) == 0));
+  }
+  const int threads = 384;
+  auto smem_of = [&](int nodes) {
+    return (size_t)((9 * nodes + 3) & ~3) * sizeof(float) +
+           (size_t)(threads / 32) * ((QCAP * 2 + 64) * sizeof(float4) + LZ_TAB * sizeof(LzSeg) +
+                                     LZ_UNIT * 32 * sizeof(uint16_t));
+  };
+  if (stat) {
+    int cd = xyz ? 0 : 1;
+    bool tma = c->opt_tma && (G.im[cd] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0) && (G.fld_len % 4 == 0);
+    int tiles = gs.nt(0) * gs.nt(1) * gs.nt(2) * G.n_patches;
+    size_t smem_bytes = smem_of(gs.sm());
+    KernelScope ks(c, "push_lazy");
+    if (tma) {
+      auto kern = k_push_lazy<DIM, DEPOSIT, GeoStatic<DIM>, true, 384, 2>;
+      PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gs, A);
+    } else {
+      auto kern = k_push_lazy<DIM, DEPOSIT, GeoStatic<DIM>, false, 384, 2>;
+      PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gs, A);
+    }
+  } else {
+    GeoDyn gd{};
+    int def[3] = {xyz ? 8 : 1, xyz ? 8 : 16, xyz ? 8 : 16};
+    for (int d = 0; d < 3; d++) {
+      bool inv = (!xyz && d == 0);
+      int t = c->opt_tile[d] > 0 ? c->opt_tile[d] : def[d];
+      gd.t_[d] = inv ? 1 : std::min(t, G.ldims[d]);
+      gd.nt_[d] = (G.ldims[d] + gd.t_[d] - 1) / gd.t_[d];
+      gd.f_[d] = inv ? 1 : gd.t_[d] + 3;
+      gd.g_[d] = inv ? 0 : 1;
+    }
+    int tiles = gd.nt(0) * gd.nt(1) * gd.nt(2) * G.n_patches;
+    size_t smem_bytes = smem_of(gd.sm());
+    if (smem_bytes > 220 * 1024) {
+      return fail("lazy push: tile does not fit in shared memory");
+    }
+    KernelScope ks(c, "push_lazy_dyn");
+    auto kern = k_push_lazy<DIM, DEPOSIT, GeoDyn, false, 384, 2>;
+    PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gd, A);
+  }
+  c->n_launches++;
+  return check_launch(c, "push_lazy");
+}
+
 } // namespace PUSH_VARIANT
+
+// lazy path: the caller (capi.cu step) has run lazy_prepare(); lazy_finish() follows
+int PUSH_CAT(push_lazy_, PUSH_VARIANT)(Ctx* c)
+{
+  using namespace PUSH_VARIANT;
+  PSC_TRY(flds_zero(c, 0, pm::JXI, pm::JXI + 3));
+#ifdef PUSH_PROBE
+  return push_lazy_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
+#else
+  if (c->gd.dim == pm::DIM_XYZ) {
+    return push_lazy_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
+  } else if (c->gd.deposit == pm::DEPOSIT_VAR1) {
+    return push_lazy_dim<pm::DIM_YZ, pm::DEPOSIT_VAR1>(c);
+  }
+  return push_lazy_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c);
+#endif
+}
 
 int PUSH_CAT(push_mprts_, PUSH_VARIANT)(Ctx* c)
 {
