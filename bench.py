@@ -182,7 +182,7 @@ def run_b200(args, rank, world, local_rank):
         dist.broadcast(idt, 0)
         grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
     for k, v in (("fma", args.fma), ("tiled", args.tiled), ("tma", args.tma),
-                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort), ("lazy", args.lazy)):
+                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort), ("gapped", args.gapped), ("gap_slack", args.gap_slack)):
         grid.set_option(k, v)
     if args.tile:
         grid.set_option("tile", args.tile)
@@ -271,7 +271,7 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                for k, v in prof.items()}
-    push_key = next((k for k in ("push_lazy", "push_tiled_tma", "push_tiled", "push_general") if k in prof), None)
+    push_key = next((k for k in ("push_gap", "push_tiled_tma", "push_tiled", "push_general") if k in prof), None)
     roofline = None
     if push_key:
         t_push = prof[push_key][0] / max(1, prof[push_key][1]) * 1e-3
@@ -308,7 +308,7 @@ def run_b200(args, rank, world, local_rank):
                    "particles_per_gpu": n_prts, "cells_per_gpu": n ** 3, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
                    "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma, "warp_reduce": args.warp_reduce,
-                                                "fused_sort": args.fused_sort, "lazy": args.lazy}},
+                                                "fused_sort": args.fused_sort, "gapped": args.gapped}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "kernels": kernels,
     }
@@ -330,7 +330,8 @@ def main():
     ap.add_argument("--tma", type=int, default=1)
     ap.add_argument("--warp-reduce", dest="warp_reduce", type=int, default=1)
     ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
-    ap.add_argument("--lazy", type=int, default=0, help="lazy particle store (no sort pass)")
+    ap.add_argument("--gapped", type=int, default=1, help="gapped particle store (no sort pass)")
+    ap.add_argument("--gap-slack", dest="gap_slack", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--min-blocks", dest="min_blocks", type=int, default=0)

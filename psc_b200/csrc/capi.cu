@@ -248,7 +248,7 @@ static void ctx_destroy(Ctx* c)
     cudaFree(c->xi4[b]);
     cudaFree(c->pxi4[b]);
   }
-  lazy_release(c);
+  gap_release(c);
   cudaFree(c->d_off);
   cudaFree(c->d_cell_off);
   cudaFree(c->d_cell_off_alt);
@@ -281,20 +281,30 @@ static int push_mprts(Ctx* c)
 // Psc::step (src/include/psc.hxx:321-486) without collisions / injection / output
 static int step(Ctx* c, const psc_b200_step_params* prm)
 {
-  // lazy path (lazy.cuh): the store stays a set of per-cell segments from step to step;
-  // push + deposit + boundary exchange + sort are one pass over the particles
-  const bool lazy_ok = prm->sort && c->opt_fused_sort && c->opt_lazy && c->opt_tiled && !c->comm &&
-                       !prm->checks && prm->marder_loop <= 0 && c->n_prts > 0;
-  if (!lazy_ok) {
+  // gapped store (gap.cuh): push + deposit + boundary exchange + sort are one pass over the
+  // particles; the store stays gapped from step to step
+  bool gap_ok = prm->sort && c->opt_fused_sort && c->opt_gapped && c->opt_tiled && !c->comm &&
+                !prm->checks && prm->marder_loop <= 0 && c->n_prts > 0;
+  if (!gap_ok) {
     PSC_TRY(store_ready(c));
   }
-  if (prm->sort && !c->sorted && !c->lazy) {
+  if (prm->sort && !c->sorted && !c->gapped) {
     PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
   }
-  if (lazy_ok) {
-    PSC_TRY(lazy_prepare(c));
-    PSC_TRY(c->opt_fma ? push_lazy_fast(c) : push_lazy_exact(c)); // :389 (+ :412, :356 of the next step)
-    PSC_TRY(lazy_finish(c));
+  if (gap_ok) {
+    PSC_TRY(gap_prepare(c, &gap_ok));
+  }
+  if (gap_ok) {
+    bool redo = false;
+    PSC_TRY(c->opt_fma ? push_gap_fast(c) : push_gap_exact(c)); // :389 (+ :412, :356 of the next step)
+    PSC_TRY(gap_finish(c, &redo));
+    if (redo) {
+      // nothing was committed (the push never writes the store it reads): eager path
+      PSC_TRY(store_ready(c));
+      gap_ok = false;
+    }
+  }
+  if (gap_ok) {
     PSC_TRY(bndf_add_ghosts_J(c));                       // :417
     PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
     PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
@@ -429,7 +439,7 @@ int psc_b200_get_ldims(const psc_b200_ctx* ctx, int ldims[3], int ibn[3])
 
 int psc_b200_mprts_set(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
 {
-  GUARD(c->lazy = false; return prts_set(c, prts, n_by_patch);)
+  GUARD(c->gapped = false; return prts_set(c, prts, n_by_patch);)
 }
 
 int psc_b200_mprts_inject(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
@@ -454,7 +464,7 @@ int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts, uint32_t* off)
 
 int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth, uint64_t seed)
 {
-  GUARD(c->lazy = false; return prts_setup_thermal(c, ppc, vth, seed);)
+  GUARD(c->gapped = false; return prts_setup_thermal(c, ppc, vth, seed);)
 }
 
 int psc_b200_mflds_create(psc_b200_ctx* ctx, int n_comps, int* field_id)
@@ -623,7 +633,8 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "tile_z") { c->opt_tile[2] = v; }
     else if (n == "profile") { c->opt_profile = v; }
     else if (n == "fused_sort") { c->opt_fused_sort = v; }
-    else if (n == "lazy") { c->opt_lazy = v; }
+    else if (n == "gapped") { c->opt_gapped = v; }
+    else if (n == "gap_slack") { c->opt_gap_slack = v; }
     else { return fail("unknown option " + n); }
     return 0;)
 }
@@ -639,8 +650,10 @@ int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
     else if (n == "capacity") { *value = (double)c->cap; }
     else if (n == "n_slots") { *value = c->n_slots; }
     else if (n == "fused_steps") { *value = (double)c->n_fused; }
-    else if (n == "lazy_steps") { *value = (double)c->n_lazy; }
-    else if (n == "lazy_movers") { *value = (double)c->lz_mov_used; }
+    else if (n == "gap_steps") { *value = (double)c->n_gap_steps; }
+    else if (n == "gap_relayouts") { *value = (double)c->n_gap_relayouts; }
+    else if (n == "gap_redone") { *value = (double)c->n_gap_redone; }
+    else if (n == "gap_movers") { *value = (double)c->g_mov_used; }
     else if (n == "fused_fallbacks") { *value = (double)c->n_fused_fallback; }
     else { return fail("unknown stat " + n); }
     return 0;)

@@ -100,7 +100,8 @@ struct Ctx
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
-  int opt_lazy = 0;        // step(): never materialise the sort (lazy.cuh); needs fused_sort
+  int opt_gapped = 1;      // step(): gapped store (gap.cuh), no sort pass; needs fused_sort
+  int opt_gap_slack = 0;   // free slots behind every cell's run, 0 = half the mean population
 
   // ---- particles
   float4* xi4[2] = {nullptr, nullptr};
@@ -121,22 +122,26 @@ struct Ctx
   uint64_t n_fused_fallback = 0;
   uint64_t n_dropped = 0;        // absorbed at open/absorbing walls so far
 
-  // ---- lazy store (lazy.cuh): when `lazy` is set, xi4/pxi4[cur] hold per-cell runs
-  // (stayers at the front) delimited by d_vprev, mvx/mvp[cur] the movers grouped by
-  // (cell, class), lz_*[cur] the metadata, and d_cell_off the offsets of the cell-ordered
-  // sequence the store stands for (h_off / n_prts describe that sequence)
-  bool lazy = false;
-  uint64_t n_lazy = 0;           // steps taken on the lazy path
-  float4* mvx[2] = {nullptr, nullptr};
-  float4* mvp[2] = {nullptr, nullptr};
+  // ---- gapped store (gap.cuh): when `gapped` is set, xi4/pxi4[cur] hold one run per cell,
+  // [g_start[t], g_start[t] + g_n[t]) inside the slab [g_v[t], g_v[t + 1]); h_off / n_prts
+  // describe the contiguous patch-by-patch sequence the store stands for
+  bool gapped = false;
+  uint64_t n_gap_steps = 0;      // steps taken on the gapped path
+  uint64_t n_gap_relayouts = 0;  // ... of which re-laid the store out (a slab overflowed)
+  uint64_t n_gap_redone = 0;     // steps redone on the eager path
+  uint32_t* g_v = nullptr;       // slab starts [nct + 1]
+  uint32_t* g_v_alt = nullptr;
+  uint32_t* g_start[2] = {nullptr, nullptr}; // [0]: current runs, [1]: written by the step
+  uint32_t* g_n[2] = {nullptr, nullptr};
+  uint32_t* g_nstay = nullptr;   // stayers per cell of the last push
+  uint32_t* g_ctl = nullptr;     // GAP_CTL_WORDS control words
+  uint32_t g_rl = 8;             // slots kept free in front of the stayers (adaptive)
+  uint32_t g_slack = 0;          // slots kept free behind a run at layout time
+  float4* mvx = nullptr;         // mover list
+  float4* mvp = nullptr;
+  uint4* mvtag = nullptr;
   size_t mov_cap = 0;
-  uint32_t* lz_ncen[2] = {nullptr, nullptr};
-  uint32_t* lz_mbase[2] = {nullptr, nullptr};
-  uint16_t* lz_pre[2] = {nullptr, nullptr};
-  uint32_t* d_vprev = nullptr;   // run offsets of the lazy store [nct + 1]
-  uint32_t* lz_newpop = nullptr; // [nct + 1]
-  uint32_t* lz_counter = nullptr;
-  uint32_t lz_mov_used = 0;      // movers stored by the last lazy push
+  uint32_t g_mov_used = 0;       // mover slots used by the last gapped push
 
   // ---- per-patch tables (device)
   pm::PatchBnd* d_patch_bnd = nullptr; // n_patches
@@ -208,17 +213,17 @@ int sort_mprts(Ctx* c);
 int sort_pairs(Ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
                size_t n, int key_bits, bool iota_vals, bool* result_in_alt);
 int fused_bnd_sort(Ctx* c); // boundary exchange + sort of a pushed, previously sorted store
-// lazy store (lazy.cuh)
-int lazy_prepare(Ctx* c);      // allocations + per-step clears; false path when not applicable
-int lazy_finish(Ctx* c);       // after the lazy push: scan populations, rotate the buffers
-int lazy_materialize(Ctx* c);  // lazy store -> cell-ordered store (sorted = true)
-void lazy_release(Ctx* c);
-int push_lazy_exact(Ctx* c);
-int push_lazy_fast(Ctx* c);
+// gapped store (gap.cuh)
+int gap_prepare(Ctx* c, bool* ok); // allocations, layout, per-step clears; *ok = false: not applicable
+int gap_finish(Ctx* c, bool* redo); // offsets, mover placement, commit; *redo: take the eager path
+int gap_compact(Ctx* c);           // gapped store -> contiguous cell-ordered store (sorted = true)
+void gap_release(Ctx* c);
+int push_gap_exact(Ctx* c);
+int push_gap_fast(Ctx* c);
 // every operator that reads the particle store directly calls this first
 inline int store_ready(Ctx* c)
 {
-  return c->lazy ? lazy_materialize(c) : 0;
+  return c->gapped ? gap_compact(c) : 0;
 }
 
 // ---- bndp.cu

@@ -26,7 +26,7 @@
 // If any particle breaks the precondition (moved more than one cell, leaves for another
 // rank) a flag is raised and the caller falls back to bnd_particles() + sort_mprts();
 // the source store is never modified here.
-#include "lazy.cuh"
+#include "gap.cuh"
 
 #include <algorithm>
 
@@ -109,9 +109,11 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
 // ascending source-cell order = descending delta.  All counters are loaded before the
 // first one is rewritten, so the (up to 27) loads are in flight together instead of
 // forming a load -> store -> load chain (the array is updated in place).
+template <bool CENTER_INFO = false>
 __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_t* __restrict__ cnt,
                                          int ps, int c0, int c1, int c2, int t0, int t1, int t2,
-                                         uint32_t& total)
+                                         uint32_t& total, uint32_t* n_lower = nullptr,
+                                         uint32_t* n_center = nullptr)
 {
   const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
   const size_t pbase = (size_t)ps * G.n_cells;
@@ -138,6 +140,10 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_
       int z = c2 - e2 + t2 * ld2, y = c1 - e1 + t1 * ld1, x = c0 - e0 + t0 * ld0;
       cnt[(size_t)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct + pbase +
           (size_t)((z * ld1 + y) * ld0 + x)] = total;
+      if (CENTER_INFO && k == 13) {
+        *n_lower = total;
+        *n_center = n[k];
+      }
       total += n[k];
     }
   }
@@ -621,215 +627,397 @@ int fused_bnd_sort(Ctx* c)
   return prts_upload_off(c);
 }
 
-// ====================================================================== lazy store
+
+// ====================================================================== gapped store
 
 namespace
 {
 
-// lazy store -> cell-ordered store: every cell's segments copied back to back (the read
-// side of k_push_lazy without the push).  One warp per LZ_UNIT consecutive cells.
-constexpr int MZ_WARPS = 8;
-
-__global__ void __launch_bounds__(MZ_WARPS * 32)
-  k_lz_materialize(GridDev G, const int* __restrict__ nei_patch, LzIn in, const uint32_t* __restrict__ v,
-                   float4* __restrict__ xo, float4* __restrict__ po, uint32_t* __restrict__ flags)
+// per target cell: like k_fs_offsets, but the positions are relative to the start of the
+// cell's run, the run is anchored so that the stayers (already written by the push) sit at
+// V + RL, and a slab that cannot take its arrivals is flagged
+__global__ void k_gap_offsets(GridDev G, const int* __restrict__ nei_patch, uint32_t nct,
+                              uint32_t* __restrict__ cnt, const uint32_t* __restrict__ v, uint32_t rl,
+                              uint32_t* __restrict__ new_start, uint32_t* __restrict__ new_n,
+                              uint32_t* __restrict__ nstay, uint32_t* __restrict__ ctl)
 {
-  __shared__ LzSeg tab_s[MZ_WARPS][LZ_TAB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t g0 = (blockIdx.x * MZ_WARPS + warp) * LZ_UNIT;
-  if (g0 >= in.nct) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nct) {
     return;
   }
-  const int nc = min((uint32_t)LZ_UNIT, in.nct - g0);
-  LzSeg* tab = tab_s[warp];
-  int n_ent = 0;
-  uint32_t vbase = 0;
-  for (int j = 0; j < nc; j++) {
-    const uint32_t g = g0 + j;
-    const int p = g / G.n_cells;
-    const int s = g - p * G.n_cells;
-    const int c0 = s % G.ldims[0], c1 = (s / G.ldims[0]) % G.ldims[1], c2 = s / (G.ldims[0] * G.ldims[1]);
-    uint32_t len, addr, vstart, total;
-    int src, eidx, ne;
-    lz_cell_segments(G, nei_patch, in, p, c0, c1, c2, lane, len, addr, src, vstart, eidx, ne, total);
-    if (len) {
-      tab[n_ent + eidx] = LzSeg{(vbase + vstart) | ((uint32_t)src << 28), addr};
+  const int q = g / G.n_cells;
+  const int c = g - q * G.n_cells;
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  const int c0 = c % ld0, c1 = (c / ld0) % ld1, c2 = c / (ld0 * ld1);
+  uint32_t total = 0, nl = 0, nc = 0;
+  fs_route<true>(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total, &nl, &nc);
+  const bool lo0 = c0 == 0, hi0 = c0 == ld0 - 1, lo1 = c1 == 0, hi1 = c1 == ld1 - 1, lo2 = c2 == 0,
+             hi2 = c2 == ld2 - 1;
+  if (lo0 | hi0 | lo1 | hi1 | lo2 | hi2) {
+    for (int t2 = 1; t2 >= -1; t2--) {
+      if ((t2 == 1 && !lo2) || (t2 == -1 && !hi2)) {
+        continue;
+      }
+      for (int t1 = 1; t1 >= -1; t1--) {
+        if ((t1 == 1 && !lo1) || (t1 == -1 && !hi1)) {
+          continue;
+        }
+        for (int t0 = 1; t0 >= -1; t0--) {
+          if ((t0 == 1 && !lo0) || (t0 == -1 && !hi0) || (t0 == 0 && t1 == 0 && t2 == 0)) {
+            continue;
+          }
+          int dip = ((-t2 + 1) * 3 + (-t1 + 1)) * 3 + (-t0 + 1);
+          int ps = nei_patch[q * 27 + dip];
+          if (ps >= 0) {
+            fs_route(G, nct, cnt, ps, c0, c1, c2, t0, t1, t2, total);
+          }
+        }
+      }
     }
-    if (lane == 0 && total != v[g + 1] - v[g]) {
-      atomicExch(&flags[0], 1u);
-    }
-    n_ent += ne;
-    vbase += total;
   }
-  __syncwarp();
-  const uint32_t out0 = v[g0];
-  for (uint32_t i = lane; i < vbase; i += 32) {
-    int src;
-    uint32_t addr;
-    lz_lookup(tab, n_ent, i, src, addr);
-    const float4* sx = src == LZ_SRC_B ? in.bx : (src == LZ_SRC_M ? in.mx : in.rx);
-    const float4* sp = src == LZ_SRC_B ? in.bp : (src == LZ_SRC_M ? in.mp : in.rp);
-    xo[out0 + i] = sx[addr];
-    po[out0 + i] = sp[addr];
+  const uint32_t v0 = v[g], v1 = v[g + 1];
+  new_start[g] = v0 + rl - nl; // (meaningless when nl > rl: the store is re-laid out then)
+  new_n[g] = total;
+  nstay[g] = nc;
+  if (nl > rl || rl - nl + total > v1 - v0) {
+    atomicExch(&ctl[GAP_CTL_OVERFLOW], 1u);
+  }
+  if (nl > rl) {
+    atomicMax(&ctl[GAP_CTL_MAX_NL], nl);
   }
 }
+
+// per patch: population of the new store (one CTA per patch)
+__global__ void __launch_bounds__(256)
+  k_gap_patch_sums(const uint32_t* __restrict__ n, int n_cells, uint32_t* __restrict__ out)
+{
+  __shared__ uint32_t ws[8];
+  const uint32_t* np = n + (size_t)blockIdx.x * n_cells;
+  uint32_t s = 0;
+  for (int i = threadIdx.x; i < n_cells; i += 256) {
+    s += np[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(FULL, s, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ws[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < 8; k++) {
+      t += ws[k];
+    }
+    out[blockIdx.x] = t;
+  }
+}
+
+// one thread per mover slot: the record goes to start[target] + offset of its (source
+// cell, class) group inside the target's run + its rank inside the group
+__global__ void k_gap_place(uint32_t n_slots, const uint4* __restrict__ mtag, const float4* __restrict__ mx,
+                            const float4* __restrict__ mp, const uint32_t* __restrict__ start,
+                            const uint32_t* __restrict__ rel, float4* __restrict__ xo,
+                            float4* __restrict__ po)
+{
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) {
+    return;
+  }
+  const uint4 t = mtag[s];
+  if (!t.w) {
+    return;
+  }
+  const uint32_t dst = __ldg(&start[t.x]) + __ldg(&rel[t.y]) + t.z;
+  xo[dst] = mx[s];
+  po[dst] = mp[s];
+}
+
+// copy one run per cell: [src_start[t] (+ src_bias), + n[t]) -> [dst_start[t] + dst_bias (+
+// dst_shift[t]), ...).  One warp per GC_CPW consecutive cells.
+constexpr int GC_WARPS = 8;
+constexpr int GC_CPW = 8;
+
+__global__ void __launch_bounds__(GC_WARPS * 32)
+  k_gap_copy_runs(uint32_t nct, const uint32_t* __restrict__ src_start, uint32_t src_bias,
+                  const uint32_t* __restrict__ n, const uint32_t* __restrict__ dst_start, uint32_t dst_bias,
+                  const uint32_t* __restrict__ dst_shift_a, const uint32_t* __restrict__ dst_shift_b,
+                  const float4* __restrict__ xi, const float4* __restrict__ pi, float4* __restrict__ xo,
+                  float4* __restrict__ po, uint32_t* __restrict__ new_start)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t g0 = (blockIdx.x * GC_WARPS + (threadIdx.x >> 5)) * GC_CPW;
+  for (int k = 0; k < GC_CPW; k++) {
+    const uint32_t g = g0 + k;
+    if (g >= nct) {
+      return;
+    }
+    const uint32_t cnt = n[g], src = src_start[g] + src_bias;
+    uint32_t dst = dst_start[g] + dst_bias;
+    if (new_start && lane == 0) {
+      new_start[g] = dst; // the run begins where the lower movers will be placed
+    }
+    if (dst_shift_a) {
+      // + (a - b): the lower movers of the cell come first (a = V + RL, b = old run start)
+      dst += dst_shift_a[g] + src_bias - dst_shift_b[g];
+    }
+    for (uint32_t i = lane; i < cnt; i += 32) {
+      xo[dst + i] = xi[src + i];
+      po[dst + i] = pi[src + i];
+    }
+  }
+}
+
+__global__ void k_gap_runs_of_sorted(uint32_t nct, const uint32_t* __restrict__ cell_off,
+                                     uint32_t* __restrict__ start, uint32_t* __restrict__ n)
+{
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nct) {
+    const uint32_t a = cell_off[g];
+    start[g] = a;
+    n[g] = cell_off[g + 1] - a;
+  }
+}
+
+// slab size of a cell = RL + population + slack
+struct SlabSize
+{
+  const uint32_t* n;
+  uint32_t extra;
+  __device__ __forceinline__ uint32_t operator()(size_t i) const { return n[i] + extra; }
+};
 
 } // namespace
 
-void lazy_release(Ctx* c)
+void gap_release(Ctx* c)
 {
+  cudaFree(c->g_v);
+  cudaFree(c->g_v_alt);
   for (int b = 0; b < 2; b++) {
-    cudaFree(c->mvx[b]);
-    cudaFree(c->mvp[b]);
-    cudaFree(c->lz_ncen[b]);
-    cudaFree(c->lz_mbase[b]);
-    cudaFree(c->lz_pre[b]);
-    c->mvx[b] = c->mvp[b] = nullptr;
-    c->lz_ncen[b] = c->lz_mbase[b] = nullptr;
-    c->lz_pre[b] = nullptr;
+    cudaFree(c->g_start[b]);
+    cudaFree(c->g_n[b]);
+    c->g_start[b] = c->g_n[b] = nullptr;
   }
-  cudaFree(c->d_vprev);
-  cudaFree(c->lz_newpop);
-  cudaFree(c->lz_counter);
-  c->d_vprev = c->lz_newpop = c->lz_counter = nullptr;
+  cudaFree(c->g_nstay);
+  cudaFree(c->g_ctl);
+  cudaFree(c->mvx);
+  cudaFree(c->mvp);
+  cudaFree(c->mvtag);
+  c->g_v = c->g_v_alt = c->g_nstay = c->g_ctl = nullptr;
+  c->mvx = c->mvp = nullptr;
+  c->mvtag = nullptr;
   c->mov_cap = 0;
-  c->lazy = false;
+  c->gapped = false;
 }
 
-// allocations (first use / growth) and the per-step clears of the lazy push
-int lazy_prepare(Ctx* c)
+static uint32_t gap_slack(const Ctx* c, size_t nct)
+{
+  if (c->opt_gap_slack > 0) {
+    return (uint32_t)c->opt_gap_slack;
+  }
+  // half the mean population: room for the Poisson-level drift of a cell's population
+  size_t mean = c->n_prts / std::max<size_t>(nct, 1);
+  return (uint32_t)std::min<size_t>(64, std::max<size_t>(8, mean / 2));
+}
+
+// allocations (first use / growth), layout of the store the push writes, per-step clears.
+// *ok = false (and nothing changed): this step cannot take the gapped path.
+int gap_prepare(Ctx* c, bool* ok)
 {
   const GridDev& G = c->gd;
   const size_t nct = (size_t)G.n_cells * G.n_patches;
-  if (!c->lz_newpop) {
-    for (int b = 0; b < 2; b++) {
-      PSC_CUDA_TRY(cudaMalloc(&c->lz_ncen[b], nct * sizeof(uint32_t)));
-      PSC_CUDA_TRY(cudaMalloc(&c->lz_mbase[b], nct * sizeof(uint32_t)));
-      PSC_CUDA_TRY(cudaMalloc(&c->lz_pre[b], nct * LZ_PLANES * sizeof(uint16_t)));
-    }
-    PSC_CUDA_TRY(cudaMalloc(&c->d_vprev, (nct + 1) * sizeof(uint32_t)));
-    PSC_CUDA_TRY(cudaMalloc(&c->lz_newpop, (nct + 1) * sizeof(uint32_t)));
-    PSC_CUDA_TRY(cudaMalloc(&c->lz_counter, 4 * sizeof(uint32_t)));
+  *ok = false;
+  if (nct * FS_PLANES >= (size_t(1) << 32) || c->n_prts == 0) {
+    return 0;
   }
-  // mover arrays: every particle of a small store may move, a quarter of a big one; grown
+  if (!c->gapped) {
+    // entering from a cell-ordered contiguous store: lay out the slabs around its runs
+    const uint32_t slack = gap_slack(c, nct);
+    const size_t slots = (size_t)c->n_prts + nct * ((size_t)c->g_rl + slack) + c->g_rl + 1024;
+    if (slots >= (size_t(1) << 32)) {
+      return 0;
+    }
+    if (slots > c->cap) {
+      // the store grows one pair of buffers at a time (prts_reserve): is there room for
+      // the slack, the mover list and the counters?
+      size_t free_b = 0, total_b = 0;
+      PSC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      const size_t have = free_b + c->cap * 4 * sizeof(float4);
+      const size_t need = slots * 4 * sizeof(float4) + (size_t)c->n_prts / 8 * 48 + nct * (FS_PLANES + 8) * 4 +
+                          (size_t(2) << 30);
+      if (need > have) {
+        c->opt_gapped = 0; // not enough memory for the slack: stay on the eager path
+        return 0;
+      }
+      PSC_TRY(prts_reserve(c, slots));
+    }
+    c->g_slack = slack;
+  }
+  if (!c->g_ctl) {
+    PSC_CUDA_TRY(cudaMalloc(&c->g_v, (nct + 1) * sizeof(uint32_t)));
+    PSC_CUDA_TRY(cudaMalloc(&c->g_v_alt, (nct + 1) * sizeof(uint32_t)));
+    for (int b = 0; b < 2; b++) {
+      PSC_CUDA_TRY(cudaMalloc(&c->g_start[b], nct * sizeof(uint32_t)));
+      PSC_CUDA_TRY(cudaMalloc(&c->g_n[b], nct * sizeof(uint32_t)));
+    }
+    PSC_CUDA_TRY(cudaMalloc(&c->g_nstay, nct * sizeof(uint32_t)));
+    PSC_CUDA_TRY(cudaMalloc(&c->g_ctl, GAP_CTL_WORDS * sizeof(uint32_t)));
+  }
+  // mover list: every particle of a small store may move, an eighth of a big one; grown
   // when the last step used more than half
-  size_t want = c->n_prts <= (size_t(1) << 26) ? (size_t)c->n_prts : (size_t)c->n_prts / 4;
-  want = std::max<size_t>(want, 1024);
-  if (c->lz_mov_used > c->mov_cap / 2) {
-    want = std::max(want, std::min<size_t>(c->n_prts, 2 * c->mov_cap));
+  size_t want = c->n_prts <= (size_t(1) << 24) ? (size_t)c->n_prts + GAP_BATCH * 4096 : (size_t)c->n_prts / 8;
+  if (c->g_mov_used > c->mov_cap / 2) {
+    want = std::max(want, 2 * c->mov_cap);
   }
   if (want > c->mov_cap) {
-    want += want / 8;
-    float4 *nx[2], *np[2];
-    for (int b = 0; b < 2; b++) {
-      PSC_CUDA_TRY(cudaMalloc(&nx[b], want * sizeof(float4)));
-      PSC_CUDA_TRY(cudaMalloc(&np[b], want * sizeof(float4)));
-    }
-    if (c->lazy && c->lz_mov_used) { // live movers of the current store
-      PSC_CUDA_TRY(cudaMemcpyAsync(nx[c->cur], c->mvx[c->cur], c->lz_mov_used * sizeof(float4),
-                                   cudaMemcpyDeviceToDevice, c->stream));
-      PSC_CUDA_TRY(cudaMemcpyAsync(np[c->cur], c->mvp[c->cur], c->lz_mov_used * sizeof(float4),
-                                   cudaMemcpyDeviceToDevice, c->stream));
-      PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    }
-    for (int b = 0; b < 2; b++) {
-      cudaFree(c->mvx[b]);
-      cudaFree(c->mvp[b]);
-      c->mvx[b] = nx[b];
-      c->mvp[b] = np[b];
-    }
+    cudaFree(c->mvx);
+    cudaFree(c->mvp);
+    cudaFree(c->mvtag);
+    c->mvx = c->mvp = nullptr;
+    c->mvtag = nullptr;
+    c->mov_cap = 0;
+    PSC_CUDA_TRY(cudaMalloc(&c->mvx, want * sizeof(float4)));
+    PSC_CUDA_TRY(cudaMalloc(&c->mvp, want * sizeof(float4)));
+    PSC_CUDA_TRY(cudaMalloc(&c->mvtag, want * sizeof(uint4)));
     c->mov_cap = want;
   }
-  PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));
-  PSC_CUDA_TRY(cudaMemsetAsync(c->scr[11].p, 0, 4 * sizeof(uint32_t), c->stream));
-  PSC_CUDA_TRY(cudaMemsetAsync(c->lz_newpop, 0, (nct + 1) * sizeof(uint32_t), c->stream));
-  PSC_CUDA_TRY(cudaMemsetAsync(c->lz_counter, 0, 4 * sizeof(uint32_t), c->stream));
+  if (!c->gapped) {
+    KernelScope ks(c, "gap_layout");
+    k_gap_runs_of_sorted<<<div_up(nct, 256), 256, 0, c->stream>>>((uint32_t)nct, c->d_cell_off, c->g_start[0],
+                                                                   c->g_n[0]);
+    c->n_launches++;
+    PSC_TRY(scan_exclusive<uint32_t>(c, SlabSize{c->g_n[0], c->g_rl + c->g_slack}, nct, c->g_v, c->scr[2]));
+  }
+  PSC_CUDA_TRY(cudaMemsetAsync(c->g_ctl, 0, GAP_CTL_WORDS * sizeof(uint32_t), c->stream));
+  *ok = true;
   return 0;
 }
 
-// after k_push_lazy: populations -> offsets of the next cell-ordered sequence; the written
-// buffers become the current store
-int lazy_finish(Ctx* c)
+// after the gapped push: group offsets, overflow check, (re-layout,) mover placement,
+// commit.  *redo = true: nothing was committed, the step has to take the eager path (the
+// store the push read is intact).
+int gap_finish(Ctx* c, bool* redo)
 {
   const GridDev& G = c->gd;
   const size_t nct = (size_t)G.n_cells * G.n_patches;
   const int np = G.n_patches;
-  uint32_t* flags = c->scr[11].as<uint32_t>();
+  *redo = false;
+  uint32_t* cnt = c->scr[9].as<uint32_t>();
+  uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, dropped, remote, -, new patch sizes...]
   {
-    KernelScope ks(c, "lazy_scan");
-    PSC_TRY(scan_exclusive<uint32_t>(c, LoadArr<uint32_t>{c->lz_newpop}, nct, c->d_cell_off_alt, c->scr[2]));
-    k_patch_offsets<<<div_up(np + 1, 128), 128, 0, c->stream>>>(c->d_cell_off_alt, np, G.n_cells, flags + 4);
+    KernelScope ks(c, "gap_offsets");
+    k_gap_offsets<<<div_up(nct, 128), 128, 0, c->stream>>>(G, c->d_nei_patch, (uint32_t)nct, cnt, c->g_v,
+                                                           c->g_rl, c->g_start[1], c->g_n[1], c->g_nstay,
+                                                           c->g_ctl);
+    k_gap_patch_sums<<<np, 256, 0, c->stream>>>(c->g_n[1], G.n_cells, flags + 4);
+    c->n_launches += 2;
+  }
+  std::vector<uint32_t> h(np + 4);
+  uint32_t ctl[GAP_CTL_WORDS];
+  PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaMemcpyAsync(ctl, c->g_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  PSC_TRY(check_launch(c, "gap_offsets"));
+  c->counts_valid = false;
+  c->g_mov_used = ctl[GAP_CTL_MOVERS];
+  if (h[0] || h[2] || ctl[GAP_CTL_M_FULL]) {
+    // a particle moved further than one cell / left for another rank / the mover list is
+    // full: nothing has been committed
+    *redo = true;
+    c->n_gap_redone++;
+    if (ctl[GAP_CTL_M_FULL]) {
+      c->g_mov_used = (uint32_t)std::min<size_t>(c->mov_cap, 0xffffffffu); // grows the list next time
+    }
+    return 0;
+  }
+  size_t n_new = 0;
+  for (int p = 0; p < np; p++) {
+    n_new += h[4 + p];
+  }
+  const uint32_t n_slots = std::min<uint32_t>(ctl[GAP_CTL_MOVERS], (uint32_t)std::min<size_t>(c->mov_cap, 0xffffffffu));
+  float4 *xo = c->xi_alt(), *po = c->pxi_alt();
+  bool relayout = ctl[GAP_CTL_OVERFLOW] != 0;
+  if (relayout) {
+    // fresh slabs around the new populations; the stayers move from the buffer the push
+    // wrote back into the one it read (consumed), behind the room of their lower movers
+    uint32_t rl_new = c->g_rl;
+    if (ctl[GAP_CTL_MAX_NL] > c->g_rl) {
+      rl_new = 2 * ctl[GAP_CTL_MAX_NL];
+    }
+    uint32_t slack = gap_slack(c, nct);
+    size_t slots = n_new + nct * ((size_t)rl_new + slack) + rl_new + 1024;
+    if (slots > c->cap) {
+      // shrink the slack to what the buffers hold
+      size_t fixed = n_new + nct * (size_t)rl_new + rl_new + 1024;
+      if (fixed + nct * 4 > c->cap) {
+        // no room at all: this step is redone on the eager path, which regrows the store
+        *redo = true;
+        c->n_gap_redone++;
+        return 0;
+      }
+      slack = (uint32_t)((c->cap - fixed) / nct);
+    }
+    KernelScope ks(c, "gap_relayout");
+    PSC_TRY(scan_exclusive<uint32_t>(c, SlabSize{c->g_n[1], rl_new + slack}, nct, c->g_v_alt, c->scr[2]));
+    // stayers: [V + RL, + nstay) of the written buffer -> V' + RL' + n_L of the read one;
+    // n_L = (V + RL) - start_new
+    k_gap_copy_runs<<<div_up(nct, GC_WARPS * GC_CPW), GC_WARPS * 32, 0, c->stream>>>(
+      (uint32_t)nct, c->g_v, c->g_rl, c->g_nstay, c->g_v_alt, rl_new, c->g_v, c->g_start[1], xo, po, c->xi(),
+      c->pxi(), c->g_start[0]);
+    c->n_launches++;
+    std::swap(c->g_v, c->g_v_alt);
+    std::swap(c->g_n[0], c->g_n[1]);
+    // g_start[0] = V' + RL' was written by the copy; the new store is the buffer that was read
+    xo = c->xi();
+    po = c->pxi();
+    c->g_rl = rl_new;
+    c->g_slack = slack;
+    c->n_gap_relayouts++;
+  } else {
+    std::swap(c->g_start[0], c->g_start[1]);
+    std::swap(c->g_n[0], c->g_n[1]);
+    c->cur ^= 1;
+  }
+  if (n_slots) {
+    KernelScope ks(c, "gap_place");
+    k_gap_place<<<div_up(n_slots, 256), 256, 0, c->stream>>>(n_slots, c->mvtag, c->mvx, c->mvp, c->g_start[0], cnt,
+                                                             xo, po);
     c->n_launches++;
   }
-  std::vector<uint32_t> h(np + 1 + 4);
-  uint32_t used = 0;
-  PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaMemcpyAsync(&used, c->lz_counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  PSC_TRY(check_launch(c, "lazy_finish"));
-  if (h[3]) {
-    return fail("lazy push: mover array overflow (more than a quarter of the particles changed cell in one step)");
-  }
-  if (h[0]) {
-    return fail("lazy push: a particle moved more than one cell in a step (dt exceeds the cell size) or left "
-                "for a patch that is not local; rerun with option lazy = 0");
-  }
-  // rotate: B' -> B, V -> vprev, scan -> V
-  c->cur ^= 1;
-  uint32_t* t = c->d_vprev;
-  c->d_vprev = c->d_cell_off;
-  c->d_cell_off = c->d_cell_off_alt;
-  c->d_cell_off_alt = t;
-  for (int p = 0; p <= np; p++) {
-    c->h_off[p] = h[4 + p];
+  PSC_TRY(check_launch(c, "gap_place"));
+  c->h_off[0] = 0;
+  for (int p = 0; p < np; p++) {
+    c->h_off[p + 1] = c->h_off[p] + h[4 + p];
   }
   c->n_prts = c->h_off[np];
   c->n_dropped += h[1];
-  c->lz_mov_used = used;
-  c->lazy = true;
+  c->gapped = true;
   c->sorted = false;
   c->pushed_from_sorted = false;
-  c->counts_valid = false;
-  c->n_lazy++;
+  c->n_gap_steps++;
   return prts_upload_off(c);
 }
 
-int lazy_materialize(Ctx* c)
+// gapped store -> the reference's contiguous patch-by-patch array, ordered by cell
+int gap_compact(Ctx* c)
 {
-  if (!c->lazy) {
+  if (!c->gapped) {
     return 0;
   }
   const GridDev& G = c->gd;
-  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
-  const int b = c->cur;
-  LzIn in{};
-  in.vprev = c->d_vprev;
-  in.ncen = c->lz_ncen[b];
-  in.mbase = c->lz_mbase[b];
-  in.pre = c->lz_pre[b];
-  in.bx = c->xi4[b], in.bp = c->pxi4[b];
-  in.mx = c->mvx[b], in.mp = c->mvp[b];
-  in.nct = nct;
-  if (c->n_prts > c->cap) {
-    return fail("lazy store: particle capacity exceeded");
-  }
-  uint32_t* flags = c->scr[11].as<uint32_t>();
-  PSC_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), c->stream));
+  const size_t nct = (size_t)G.n_cells * G.n_patches;
   {
-    KernelScope ks(c, "lazy_materialize");
-    k_lz_materialize<<<div_up(nct, MZ_WARPS * LZ_UNIT), MZ_WARPS * 32, 0, c->stream>>>(
-      G, c->d_nei_patch, in, c->d_cell_off, c->xi4[b ^ 1], c->pxi4[b ^ 1], flags);
+    KernelScope ks(c, "gap_compact");
+    PSC_TRY(scan_exclusive<uint32_t>(c, LoadArr<uint32_t>{c->g_n[0]}, nct, c->d_cell_off, c->scr[2]));
+    k_gap_copy_runs<<<div_up(nct, GC_WARPS * GC_CPW), GC_WARPS * 32, 0, c->stream>>>(
+      (uint32_t)nct, c->g_start[0], 0u, c->g_n[0], c->d_cell_off, 0u, nullptr, nullptr, c->xi(), c->pxi(),
+      c->xi_alt(), c->pxi_alt(), nullptr);
     c->n_launches++;
   }
-  uint32_t h = 0;
-  PSC_CUDA_TRY(cudaMemcpyAsync(&h, flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
-  PSC_TRY(check_launch(c, "lazy_materialize"));
-  if (h) {
-    return fail("lazy store inconsistent: segment lengths do not add up to the cell populations");
-  }
+  PSC_TRY(check_launch(c, "gap_compact"));
   c->cur ^= 1;
-  c->lazy = false;
+  c->gapped = false;
   c->sorted = true; // ordered by (patch, cell), d_cell_off describes it
   c->pushed_from_sorted = false;
   return 0;

@@ -183,25 +183,28 @@ int prts_reserve(Ctx* c, size_t n)
   if (ncap >= (size_t(1) << 32)) {
     return fail("more than 2^32 particles on one rank (PSC indexes particles with uint)");
   }
-  float4* nx[2];
-  float4* np[2];
-  for (int b = 0; b < 2; b++) {
-    PSC_CUDA_TRY(cudaMalloc(&nx[b], ncap * sizeof(float4)));
-    PSC_CUDA_TRY(cudaMalloc(&np[b], ncap * sizeof(float4)));
-  }
+  // one pair of buffers at a time (the idle pair first), so that the peak is the old
+  // current pair + the new buffers, not twice everything
+  const int cur = c->cur, alt = c->cur ^ 1;
+  cudaFree(c->xi4[alt]);
+  cudaFree(c->pxi4[alt]);
+  c->xi4[alt] = c->pxi4[alt] = nullptr;
+  PSC_CUDA_TRY(cudaMalloc(&c->xi4[alt], ncap * sizeof(float4)));
+  PSC_CUDA_TRY(cudaMalloc(&c->pxi4[alt], ncap * sizeof(float4)));
   if (c->n_prts) {
-    PSC_CUDA_TRY(cudaMemcpyAsync(nx[c->cur], c->xi4[c->cur], c->n_prts * sizeof(float4),
+    PSC_CUDA_TRY(cudaMemcpyAsync(c->xi4[alt], c->xi4[cur], c->n_prts * sizeof(float4),
                                  cudaMemcpyDeviceToDevice, c->stream));
-    PSC_CUDA_TRY(cudaMemcpyAsync(np[c->cur], c->pxi4[c->cur], c->n_prts * sizeof(float4),
+    PSC_CUDA_TRY(cudaMemcpyAsync(c->pxi4[alt], c->pxi4[cur], c->n_prts * sizeof(float4),
                                  cudaMemcpyDeviceToDevice, c->stream));
     PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
   }
-  for (int b = 0; b < 2; b++) {
-    cudaFree(c->xi4[b]);
-    cudaFree(c->pxi4[b]);
-    c->xi4[b] = nx[b];
-    c->pxi4[b] = np[b];
-  }
+  cudaFree(c->xi4[cur]);
+  cudaFree(c->pxi4[cur]);
+  c->xi4[cur] = c->pxi4[cur] = nullptr;
+  c->cap = 0;
+  c->cur = alt; // the data live in the pair that was grown first
+  PSC_CUDA_TRY(cudaMalloc(&c->xi4[cur], ncap * sizeof(float4)));
+  PSC_CUDA_TRY(cudaMalloc(&c->pxi4[cur], ncap * sizeof(float4)));
   c->cap = ncap;
   return 0;
 }

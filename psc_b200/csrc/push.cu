@@ -32,7 +32,7 @@
 // This file is compiled twice: -fmad=false (namespace exact: particle update is
 // bit-identical to PSC's x86-64 build, which has no FMA) and with FMA contraction
 // (namespace fast, within a few ULP).
-#include "lazy.cuh"
+#include "gap.cuh"
 
 #include <algorithm>
 
@@ -370,6 +370,19 @@ struct PushArgs
   uint32_t nct;
   int same_dxi; // 1/float(dx) == float(dx_inv) bitwise: the pusher's cell = the indexer's cell
   FsTables tab;
+  GapPush gap; // GAP variant only (gap.cuh)
+};
+
+// first step of the lane-parallel search for the cell of a virtual particle index
+template <typename GEO, int DIM>
+struct RowSearch
+{
+  static constexpr int top = 16;
+};
+template <int DIM>
+struct RowSearch<GeoStatic<DIM>, DIM>
+{
+  static constexpr int top = GeoStatic<DIM>::t(DIM == pm::DIM_XYZ ? 0 : 1) / 2;
 };
 
 // per-lane deposit of one leaf into the shared J tile (or global when outside it)
@@ -405,9 +418,14 @@ __device__ __forceinline__ void leaf_deposit(const GridDev& G, const GEO& geo, f
 // case.  Particles that leave their cell are parked in a per-warp shared queue and
 // split/deposited 32 at a time, so the divergent Villasenor-Buneman walk runs with full
 // warps.
-template <int DIM, int DEPOSIT, typename GEO, bool TMA, bool COUNT, int MAXT, int MINB>
+//
+// GAP (gap.cuh): the rows are read through per-cell runs (start, n) instead of contiguous
+// offsets, nothing is written in place: stayers go to their final slot of the other
+// buffer, movers (boundary fix-ups applied) to the tagged mover list.
+template <int DIM, int DEPOSIT, typename GEO, bool TMA, bool COUNT, bool GAP, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, PushArgs A)
 {
+  static_assert(!GAP || COUNT, "the gapped store needs the destination counts");
   constexpr int NV = pm::LeafShape<DIM>::NV;
   constexpr int NVP = (DIM == pm::DIM_XYZ) ? 16 : 8;
   constexpr bool XYZ = DIM == pm::DIM_XYZ;
@@ -500,6 +518,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   float4* myQ = sQ + (size_t)warp * QCAP * 2;
   const uint32_t myP = smem_u32(sP + (size_t)warp * 64 + lane);
   int qn = 0; // queued trajectories of this warp (warp-uniform)
+  uint32_t mb_next = 0, mb_end = 0; // GAP: this warp's batch of mover slots (warp-uniform)
 
   // split + deposit `cnt` queued trajectories (entries [qn - cnt, qn)), one per lane
   auto drain = [&](int cnt) {
@@ -548,8 +567,43 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
       rs1 = o[1], rs2 = o[2] + row;
       c0 = rs2 * G.ldims[1] + o[1];
     }
-    // lane j holds the offset of the row's j-th cell boundary
-    const uint32_t myoff = __ldg(&coff[c0 + min(lane, run_cells)]);
+    // lane j holds the offset of the row's j-th cell boundary (GAP: inside the row's
+    // virtual sequence = its cells' runs back to back; my_st = where run j really starts,
+    // my_vo = where the stayers of cell j are written)
+    uint32_t myoff, my_st = 0, my_vo = 0;
+    if constexpr (GAP) {
+      const size_t gc = (size_t)p * G.n_cells + (size_t)(c0 + min(lane, run_cells - 1));
+      const uint32_t nj = lane < run_cells ? __ldg(&A.gap.in_n[gc]) : 0u;
+      my_st = __ldg(&A.gap.in_start[gc]);
+      my_vo = __ldg(&A.gap.out_v[gc]) + A.gap.rl;
+      uint32_t incl = nj;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) {
+          incl += t;
+        }
+      }
+      myoff = incl - nj;
+    } else {
+      myoff = __ldg(&coff[c0 + min(lane, run_cells)]);
+    }
+    // GAP: record iv of the row's virtual sequence -> index into the store
+    auto src_of = [&](uint32_t iv) -> uint32_t {
+      int j = 0;
+#pragma unroll
+      for (int st = RowSearch<GEO, DIM>::top; st >= 1; st >>= 1) {
+        const int jj = j + st;
+        const uint32_t t = __shfl_sync(FULL, myoff, jj & 31);
+        if (jj < run_cells && iv >= t) {
+          j = jj;
+        }
+      }
+      return __shfl_sync(FULL, my_st, j) + (iv - __shfl_sync(FULL, myoff, j));
+    };
+    const float4* const src_x = GAP ? A.gap.in_x : A.xi4;
+    const float4* const src_p = GAP ? A.gap.in_p : A.pxi4;
+    uint32_t vo_cur = GAP ? __shfl_sync(FULL, my_vo, 0) : 0u; // GAP: stayer slots of the current cell
     const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, run_cells);
     int cur = 0;                                     // cell of the row the passes are at
     uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
@@ -563,9 +617,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
 
     // the next chunk travels global -> shared with cp.async while this one is computed
     // (no registers held across the chunk body)
-    if (begin + lane < end) {
-      cp_async16(myP, A.xi4 + begin + lane);
-      cp_async16(myP + 32 * sizeof(float4), A.pxi4 + begin + lane);
+    {
+      const uint32_t a0 = GAP ? src_of(begin + lane) : begin + lane;
+      if (begin + lane < end) {
+        cp_async16(myP, src_x + a0);
+        cp_async16(myP + 32 * sizeof(float4), src_p + a0);
+      }
     }
     cp_async_commit();
     uint32_t base = begin;
@@ -573,10 +630,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
       const uint32_t i = base + lane;
       const bool act = i < end;
       cp_async_wait_all();
-      const float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
-      if (i + 32 < end) {
-        cp_async16(myP, A.xi4 + i + 32);
-        cp_async16(myP + 32 * sizeof(float4), A.pxi4 + i + 32);
+      float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
+      {
+        const uint32_t a1 = GAP ? src_of(i + 32) : i + 32;
+        if (i + 32 < end) {
+          cp_async16(myP, src_x + a1);
+          cp_async16(myP + 32 * sizeof(float4), src_p + a1);
+        }
       }
       cp_async_commit();
       if (qn > QCAP - 32) {
@@ -592,8 +652,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         if (act) {
           float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
           pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+          if constexpr (GAP) {
+            X = make_float4(x[0], x[1], x[2], X.w);
+            U = make_float4(u[0], u[1], u[2], U.w);
+          } else {
+            A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+            A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+          }
           cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
           single = !cross;
           if (single) {
@@ -638,6 +703,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         }
         if (COUNT) {
           int cls = CLS_NONE;
+          uint32_t tcell = 0; // GAP: target cell (rank-wide index)
           if (mine) {
             const int d0 = pos[0] - s0, d1 = pos[1] - s1, d2 = pos[2] - s2;
             const bool ok = (unsigned)pos[0] < (unsigned)G.ldims[0] && (unsigned)pos[1] < (unsigned)G.ldims[1] &&
@@ -645,26 +711,88 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
                             (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
             if (ok) {
               cls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
+              if constexpr (GAP) {
+                tcell = (uint32_t)p * G.n_cells + (uint32_t)((pos[2] * G.ldims[1] + pos[1]) * G.ldims[0] + pos[0]);
+              }
             } else {
-              // patch boundary: the pushed record is re-read (written by this thread above)
-              const float4 Xr = A.xi4[i], Ur = A.pxi4[i];
-              float xx[3] = {Xr.x, Xr.y, Xr.z}, uu[3] = {Ur.x, Ur.y, Ur.z};
-              int q, c;
-              cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
+              int q = 0, c = 0;
+              if constexpr (GAP) {
+                // patch boundary: the record leaves with the boundary fix-ups applied
+                float xx[3] = {X.x, X.y, X.z}, uu[3] = {U.x, U.y, U.z};
+                cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
+                X = make_float4(xx[0], xx[1], xx[2], X.w);
+                U = make_float4(uu[0], uu[1], uu[2], U.w);
+                tcell = (uint32_t)q * G.n_cells + (uint32_t)c;
+              } else {
+                // patch boundary: the pushed record is re-read (written by this thread above)
+                const float4 Xr = A.xi4[i], Ur = A.pxi4[i];
+                float xx[3] = {Xr.x, Xr.y, Xr.z}, uu[3] = {Ur.x, Ur.y, Ur.z};
+                cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
+              }
             }
           }
+          [[maybe_unused]] const unsigned lt = (1u << lane) - 1u;
           unsigned grp = __ballot_sync(FULL, cls == CLS_CENTER);
+          if constexpr (GAP) {
+            // stayers: final slot = rank among the stayers of the cell (old order)
+            const uint32_t r0 = __shfl_sync(FULL, mycount, CLS_CENTER);
+            if (cls == CLS_CENTER) {
+              const uint32_t dst = vo_cur + r0 + __popc(grp & lt);
+              A.gap.out_x[dst] = X;
+              A.gap.out_p[dst] = U;
+            }
+          }
           if (lane == CLS_CENTER) {
             mycount += __popc(grp);
           }
           unsigned rem = __ballot_sync(FULL, mine) & ~grp;
+          uint32_t rank = 0; // GAP: rank inside the (source cell, class) group
           while (rem) {
             const int v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
             grp = __ballot_sync(FULL, cls == v);
+            if constexpr (GAP) {
+              const uint32_t r0 = __shfl_sync(FULL, mycount, v);
+              if (cls == v) {
+                rank = r0 + __popc(grp & lt);
+              }
+            }
             if (lane == v) {
               mycount += __popc(grp);
             }
             rem &= ~grp;
+          }
+          if constexpr (GAP) {
+            // movers: parked in the tagged list, slots handed out GAP_BATCH at a time
+            const bool mover = mine && cls < FS_PLANES && cls != CLS_CENTER;
+            const unsigned mm = __ballot_sync(FULL, mover);
+            if (mm) {
+              const uint32_t nm = __popc(mm), room = mb_end - mb_next;
+              uint32_t nb = 0;
+              if (nm > room) {
+                if (lane == 0) {
+                  nb = atomicAdd(&A.gap.ctl[GAP_CTL_MOVERS], (uint32_t)GAP_BATCH);
+                }
+                nb = __shfl_sync(FULL, nb, 0);
+              }
+              if (mover) {
+                const uint32_t r = __popc(mm & lt);
+                const uint32_t slot = r < room ? mb_next + r : nb + (r - room);
+                if (slot < A.gap.m_cap) {
+                  A.gap.mx[slot] = X;
+                  A.gap.mp[slot] = U;
+                  A.gap.mtag[slot] = make_uint4(tcell, (uint32_t)cls * A.nct + (uint32_t)p * G.n_cells + (uint32_t)(c0 + cur),
+                                                rank, 1u);
+                } else {
+                  atomicExch(&A.gap.ctl[GAP_CTL_M_FULL], 1u);
+                }
+              }
+              if (nm > room) {
+                mb_next = nb + (nm - room);
+                mb_end = nb + GAP_BATCH;
+              } else {
+                mb_next += nm;
+              }
+            }
           }
         }
         if (ce > base + 32) {
@@ -709,6 +837,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         }
         cb = ce;
         ce = __shfl_sync(FULL, myoff, cur + 1);
+        if constexpr (GAP) {
+          vo_cur = __shfl_sync(FULL, my_vo, cur);
+        }
       }
       base += 32;
     } while (base < end);
@@ -719,6 +850,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
   while (qn > 0) {
     drain(min(qn, 32));
+  }
+  if constexpr (GAP) {
+    // slots of the last batch that were not used
+    for (uint32_t sl = mb_next + lane; sl < mb_end && sl < A.gap.m_cap; sl += 32) {
+      A.gap.mtag[sl] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   __syncthreads();
 
@@ -739,12 +876,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
 }
 
-#include "push_lazy.cuh"
-
 // ---------------------------------------------------------------- host side
 
 template <int DIM, int DEPOSIT, typename GEO, bool TUNE>
-static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const PushArgs& A)
+static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, bool gap, const PushArgs& A)
 {
   const GridDev& G = c->gd;
   int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
@@ -764,49 +899,57 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
   if (smem_bytes > 220 * 1024) {
     return -1;
   }
-#define PSC_LAUNCH(TM, CN, MT, MB)                                                                \
+#define PSC_LAUNCH(TM, CN, GP, MT, MB)                                                            \
   do {                                                                                            \
-    auto kern = k_push_tiled<DIM, DEPOSIT, GEO, TM, CN, MT, MB>;                                  \
+    auto kern = k_push_tiled<DIM, DEPOSIT, GEO, TM, CN, GP, MT, MB>;                              \
     PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                       (int)smem_bytes));                                          \
     kern<<<tiles, threads, smem_bytes, c->stream>>>(G, geo, A);                                   \
   } while (0)
 #ifdef PUSH_PROBE
-  PSC_LAUNCH(true, true, PUSH_PROBE_T, PUSH_PROBE_B);
+  PSC_LAUNCH(true, true, PUSH_PROBE_G, PUSH_PROBE_T, PUSH_PROBE_B);
 #else
-#define PSC_LAUNCH_LB(TM, CN)                                                                     \
+#define PSC_LAUNCH_LB(TM, CN, GP)                                                                 \
   do {                                                                                            \
     if constexpr (TUNE) {                                                                         \
       if (lb == 0) {                                                                              \
-        PSC_LAUNCH(TM, CN, 256, 3);                                                               \
+        PSC_LAUNCH(TM, CN, GP, 256, 3);                                                           \
       } else if (lb == 2) {                                                                       \
-        PSC_LAUNCH(TM, CN, 512, 1);                                                               \
+        PSC_LAUNCH(TM, CN, GP, 512, 1);                                                           \
       } else if (lb == 3) {                                                                       \
-        PSC_LAUNCH(TM, CN, 384, 2);                                                               \
+        PSC_LAUNCH(TM, CN, GP, 384, 2);                                                           \
       } else if (lb == 4) {                                                                       \
-        PSC_LAUNCH(TM, CN, 192, 3);                                                               \
+        PSC_LAUNCH(TM, CN, GP, 192, 3);                                                           \
       } else {                                                                                    \
-        PSC_LAUNCH(TM, CN, 256, 2);                                                               \
+        PSC_LAUNCH(TM, CN, GP, 256, 2);                                                           \
       }                                                                                           \
     } else {                                                                                      \
-      PSC_LAUNCH(TM, CN, 256, 2);                                                                 \
+      PSC_LAUNCH(TM, CN, GP, 256, 2);                                                             \
     }                                                                                             \
   } while (0)
-  if (count) {
+  if (gap) {
     if (tma) {
       if constexpr (TUNE) {
-        PSC_LAUNCH_LB(true, true);
+        PSC_LAUNCH_LB(true, true, true);
       }
     } else {
-      PSC_LAUNCH_LB(false, true);
+      PSC_LAUNCH_LB(false, true, true);
+    }
+  } else if (count) {
+    if (tma) {
+      if constexpr (TUNE) {
+        PSC_LAUNCH_LB(true, true, false);
+      }
+    } else {
+      PSC_LAUNCH_LB(false, true, false);
     }
   } else {
     if (tma) {
       if constexpr (TUNE) {
-        PSC_LAUNCH_LB(true, false);
+        PSC_LAUNCH_LB(true, false, false);
       }
     } else {
-      PSC_LAUNCH_LB(false, false);
+      PSC_LAUNCH_LB(false, false, false);
     }
   }
 #undef PSC_LAUNCH_LB
@@ -815,15 +958,17 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, const Push
   return 0;
 }
 
+// gap: the gapped-store variant (gap.cuh); the caller (gap_prepare) has laid out the store
+// that is written and cleared the control words
 template <int DIM, int DEPOSIT>
-static int push_dim(Ctx* c)
+static int push_dim(Ctx* c, bool gap)
 {
   const GridDev& G = c->gd;
   c->counts_valid = false;
   if (c->n_prts == 0) {
-    return 0;
+    return gap ? fail("gapped push: empty store") : 0;
   }
-  if (c->sorted && c->opt_tiled) {
+  if (gap || (c->sorted && c->opt_tiled)) {
     PushArgs A{};
     A.cell_off = c->d_cell_off;
     A.xi4 = c->xi();
@@ -836,7 +981,7 @@ static int push_dim(Ctx* c)
     for (int d = 0; d < 3; d++) {
       A.same_dxi = A.same_dxi && G.pc.dxi[d] == G.pc.dxi_idx[d];
     }
-    bool count = c->want_counts;
+    bool count = c->want_counts || gap;
     if (count) {
       // the kernel writes every cnt[class][cell] entry exactly once: no memset
       PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(uint32_t)));
@@ -844,6 +989,22 @@ static int push_dim(Ctx* c)
       A.cnt = c->scr[9].as<uint32_t>();
       A.flags = c->scr[11].as<uint32_t>();
       PSC_CUDA_TRY(cudaMemsetAsync(A.flags, 0, 4 * sizeof(uint32_t), c->stream));
+    }
+    if (gap) {
+      GapPush& g = A.gap;
+      g.in_start = c->g_start[0];
+      g.in_n = c->g_n[0];
+      g.in_x = c->xi();
+      g.in_p = c->pxi();
+      g.out_v = c->g_v;
+      g.rl = c->g_rl;
+      g.out_x = c->xi_alt();
+      g.out_p = c->pxi_alt();
+      g.mx = c->mvx;
+      g.mp = c->mvp;
+      g.mtag = c->mvtag;
+      g.ctl = c->g_ctl;
+      g.m_cap = (uint32_t)std::min<size_t>(c->mov_cap, 0xffffffffu);
     }
     const bool xyz = DIM == pm::DIM_XYZ;
     bool custom_tile = c->opt_tile[0] > 0 || c->opt_tile[1] > 0 || c->opt_tile[2] > 0;
@@ -860,8 +1021,8 @@ static int push_dim(Ctx* c)
       int cd = xyz ? 0 : 1;
       bool tma = c->opt_tma && (G.im[cd] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0) &&
                  (G.fld_len % 4 == 0);
-      KernelScope ks(c, tma ? "push_tiled_tma" : "push_tiled");
-      rc = launch_tiled<DIM, DEPOSIT, GeoStatic<DIM>, true>(c, gs, tma, count, A);
+      KernelScope ks(c, gap ? "push_gap" : (tma ? "push_tiled_tma" : "push_tiled"));
+      rc = launch_tiled<DIM, DEPOSIT, GeoStatic<DIM>, true>(c, gs, tma, count, gap, A);
     }
     if (rc == -1) {
       GeoDyn gd{};
@@ -874,8 +1035,8 @@ static int push_dim(Ctx* c)
         gd.f_[d] = inv ? 1 : gd.t_[d] + 3;
         gd.g_[d] = inv ? 0 : 1;
       }
-      KernelScope ks(c, "push_tiled_dyn");
-      rc = launch_tiled<DIM, DEPOSIT, GeoDyn, false>(c, gd, false, count, A);
+      KernelScope ks(c, gap ? "push_gap_dyn" : "push_tiled_dyn");
+      rc = launch_tiled<DIM, DEPOSIT, GeoDyn, false>(c, gd, false, count, gap, A);
     }
     if (rc == 0) {
       c->n_launches++;
@@ -884,6 +1045,9 @@ static int push_dim(Ctx* c)
     }
     if (rc > 0) {
       return rc;
+    }
+    if (gap) {
+      return fail("gapped push: no tile geometry fits this grid");
     }
   }
   {
@@ -895,113 +1059,28 @@ static int push_dim(Ctx* c)
   return check_launch(c, "push_general");
 }
 
-
-// ---- lazy store: push + deposit + (implicit) boundary exchange and sort
 template <int DIM, int DEPOSIT>
-static int push_lazy_dim(Ctx* c)
+static int push_dim(Ctx* c)
 {
-  const GridDev& G = c->gd;
-  const bool xyz = DIM == pm::DIM_XYZ;
-  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
-  LazyArgs A{};
-  A.v = c->d_cell_off;
-  A.flds = c->fld(0);
-  A.slot_len = c->fld_slot_len(0);
-  A.flags = c->scr[11].as<uint32_t>();
-  A.same_dxi = 1;
-  for (int d = 0; d < 3; d++) {
-    A.same_dxi = A.same_dxi && G.pc.dxi[d] == G.pc.dxi_idx[d];
-  }
-  A.tab = FsTables{c->d_patch_bnd, c->d_nei_patch};
-  const int b = c->cur;
-  A.in.vprev = c->lazy ? c->d_vprev : c->d_cell_off;
-  A.in.ncen = c->lazy ? c->lz_ncen[b] : nullptr;
-  A.in.mbase = c->lz_mbase[b];
-  A.in.pre = c->lz_pre[b];
-  A.in.rstart = nullptr;
-  A.in.rcount = nullptr;
-  A.in.bx = c->xi4[b], A.in.bp = c->pxi4[b];
-  A.in.mx = c->mvx[b], A.in.mp = c->mvp[b];
-  A.in.rx = nullptr, A.in.rp = nullptr;
-  A.in.nct = nct;
-  A.out.bx = c->xi4[b ^ 1], A.out.bp = c->pxi4[b ^ 1];
-  A.out.mx = c->mvx[b ^ 1], A.out.mp = c->mvp[b ^ 1];
-  A.out.ncen = c->lz_ncen[b ^ 1];
-  A.out.mbase = c->lz_mbase[b ^ 1];
-  A.out.pre = c->lz_pre[b ^ 1];
-  A.out.newpop = c->lz_newpop;
-  A.out.mov_counter = c->lz_counter;
-  A.out.mov_cap = (uint32_t)std::min<size_t>(c->mov_cap, 0xffffffffu);
-
-  GeoStatic<DIM> gs{};
-  bool stat = !(c->opt_tile[0] > 0 || c->opt_tile[1] > 0 || c->opt_tile[2] > 0);
-  for (int d = 0; d < 3; d++) {
-    bool inv = (!xyz && d == 0);
-    gs.nt_[d] = inv ? 1 : G.ldims[d] / gs.t(d);
-    stat = stat && (inv || (G.ibn[d] == 2 && G.ldims[d] % gs.t(d) == 0));
-  }
-  const int threads = 384;
-  auto smem_of = [&](int nodes) {
-    return (size_t)((9 * nodes + 3) & ~3) * sizeof(float) +
-           (size_t)(threads / 32) * ((QCAP * 2 + 64) * sizeof(float4) + LZ_TAB * sizeof(LzSeg) +
-                                     LZ_UNIT * 32 * sizeof(uint16_t));
-  };
-  if (stat) {
-    int cd = xyz ? 0 : 1;
-    bool tma = c->opt_tma && (G.im[cd] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0) && (G.fld_len % 4 == 0);
-    int tiles = gs.nt(0) * gs.nt(1) * gs.nt(2) * G.n_patches;
-    size_t smem_bytes = smem_of(gs.sm());
-    KernelScope ks(c, "push_lazy");
-    if (tma) {
-      auto kern = k_push_lazy<DIM, DEPOSIT, GeoStatic<DIM>, true, 384, 2>;
-      PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gs, A);
-    } else {
-      auto kern = k_push_lazy<DIM, DEPOSIT, GeoStatic<DIM>, false, 384, 2>;
-      PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-      kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gs, A);
-    }
-  } else {
-    GeoDyn gd{};
-    int def[3] = {xyz ? 8 : 1, xyz ? 8 : 16, xyz ? 8 : 16};
-    for (int d = 0; d < 3; d++) {
-      bool inv = (!xyz && d == 0);
-      int t = c->opt_tile[d] > 0 ? c->opt_tile[d] : def[d];
-      gd.t_[d] = inv ? 1 : std::min(t, G.ldims[d]);
-      gd.nt_[d] = (G.ldims[d] + gd.t_[d] - 1) / gd.t_[d];
-      gd.f_[d] = inv ? 1 : gd.t_[d] + 3;
-      gd.g_[d] = inv ? 0 : 1;
-    }
-    int tiles = gd.nt(0) * gd.nt(1) * gd.nt(2) * G.n_patches;
-    size_t smem_bytes = smem_of(gd.sm());
-    if (smem_bytes > 220 * 1024) {
-      return fail("lazy push: tile does not fit in shared memory");
-    }
-    KernelScope ks(c, "push_lazy_dyn");
-    auto kern = k_push_lazy<DIM, DEPOSIT, GeoDyn, false, 384, 2>;
-    PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    kern<<<tiles, threads, smem_bytes, c->stream>>>(G, gd, A);
-  }
-  c->n_launches++;
-  return check_launch(c, "push_lazy");
+  return push_dim<DIM, DEPOSIT>(c, false);
 }
 
 } // namespace PUSH_VARIANT
 
-// lazy path: the caller (capi.cu step) has run lazy_prepare(); lazy_finish() follows
-int PUSH_CAT(push_lazy_, PUSH_VARIANT)(Ctx* c)
+// gapped store: gap_prepare() has run; gap_finish() follows (capi.cu step)
+int PUSH_CAT(push_gap_, PUSH_VARIANT)(Ctx* c)
 {
   using namespace PUSH_VARIANT;
   PSC_TRY(flds_zero(c, 0, pm::JXI, pm::JXI + 3));
 #ifdef PUSH_PROBE
-  return push_lazy_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
+  return push_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c, true);
 #else
   if (c->gd.dim == pm::DIM_XYZ) {
-    return push_lazy_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c);
+    return push_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c, true);
   } else if (c->gd.deposit == pm::DEPOSIT_VAR1) {
-    return push_lazy_dim<pm::DIM_YZ, pm::DEPOSIT_VAR1>(c);
+    return push_dim<pm::DIM_YZ, pm::DEPOSIT_VAR1>(c, true);
   }
-  return push_lazy_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c);
+  return push_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c, true);
 #endif
 }
 

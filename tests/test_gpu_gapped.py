@@ -1,10 +1,11 @@
-"""The lazy particle store (psc_b200/csrc/lazy.cuh): psc_b200_step never runs the boundary
-exchange + sort as a pass of its own; the push gathers each cell's particles from the
-segments the previous push left behind.  What it stands for must be exactly what the
-reference's BndParticles + SortCountsort2 produce: with the fields held fixed
-(push_fields = 0) the particle update is independent of the deposit's summation order, so
-after k consecutive lazy steps the store is compared BIT-EXACT with the CPU oracle
-(sort, push, exchange) x k -- records, per-patch offsets, per-cell counts."""
+"""The gapped particle store (psc_b200/csrc/gap.cuh): psc_b200_step never runs the boundary
+exchange + sort as a pass of its own; the push writes every particle that stays in its
+cell to its final slot and only the movers are placed afterwards.  What the store stands
+for must be exactly what the reference's BndParticles + SortCountsort2 produce: with the
+fields held fixed (push_fields = 0) the particle update is independent of the deposit's
+summation order, so after k consecutive gapped steps the store is compared BIT-EXACT with
+the CPU oracle (sort, push, exchange) x k -- records, per-patch offsets, per-cell counts.
+Tight slack forces the re-layout path, a tiny mover list the redo-on-the-eager-path one."""
 import ctypes as C
 
 import numpy as np
@@ -50,10 +51,11 @@ def _run_oracle(og, flds, prts, off, k):
     return f, p, o, n_drop
 
 
+@pytest.mark.parametrize("slack", [0, 1], ids=["auto_slack", "slack1"])
 @pytest.mark.parametrize("k", [1, 2, 5])
 @pytest.mark.parametrize("vth", [0.05, 0.5])
 @pytest.mark.parametrize("name", list(CASES))
-def test_lazy_steps_bit_exact(name, vth, k):
+def test_gapped_steps_bit_exact(name, vth, k, slack):
     import psc_b200 as pb
     gkw, opts = CASES[name]
     dx = [l / g for l, g in zip(gkw["length"], gkw["gdims"])]
@@ -63,25 +65,27 @@ def test_lazy_steps_bit_exact(name, vth, k):
     prts, off = thermal_plasma(og, ppc=6, seed=12, vth=(vth, vth / 10))
     rf, rp, ro, n_drop = _run_oracle(og, flds, prts, off, k)
 
-    grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(opts, lazy=1))
+    grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(opts, gapped=1, gap_slack=slack))
     prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=0, checks=0)
     for _ in range(k):
         pb.check(grid.lib.psc_b200_step(grid.ctx, C.byref(prm)))
-    assert grid.get_stat("lazy_steps") == k
+    assert grid.get_stat("gap_steps") == k and grid.get_stat("gap_redone") == 0
+    if slack == 1 and vth > 0.1 and k > 1:
+        assert grid.get_stat("gap_relayouts") > 0
     # sizes are known without materialising the store
     assert np.array_equal(mprts.sizeByPatch(), np.diff(ro))
     assert mprts.size() == len(rp)
     j = mflds.download(0, 3)
     got, got_off = mprts.get()
     assert np.array_equal(got_off, ro)
-    assert got.tobytes() == rp.tobytes(), "lazy store differs from sort+push+exchange of the oracle"
+    assert got.tobytes() == rp.tobytes(), "gapped store differs from sort+push+exchange of the oracle"
     assert np.array_equal(ol.count_by_cell(og, got, got_off), ol.count_by_cell(og, rp, ro))
     assert grid.get_stat("n_dropped") == n_drop
     if "absorbing" in name and vth > 0.1:
         assert n_drop > 0
     scale = np.abs(rf[:, :3]).max()
     assert np.abs(j - rf[:, :3]).max() <= 1e-5 * scale
-    # the materialised store is a plain cell-ordered one: one more step from it, lazy again
+    # the compacted store is a plain cell-ordered one: one more step from it, gapped again
     pb.check(grid.lib.psc_b200_step(grid.ctx, C.byref(prm)))
     rf2, rp2, ro2, _ = _run_oracle(og, flds, rp, ro, 1)
     got2, got_off2 = mprts.get()
@@ -89,8 +93,8 @@ def test_lazy_steps_bit_exact(name, vth, k):
     grid.close()
 
 
-def test_lazy_equals_eager_fused_with_fields():
-    """full Psc::step (fields evolving): lazy and eager paths agree to round-off over
+def test_gapped_equals_eager_fused_with_fields():
+    """full Psc::step (fields evolving): gapped and eager paths agree to round-off over
     several steps and conserve the particle number"""
     import psc_b200 as pb
     og = ol.Grid(gdims=(16, 16, 16), length=(16., 16., 16.), np_=(2, 2, 2), dt=0.4, kinds=KINDS, nicell=8)
@@ -98,12 +102,12 @@ def test_lazy_equals_eager_fused_with_fields():
     ol.fill_ghosts(og, flds, 3, 9)
     prts, off = thermal_plasma(og, ppc=8, seed=9, vth=(0.2, 0.02), margin=0.05)
     res = []
-    for lazy in (0, 1):
-        grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(lazy=lazy))
+    for gapped in (0, 1):
+        grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(gapped=gapped))
         psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=True)
         for _ in range(6):
             psc.step()
-        assert grid.get_stat("lazy_steps") == (6 if lazy else 0)
+        assert grid.get_stat("gap_steps") == (6 if gapped else 0)
         res.append((mprts.get(), mflds.download(), pb.api.energies(grid)))
         grid.close()
     (p0, o0), f0, e0 = res[0]

@@ -160,7 +160,7 @@ def test_fused_step_equals_separate_operators():
     prts, off = thermal_plasma(og, ppc=10, seed=9, vth=(0.4, 0.04))
     res = []
     for fused in (0, 1):
-        grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(fused_sort=fused, lazy=0))
+        grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(fused_sort=fused, gapped=0))
         prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=0, checks=0)
         import ctypes as C
         for _ in range(3):
