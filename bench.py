@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--tma", type=int, default=1)
     ap.add_argument("--warp-reduce", dest="warp_reduce", type=int, default=1)
     ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
-    ap.add_argument("--gapped", type=int, default=1, help="gapped particle store (no sort pass)")
+    ap.add_argument("--gapped", type=int, default=0, help="gapped particle store (no sort pass)")
     ap.add_argument("--gap-slack", dest="gap_slack", type=int, default=0)
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)

@@ -100,7 +100,8 @@ struct Ctx
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
-  int opt_gapped = 1;      // step(): gapped store (gap.cuh), no sort pass; needs fused_sort
+  int opt_gapped = 0;      // step(): gapped store (gap.cuh), no sort pass; needs fused_sort.  Off: its push
+                           // variant is still slower than push + fused sort
   int opt_gap_slack = 0;   // free slots behind every cell's run, 0 = half the mean population
 
   // ---- particles

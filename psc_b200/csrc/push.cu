@@ -48,7 +48,20 @@ namespace PUSH_VARIANT
 {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int QCAP = 56; // crossing-particle queue entries per warp
+constexpr int QCAP = 56;     // crossing-particle queue entries per warp
+constexpr int QCAP_GAP = 48; // ... of the gapped-store variant (makes room for its count table)
+constexpr int CT = 30;       // GAP: per-warp count table [cell of the row][class 0..26, DROP, BAD, REMOTE]
+
+template <bool GAP>
+__host__ __device__ constexpr int qcap()
+{
+  return GAP ? QCAP_GAP : QCAP;
+}
+// uint16 entries of the count table of one warp (a multiple of 8: 16-byte granules)
+__host__ __device__ inline int ct_entries(int row_cells)
+{
+  return (row_cells * CT + 7) & ~7;
+}
 
 // ---------------------------------------------------------------- tile geometry
 // f = shared tile extent in nodes, g = distance of tile node 0 below the tile origin.
@@ -434,8 +447,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   const int nodes = geo.sm();
   float* sEM = smem;             // [6][f2][f1][f0]
   float* sJ = smem + 6 * nodes;  // [3][f2][f1][f0]
-  float4* sQ = reinterpret_cast<float4*>(smem + ((9 * nodes + 3) & ~3)); // [warps][QCAP][2]
-  float4* sP = sQ + (size_t)(blockDim.x >> 5) * QCAP * 2;                // [warps][2][32] next chunk
+  constexpr int QC = qcap<GAP>();
+  float4* sQ = reinterpret_cast<float4*>(smem + ((9 * nodes + 3) & ~3)); // [warps][QC][2]
+  float4* sP = sQ + (size_t)(blockDim.x >> 5) * QC * 2;                  // [warps][2][32] next chunk
   __shared__ int row_ctr; // rows are handed out dynamically (balances the warps)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
@@ -515,7 +529,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
 
   FldTile<GEO> EM{sEM, geo, n0, n1, n2};
-  float4* myQ = sQ + (size_t)warp * QCAP * 2;
+  float4* myQ = sQ + (size_t)warp * QC * 2;
+  // GAP: what this warp's row sent where, [cell][class] (written to the count planes per row)
+  [[maybe_unused]] uint16_t* const myT =
+    reinterpret_cast<uint16_t*>(sP + (size_t)n_warps * 64) + (size_t)warp * ct_entries(geo.t(XYZ ? 0 : 1));
   const uint32_t myP = smem_u32(sP + (size_t)warp * 64 + lane);
   int qn = 0; // queued trajectories of this warp (warp-uniform)
   uint32_t mb_next = 0, mb_end = 0; // GAP: this warp's batch of mover slots (warp-uniform)
@@ -574,6 +591,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
     if constexpr (GAP) {
       const size_t gc = (size_t)p * G.n_cells + (size_t)(c0 + min(lane, run_cells - 1));
       const uint32_t nj = lane < run_cells ? __ldg(&A.gap.in_n[gc]) : 0u;
+      for (int k = lane; k < run_cells * CT; k += 32) {
+        myT[k] = 0;
+      }
+      __syncwarp();
       my_st = __ldg(&A.gap.in_start[gc]);
       my_vo = __ldg(&A.gap.out_v[gc]) + A.gap.rl;
       uint32_t incl = nj;
@@ -588,8 +609,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
     } else {
       myoff = __ldg(&coff[c0 + min(lane, run_cells)]);
     }
-    // GAP: record iv of the row's virtual sequence -> index into the store
-    auto src_of = [&](uint32_t iv) -> uint32_t {
+    // GAP: cell (of the row) that holds record iv of the row's virtual sequence
+    auto cell_of = [&](uint32_t iv) -> int {
       int j = 0;
 #pragma unroll
       for (int st = RowSearch<GEO, DIM>::top; st >= 1; st >>= 1) {
@@ -599,11 +620,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
           j = jj;
         }
       }
+      return j;
+    };
+    // ... and its index into the store being read
+    auto src_of = [&](uint32_t iv, int j) -> uint32_t {
       return __shfl_sync(FULL, my_st, j) + (iv - __shfl_sync(FULL, myoff, j));
     };
     const float4* const src_x = GAP ? A.gap.in_x : A.xi4;
     const float4* const src_p = GAP ? A.gap.in_p : A.pxi4;
-    uint32_t vo_cur = GAP ? __shfl_sync(FULL, my_vo, 0) : 0u; // GAP: stayer slots of the current cell
     const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, run_cells);
     int cur = 0;                                     // cell of the row the passes are at
     uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
@@ -617,8 +641,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
 
     // the next chunk travels global -> shared with cp.async while this one is computed
     // (no registers held across the chunk body)
+    int jc = 0;               // GAP: cell of this lane's record in the next chunk to be computed
+    uint32_t carry_leave = 0; // GAP: particles that left the cell which continues into the next chunk
     {
-      const uint32_t a0 = GAP ? src_of(begin + lane) : begin + lane;
+      if constexpr (GAP) {
+        jc = cell_of(begin + lane);
+      }
+      const uint32_t a0 = GAP ? src_of(begin + lane, jc) : begin + lane;
       if (begin + lane < end) {
         cp_async16(myP, src_x + a0);
         cp_async16(myP + 32 * sizeof(float4), src_p + a0);
@@ -631,21 +660,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
       const bool act = i < end;
       cp_async_wait_all();
       float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
+      const int jcur = jc; // GAP: cell of this lane's record
       {
-        const uint32_t a1 = GAP ? src_of(i + 32) : i + 32;
+        if constexpr (GAP) {
+          jc = cell_of(i + 32);
+        }
+        const uint32_t a1 = GAP ? src_of(i + 32, jc) : i + 32;
         if (i + 32 < end) {
           cp_async16(myP, src_x + a1);
           cp_async16(myP + 32 * sizeof(float4), src_p + a1);
         }
       }
       cp_async_commit();
-      if (qn > QCAP - 32) {
+      if (qn > QC - 32) {
         drain(min(qn, 32));
       }
       float val[NV];
       int ci[3] = {0, 0, 0};
       int pos[3] = {0, 0, 0};
       bool single = false; // one trajectory segment, leaf in (ci, val)
+      [[maybe_unused]] float sxm[3] = {0.f, 0.f, 0.f}, sxp[3] = {0.f, 0.f, 0.f}, sv0 = 0.f, sqw = 0.f;
       {
         bool cross = false;
         pm::Trajectory t;
@@ -661,9 +695,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
           }
           cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
           single = !cross;
-          if (single) {
-            Walker<DIM, DEPOSIT> w;
-            w.first(G.pc, t, U.w, ci, val);
+          if constexpr (!GAP) {
+            if (single) {
+              Walker<DIM, DEPOSIT> w;
+              w.first(G.pc, t, U.w, ci, val);
+            }
+          } else {
+            // the leaf is computed once the record has left (below): its values and the
+            // record are never live together
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+              sxm[d] = t.xm[d], sxp[d] = t.xp[d];
+            }
+            sv0 = t.v[0], sqw = U.w;
           }
           if (COUNT) {
 #pragma unroll
@@ -684,12 +728,122 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
           __syncwarp();
         }
       }
+      int gcls = CLS_NONE; // GAP: destination class, known ahead of the passes
+      if constexpr (GAP) {
+        // Every lane knows its own source cell, so the record leaves right here: a stayer
+        // goes to its final slot = (index inside the cell) - (particles of the cell that left
+        // before it), a mover to the tagged list.  X, U, pos are dead before the passes.
+        const unsigned lt = (1u << lane) - 1u;
+        const uint32_t cstart = __shfl_sync(FULL, myoff, jcur); // where my cell starts in the row
+        const uint32_t vo = __shfl_sync(FULL, my_vo, jcur);
+        uint32_t tcell = 0;
+        if (act) {
+          const int s0 = XYZ ? o[0] + jcur : 0, s1 = XYZ ? rs1 : rs1 + jcur, s2 = rs2;
+          const int d0 = pos[0] - s0, d1 = pos[1] - s1, d2 = pos[2] - s2;
+          const bool ok = (unsigned)pos[0] < (unsigned)G.ldims[0] && (unsigned)pos[1] < (unsigned)G.ldims[1] &&
+                          (unsigned)pos[2] < (unsigned)G.ldims[2] && (unsigned)(d0 + 1) <= 2u &&
+                          (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
+          if (ok) {
+            gcls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
+            tcell = (uint32_t)p * G.n_cells + (uint32_t)((pos[2] * G.ldims[1] + pos[1]) * G.ldims[0] + pos[0]);
+          } else {
+            // patch boundary: the record leaves with the boundary fix-ups applied
+            float xx[3] = {X.x, X.y, X.z}, uu[3] = {U.x, U.y, U.z};
+            int q = 0, c = 0;
+            gcls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
+            X = make_float4(xx[0], xx[1], xx[2], X.w);
+            U = make_float4(uu[0], uu[1], uu[2], U.w);
+            tcell = (uint32_t)q * G.n_cells + (uint32_t)c;
+          }
+        }
+        // lanes of my cell below me; cont: my cell began in an earlier chunk
+        const unsigned below = lt & ~((1u << min(31u, cstart > base ? cstart - base : 0u)) - 1u);
+        const bool cont = cstart < base;
+        const unsigned leave = __ballot_sync(FULL, act && gcls != CLS_CENTER);
+        if (act && gcls == CLS_CENTER) {
+          const uint32_t dst = vo + (i - cstart) - (__popc(leave & below) + (cont ? carry_leave : 0u));
+          A.gap.out_x[dst] = X;
+          A.gap.out_p[dst] = U;
+        }
+        {
+          // the cell of the chunk's last record may continue
+          const uint32_t cl = __shfl_sync(FULL, cstart, 31);
+          const unsigned from = ~((1u << min(31u, cl > base ? cl - base : 0u)) - 1u);
+          carry_leave = __popc(leave & from) + (cl < base ? carry_leave : 0u);
+        }
+        // whatever left its cell is counted per (cell, class) in the warp's table; the old
+        // value is the rank of the group's first member (groups keep the old order)
+        if (leave) {
+          const bool lv = act && gcls != CLS_CENTER;
+          const unsigned same = __match_any_sync(FULL, lv ? ((jcur << 5) | gcls) : 0xffff);
+          uint32_t r0 = 0;
+          if (lv) {
+            r0 = myT[jcur * CT + gcls];
+          }
+          __syncwarp();
+          if (lv && (same & lt) == 0) {
+            myT[jcur * CT + gcls] = (uint16_t)(r0 + __popc(same));
+          }
+          __syncwarp();
+          // movers: parked in the tagged list, slots handed out GAP_BATCH at a time
+          const bool mover = lv && gcls < FS_PLANES;
+          const unsigned mm = __ballot_sync(FULL, mover);
+          if (mm) {
+            const uint32_t nm = __popc(mm), room = mb_end - mb_next;
+            uint32_t nb = 0;
+            if (nm > room) {
+              if (lane == 0) {
+                nb = atomicAdd(&A.gap.ctl[GAP_CTL_MOVERS], (uint32_t)GAP_BATCH);
+              }
+              nb = __shfl_sync(FULL, nb, 0);
+            }
+            if (mover) {
+              const uint32_t r = __popc(mm & lt);
+              const uint32_t slot = r < room ? mb_next + r : nb + (r - room);
+              if (slot < A.gap.m_cap) {
+                A.gap.mx[slot] = X;
+                A.gap.mp[slot] = U;
+                A.gap.mtag[slot] =
+                  make_uint4(tcell, (uint32_t)gcls * A.nct + (uint32_t)p * G.n_cells + (uint32_t)(c0 + jcur),
+                             r0 + __popc(same & lt), 1u);
+              } else {
+                atomicExch(&A.gap.ctl[GAP_CTL_M_FULL], 1u);
+              }
+            }
+            if (nm > room) {
+              mb_next = nb + (nm - room);
+              mb_end = nb + GAP_BATCH;
+            } else {
+              mb_next += nm;
+            }
+          }
+        }
+        if (single) {
+          pm::Trajectory t;
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            t.xm[d] = sxm[d], t.xp[d] = sxp[d];
+            t.lg[d] = pm::fint(sxm[d]), t.lf[d] = pm::fint(sxp[d]);
+            t.v[d] = 0.f;
+          }
+          t.v[0] = sv0;
+          Walker<DIM, DEPOSIT> w;
+          w.first(G.pc, t, sqw, ci, val);
+          const int s0 = XYZ ? o[0] + jcur : 0, s1 = XYZ ? rs1 : rs1 + jcur, s2 = rs2;
+          if (ci[0] != s0 || ci[1] != s1 || ci[2] != s2) {
+            // the leaf is not the run's cell (1/float(dx) and float(dx_inv) disagree at a
+            // cell edge): deposit it on its own
+            leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+            single = false;
+          }
+        }
+      }
       // ---- one pass per cell that has particles in this chunk
       for (;;) {
         const bool mine = act && i >= cb && i < ce;
         const int s0 = XYZ ? o[0] + cur : 0, s1 = XYZ ? rs1 : rs1 + cur, s2 = rs2;
         if (mine && single) {
-          if (ci[0] == s0 && ci[1] == s1 && ci[2] == s2) {
+          if (GAP || (ci[0] == s0 && ci[1] == s1 && ci[2] == s2)) {
 #pragma unroll
             for (int n = 0; n < NV; n++) {
               acc[n] += val[n];
@@ -701,9 +855,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
             leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
           }
         }
-        if (COUNT) {
+        if (COUNT && !GAP) {
           int cls = CLS_NONE;
-          uint32_t tcell = 0; // GAP: target cell (rank-wide index)
           if (mine) {
             const int d0 = pos[0] - s0, d1 = pos[1] - s1, d2 = pos[2] - s2;
             const bool ok = (unsigned)pos[0] < (unsigned)G.ldims[0] && (unsigned)pos[1] < (unsigned)G.ldims[1] &&
@@ -711,88 +864,26 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
                             (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
             if (ok) {
               cls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
-              if constexpr (GAP) {
-                tcell = (uint32_t)p * G.n_cells + (uint32_t)((pos[2] * G.ldims[1] + pos[1]) * G.ldims[0] + pos[0]);
-              }
             } else {
-              int q = 0, c = 0;
-              if constexpr (GAP) {
-                // patch boundary: the record leaves with the boundary fix-ups applied
-                float xx[3] = {X.x, X.y, X.z}, uu[3] = {U.x, U.y, U.z};
-                cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
-                X = make_float4(xx[0], xx[1], xx[2], X.w);
-                U = make_float4(uu[0], uu[1], uu[2], U.w);
-                tcell = (uint32_t)q * G.n_cells + (uint32_t)c;
-              } else {
-                // patch boundary: the pushed record is re-read (written by this thread above)
-                const float4 Xr = A.xi4[i], Ur = A.pxi4[i];
-                float xx[3] = {Xr.x, Xr.y, Xr.z}, uu[3] = {Ur.x, Ur.y, Ur.z};
-                cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
-              }
+              // patch boundary: the pushed record is re-read (written by this thread above)
+              const float4 Xr = A.xi4[i], Ur = A.pxi4[i];
+              float xx[3] = {Xr.x, Xr.y, Xr.z}, uu[3] = {Ur.x, Ur.y, Ur.z};
+              int q, c;
+              cls = fs_classify(G, A.tab, p, s0, s1, s2, xx, uu, q, c);
             }
           }
-          [[maybe_unused]] const unsigned lt = (1u << lane) - 1u;
           unsigned grp = __ballot_sync(FULL, cls == CLS_CENTER);
-          if constexpr (GAP) {
-            // stayers: final slot = rank among the stayers of the cell (old order)
-            const uint32_t r0 = __shfl_sync(FULL, mycount, CLS_CENTER);
-            if (cls == CLS_CENTER) {
-              const uint32_t dst = vo_cur + r0 + __popc(grp & lt);
-              A.gap.out_x[dst] = X;
-              A.gap.out_p[dst] = U;
-            }
-          }
           if (lane == CLS_CENTER) {
             mycount += __popc(grp);
           }
           unsigned rem = __ballot_sync(FULL, mine) & ~grp;
-          uint32_t rank = 0; // GAP: rank inside the (source cell, class) group
           while (rem) {
             const int v = __shfl_sync(FULL, cls, __ffs(rem) - 1);
             grp = __ballot_sync(FULL, cls == v);
-            if constexpr (GAP) {
-              const uint32_t r0 = __shfl_sync(FULL, mycount, v);
-              if (cls == v) {
-                rank = r0 + __popc(grp & lt);
-              }
-            }
             if (lane == v) {
               mycount += __popc(grp);
             }
             rem &= ~grp;
-          }
-          if constexpr (GAP) {
-            // movers: parked in the tagged list, slots handed out GAP_BATCH at a time
-            const bool mover = mine && cls < FS_PLANES && cls != CLS_CENTER;
-            const unsigned mm = __ballot_sync(FULL, mover);
-            if (mm) {
-              const uint32_t nm = __popc(mm), room = mb_end - mb_next;
-              uint32_t nb = 0;
-              if (nm > room) {
-                if (lane == 0) {
-                  nb = atomicAdd(&A.gap.ctl[GAP_CTL_MOVERS], (uint32_t)GAP_BATCH);
-                }
-                nb = __shfl_sync(FULL, nb, 0);
-              }
-              if (mover) {
-                const uint32_t r = __popc(mm & lt);
-                const uint32_t slot = r < room ? mb_next + r : nb + (r - room);
-                if (slot < A.gap.m_cap) {
-                  A.gap.mx[slot] = X;
-                  A.gap.mp[slot] = U;
-                  A.gap.mtag[slot] = make_uint4(tcell, (uint32_t)cls * A.nct + (uint32_t)p * G.n_cells + (uint32_t)(c0 + cur),
-                                                rank, 1u);
-                } else {
-                  atomicExch(&A.gap.ctl[GAP_CTL_M_FULL], 1u);
-                }
-              }
-              if (nm > room) {
-                mb_next = nb + (nm - room);
-                mb_end = nb + GAP_BATCH;
-              } else {
-                mb_next += nm;
-              }
-            }
           }
         }
         if (ce > base + 32) {
@@ -818,7 +909,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
           }
           dirty = false;
         }
-        if (COUNT) {
+        if (COUNT && !GAP) {
           if (lane < FS_PLANES) {
             A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur)] = mycount;
           } else if (mycount) {
@@ -837,12 +928,34 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         }
         cb = ce;
         ce = __shfl_sync(FULL, myoff, cur + 1);
-        if constexpr (GAP) {
-          vo_cur = __shfl_sync(FULL, my_vo, cur);
-        }
       }
       base += 32;
     } while (base < end);
+    if constexpr (GAP) {
+      // the row's counts: lane k writes class k of every cell; stayers = population - leavers
+      __syncwarp();
+      uint32_t special = 0;
+      for (int j = 0; j < run_cells; j++) {
+        const uint32_t v = lane < CT ? myT[j * CT + lane] : 0u;
+        const uint32_t left = __reduce_add_sync(FULL, lane == CLS_CENTER ? 0u : v);
+        const uint32_t nj = __shfl_sync(FULL, myoff, j + 1) - __shfl_sync(FULL, myoff, j);
+        if (lane < FS_PLANES) {
+          A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + j)] = lane == CLS_CENTER ? nj - left : v;
+        } else {
+          special += v;
+        }
+      }
+      if (special) {
+        if (lane == CLS_BAD) {
+          atomicExch(&A.flags[0], 1u);
+        } else if (lane == CLS_DROP) {
+          atomicAdd(&A.flags[1], special);
+        } else if (lane == CLS_REMOTE) {
+          atomicAdd(&A.flags[2], special);
+        }
+      }
+      __syncwarp();
+    }
     if (lane == 0) {
       row = atomicAdd(&row_ctr, 1);
     }
@@ -895,7 +1008,8 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, bool gap, 
     threads = std::min(threads, 256);
   }
   size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
-                      (size_t)(threads / 32) * (QCAP * 2 + 64) * sizeof(float4);
+                      (size_t)(threads / 32) * ((gap ? QCAP_GAP : QCAP) * 2 + 64) * sizeof(float4) +
+                      (gap ? (size_t)(threads / 32) * ct_entries(geo.t(DIM == pm::DIM_XYZ ? 0 : 1)) * sizeof(uint16_t) : 0);
   if (smem_bytes > 220 * 1024) {
     return -1;
   }
