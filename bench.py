@@ -247,12 +247,20 @@ def run_b200(args, rank, world, local_rank):
         out_en = np.zeros(8)
         barrier()
         t0 = time.perf_counter()
+        parts = np.zeros(4)
         for _ in range(k_e2e):
+            ta = time.perf_counter()
             pb.check(lib.psc_b200_mflds_upload(ctx, 0, pb.EX, pb.EX + 6, h_eb.ctypes.data_as(C.c_void_p)))
+            tb = time.perf_counter()
             prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=1, checks=0)
             pb.check(lib.psc_b200_step(ctx, C.byref(prm)))
+            grid.sync()
+            tc = time.perf_counter()
             pb.check(lib.psc_b200_mflds_download(ctx, 0, pb.JXI, pb.JXI + 3, h_j.ctypes.data_as(C.c_void_p)))
+            td = time.perf_counter()
             pb.check(lib.psc_b200_energies(ctx, out_en.ctypes.data_as(C.c_void_p)))
+            te = time.perf_counter()
+            parts += (tb - ta, tc - tb, td - tc, te - td)
         barrier()
         dt_e2e = time.perf_counter() - t0
         if dist:
@@ -262,6 +270,8 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": n_total * k_e2e / dt_e2e, "unit": "particle-steps/s",
                "h2d_bytes_per_step": int(h_eb.nbytes) * world, "d2h_bytes_per_step": (int(h_j.nbytes) + 64) * world,
                "steps": k_e2e,
+               "ms_per_step": {k: round(float(v) / k_e2e * 1e3, 2)
+                               for k, v in zip(("upload", "step", "download", "energies"), parts)},
                "what": "per step: upload E,B (6 comps, all patches) from pinned host memory, "
                        "psc_b200_step, download J (3 comps) + energies"}
 
@@ -346,6 +356,10 @@ def main():
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, world, local_rank)
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -327,7 +327,10 @@ int comm_init(Ctx* c, const void* id128)
     return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
   }
   c->comm = cm;
-  return 0;
+  // NCCL connects the collective channels lazily (seconds on the first all-reduce): do it
+  // here, not inside the first energy / checks call of a run
+  double warm = 0.;
+  return comm_allreduce_sum(c, &warm, 1);
 }
 
 void comm_destroy(Ctx* c)
