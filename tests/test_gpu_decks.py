@@ -1,0 +1,92 @@
+"""Deck-shaped runs (BASELINE.json configs, scaled down: tests/decks.py): the full
+Psc::step sequence for 1000 steps on the device against the CPU oracle.  North-star bar:
+field and particle energies over 1000 steps agree within 1 %; the particle number is
+conserved (periodic / reflecting boundaries).  The decks' cadence is kept (sort every 10
+steps, Marder every 100 in harris), so most steps run the unsorted-store kernels and every
+tenth one the fused boundary-exchange + sort path.
+
+The bubble's field energy is 2 % of the total and partly noise-driven: the ORACLE ITSELF,
+run twice on the same particles in a different order inside each patch (only the summation
+order of J changes), differs from itself by up to 1.6 % in that quantity after 1000 steps
+(0.1 % in the particle energies; measured with this file's _oracle_run).  It is therefore
+held to 3 % -- and to 1 % of the total energy --, everything else to the 1 % of the
+contract."""
+import functools
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from b200_helpers import gpu_state
+from decks import DECKS
+
+pytestmark = pytest.mark.gpu
+
+N_STEPS = {"bubble_yz": 1000, "harris_yz": 1000, "kelvin_helmholtz_xyz": 1000}
+FIELD_RTOL = {"bubble_yz": 3e-2, "harris_yz": 1e-2, "kelvin_helmholtz_xyz": 1e-2}
+EVERY = 100
+
+
+@functools.lru_cache(maxsize=None)
+def _deck(name):
+    return DECKS[name]()
+
+
+@functools.lru_cache(maxsize=None)
+def _oracle_energies(name, n_steps):
+    return _oracle_run(_deck(name), n_steps)
+
+
+def _oracle_run(d, n_steps):
+    og = d["og"]
+    f, p, o = d["flds"].copy(), d["prts"].copy(), d["off"].copy()
+    L, G = ol.lib(), og.byref()
+    # Psc::initialize (psc.hxx:220-238): ghosts of H, J, E
+    L.po_bndf_fill_ghosts_H(G, ol.ptr(f))
+    ol.fill_ghosts(og, f, ol.HX, ol.HX + 3)
+    ol.fill_ghosts(og, f, 0, 3)
+    L.po_bndf_fill_ghosts_E(G, ol.ptr(f))
+    ol.fill_ghosts(og, f, ol.EX, ol.EX + 3)
+    out = [ol.energies(og, f, p, o)]
+    for s in range(1, n_steps + 1):
+        do_marder = d["marder_interval"] > 0 and s % d["marder_interval"] == 0
+        p, o = ol.step(og, f, p, o, sort_now=(s % d["sort_interval"] == 0),
+                       marder_loop=1 if do_marder else 0, marder_diffusion=0.9)
+        if s % EVERY == 0:
+            out.append(ol.energies(og, f, p, o))
+    return np.array(out), len(p)
+
+
+@pytest.mark.parametrize("fma", [0, 1], ids=["exact", "fma"])
+@pytest.mark.parametrize("name", list(DECKS))
+def test_deck_energies_1000_steps(name, fma):
+    import psc_b200 as pb
+    d = _deck(name)
+    og, n_steps = d["og"], N_STEPS[name]
+    ref, n_ref = _oracle_energies(name, n_steps)
+
+    grid, mprts, mflds = gpu_state(og, d["flds"], d["prts"], d["off"], dict(fma=fma))
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=d["sort_interval"],
+                 marder_interval=d["marder_interval"], marder_diffusion=0.9, marder_loop=1, fused=True)
+    psc.initialize()
+    got = [pb.api.energies(grid)]
+    for s in range(1, n_steps + 1):
+        psc.step()
+        if s % EVERY == 0:
+            got.append(pb.api.energies(grid))
+    got = np.array(got)
+    assert mprts.size() == n_ref == len(d["prts"])
+    assert grid.get_stat("fused_steps") >= n_steps // d["sort_interval"] - 1
+    grid.close()
+
+    # the start is the same state
+    np.testing.assert_allclose(got[0], ref[0], rtol=1e-6, atol=1e-12)
+    # field energy (sum and every component against the sum), particle energy per species
+    fld_g, fld_r = got[:, :6].sum(axis=1), ref[:, :6].sum(axis=1)
+    assert np.abs(fld_g / fld_r - 1).max() < FIELD_RTOL[name], (fld_g, fld_r)
+    assert np.abs(fld_g - fld_r).max() < 1e-2 * ref.sum(axis=1).min()
+    assert np.abs(got[:, :6] - ref[:, :6]).max() < FIELD_RTOL[name] * fld_r.max()
+    assert np.abs(got[:, 6:] / ref[:, 6:] - 1).max() < 1e-2, (got[:, 6:], ref[:, 6:])
+    # and the sum is conserved to the level the oracle conserves it
+    tot_g, tot_r = got.sum(axis=1), ref.sum(axis=1)
+    assert np.abs(tot_g / tot_r - 1).max() < 1e-2
