@@ -182,7 +182,7 @@ def run_b200(args, rank, world, local_rank):
         dist.broadcast(idt, 0)
         grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
     for k, v in (("fma", args.fma), ("tiled", args.tiled), ("tma", args.tma),
-                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort), ("gapped", args.gapped), ("gap_slack", args.gap_slack)):
+                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort), ("gapped", args.gapped), ("gap_slack", args.gap_slack), ("overlap", args.overlap)):
         grid.set_option(k, v)
     if args.tile:
         grid.set_option("tile", args.tile)
@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
                    "particles_per_gpu": n_prts, "cells_per_gpu": n ** 3, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
                    "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma, "warp_reduce": args.warp_reduce,
-                                                "fused_sort": args.fused_sort, "gapped": args.gapped}},
+                                                "fused_sort": args.fused_sort, "gapped": args.gapped, "overlap": args.overlap}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "kernels": kernels,
     }
@@ -342,6 +342,7 @@ def main():
     ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
     ap.add_argument("--gapped", type=int, default=0, help="gapped particle store (no sort pass)")
     ap.add_argument("--gap-slack", dest="gap_slack", type=int, default=0)
+    ap.add_argument("--overlap", type=int, default=0, help="field chain on a second stream next to the sort")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--min-blocks", dest="min_blocks", type=int, default=0)

@@ -201,6 +201,15 @@ static int ctx_create(const psc_b200_grid_desc* desc, Ctx** out)
   }
   PSC_CUDA_TRY(cudaGetDevice(&c->device));
   PSC_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // the field chain is a string of small kernels: at high priority its CTAs are placed
+    // as soon as slots free up instead of behind the pending CTAs of the particle scatter
+    int prio_lo = 0, prio_hi = 0;
+    PSC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PSC_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
+  }
+  PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   PSC_CUDA_TRY(cudaEventCreate(&c->ev_start));
   PSC_CUDA_TRY(cudaEventCreate(&c->ev_stop));
 
@@ -269,6 +278,9 @@ static void ctx_destroy(Ctx* c)
   }
   cudaEventDestroy(c->ev_start);
   cudaEventDestroy(c->ev_stop);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -276,6 +288,26 @@ static void ctx_destroy(Ctx* c)
 static int push_mprts(Ctx* c)
 {
   return c->opt_fma ? push_mprts_fast(c) : push_mprts_exact(c);
+}
+
+// psc.hxx:417-467 without Marder: J ghosts, then the Yee leapfrog with its ghost fills
+static int field_chain(Ctx* c, const psc_b200_step_params* prm)
+{
+  PSC_TRY(bndf_add_ghosts_J(c));                       // :417
+  PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
+  PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
+  if (prm->push_fields) {
+    PSC_TRY(push_H(c, .5)); // :426
+    PSC_TRY(bndf_fill_ghosts_H(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+    PSC_TRY(push_E(c, 1.)); // :439
+    PSC_TRY(bndf_fill_ghosts_E(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
+    PSC_TRY(push_H(c, .5)); // :461
+    PSC_TRY(bndf_fill_ghosts_H(c));
+    PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
+  }
+  return 0;
 }
 
 // Psc::step (src/include/psc.hxx:321-486) without collisions / injection / output
@@ -305,27 +337,30 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
     }
   }
   if (gap_ok) {
-    PSC_TRY(bndf_add_ghosts_J(c));                       // :417
-    PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
-    PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
-    if (prm->push_fields) {
-      PSC_TRY(push_H(c, .5)); // :426
-      PSC_TRY(bndf_fill_ghosts_H(c));
-      PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
-      PSC_TRY(push_E(c, 1.)); // :439
-      PSC_TRY(bndf_fill_ghosts_E(c));
-      PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
-      PSC_TRY(push_H(c, .5)); // :461
-      PSC_TRY(bndf_fill_ghosts_H(c));
-      PSC_TRY(bnd_fill_ghosts(c, 0, pm::HX, pm::HX + 3));
-    }
-    return 0;
+    return field_chain(c, prm);
   }
   if (prm->checks) {
     PSC_TRY(check_continuity_begin(c)); // :379-384
   }
   c->want_counts = prm->sort && c->opt_fused_sort && c->sorted;
   PSC_TRY(push_mprts(c)); // :389
+  if (c->opt_overlap && prm->sort && c->opt_fused_sort && c->pushed_from_sorted && !c->comm && !prm->checks &&
+      prm->marder_loop <= 0) {
+    // The field chain (:417-467) touches only the field arrays, the fused exchange + sort
+    // (:412, :356 of the next step) only the particles, and both depend only on the push:
+    // they run side by side, the fields on the second stream.  The sort is DRAM-bound and
+    // the field kernels are small, so the fields come almost for free.
+    PSC_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    PSC_CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    std::swap(c->stream, c->stream2);
+    int rc = field_chain(c, prm);
+    cudaEventRecord(c->ev_join, c->stream);
+    std::swap(c->stream, c->stream2);
+    PSC_TRY(rc);
+    rc = fused_bnd_sort(c);
+    PSC_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    return rc;
+  }
   // :412 bndp_ -- when this step's store was cell-ordered, the exchange is fused with
   // the sort the next step would start with (same result, one pass over the particles)
   if (prm->sort && c->opt_fused_sort && c->pushed_from_sorted) {
@@ -633,6 +668,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "tile_z") { c->opt_tile[2] = v; }
     else if (n == "profile") { c->opt_profile = v; }
     else if (n == "fused_sort") { c->opt_fused_sort = v; }
+    else if (n == "overlap") { c->opt_overlap = v; }
     else if (n == "gapped") { c->opt_gapped = v; }
     else if (n == "gap_slack") { c->opt_gap_slack = v; }
     else { return fail("unknown option " + n); }

@@ -154,9 +154,13 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_
 // Class order: stayers first, then the receiver's direction loop dir' ascending; the
 // sender sits in direction dir' from q and travelled in direction t = -dir'.  A particle
 // that crossed the lower (upper) patch face lands in the first (last) cell, so only
-// cells on a patch face have routes other than "stay".
-__global__ void k_fs_offsets(GridDev G, const int* __restrict__ nei_patch, uint32_t nct,
-                             uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
+// cells on a patch face have routes other than "stay": k_fs_offsets_same handles the
+// same-patch contributions of every cell (regular, one thread per cell), and
+// k_fs_offsets_face appends the neighbour-patch routes for the cells on the patch faces
+// only (one thread per face cell; the face slabs are enumerated z, y, x and a cell that
+// lies in several is taken by the first).
+__global__ void __launch_bounds__(256, 4)
+  k_fs_offsets_same(GridDev G, uint32_t nct, uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
 {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nct) {
@@ -164,35 +168,85 @@ __global__ void k_fs_offsets(GridDev G, const int* __restrict__ nei_patch, uint3
   }
   const int q = g / G.n_cells;
   const int c = g - q * G.n_cells;
-  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1];
   const int c0 = c % ld0, c1 = (c / ld0) % ld1, c2 = c / (ld0 * ld1);
   uint32_t total = 0;
   fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
+  new_cnt[g] = total;
+}
+
+__device__ __forceinline__ void fs_face_routes(const GridDev& G, const int* __restrict__ nei_patch, uint32_t nct,
+                                               uint32_t* __restrict__ cnt, int q, int c0, int c1, int c2,
+                                               uint32_t& total)
+{
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
   const bool lo0 = c0 == 0, hi0 = c0 == ld0 - 1, lo1 = c1 == 0, hi1 = c1 == ld1 - 1, lo2 = c2 == 0,
              hi2 = c2 == ld2 - 1;
-  if (lo0 | hi0 | lo1 | hi1 | lo2 | hi2) {
-    // dir' ascending <=> t descending, z slowest
-    for (int t2 = 1; t2 >= -1; t2--) {
-      if ((t2 == 1 && !lo2) || (t2 == -1 && !hi2)) {
+  // dir' ascending <=> t descending, z slowest
+  for (int t2 = 1; t2 >= -1; t2--) {
+    if ((t2 == 1 && !lo2) || (t2 == -1 && !hi2)) {
+      continue;
+    }
+    for (int t1 = 1; t1 >= -1; t1--) {
+      if ((t1 == 1 && !lo1) || (t1 == -1 && !hi1)) {
         continue;
       }
-      for (int t1 = 1; t1 >= -1; t1--) {
-        if ((t1 == 1 && !lo1) || (t1 == -1 && !hi1)) {
+      for (int t0 = 1; t0 >= -1; t0--) {
+        if ((t0 == 1 && !lo0) || (t0 == -1 && !hi0) || (t0 == 0 && t1 == 0 && t2 == 0)) {
           continue;
         }
-        for (int t0 = 1; t0 >= -1; t0--) {
-          if ((t0 == 1 && !lo0) || (t0 == -1 && !hi0) || (t0 == 0 && t1 == 0 && t2 == 0)) {
-            continue;
-          }
-          int dip = ((-t2 + 1) * 3 + (-t1 + 1)) * 3 + (-t0 + 1);
-          int ps = nei_patch[q * 27 + dip];
-          if (ps >= 0) {
-            fs_route(G, nct, cnt, ps, c0, c1, c2, t0, t1, t2, total);
-          }
+        int dip = ((-t2 + 1) * 3 + (-t1 + 1)) * 3 + (-t0 + 1);
+        int ps = nei_patch[q * 27 + dip];
+        if (ps >= 0) {
+          fs_route(G, nct, cnt, ps, c0, c1, c2, t0, t1, t2, total);
         }
       }
     }
   }
+}
+
+// face slabs of one patch: areas (0 for a direction without neighbours to look at)
+struct FaceGeom
+{
+  int a[3];  // cells of one slab normal to d
+  int s[3];  // slabs normal to d (2, or 1 when the patch is one cell thick, or 0)
+  int per_patch;
+};
+
+__global__ void __launch_bounds__(128)
+  k_fs_offsets_face(GridDev G, FaceGeom FG, const int* __restrict__ nei_patch, uint32_t nct,
+                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = t / FG.per_patch;
+  if (q >= G.n_patches) {
+    return;
+  }
+  int r = t - q * FG.per_patch;
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  const bool f0 = FG.s[0] > 0, f1 = FG.s[1] > 0; // directions whose faces are enumerated
+  int c0, c1, c2;
+  if (r < FG.s[2] * FG.a[2]) {
+    const int side = r / FG.a[2], rr = r - side * FG.a[2];
+    c2 = side ? ld2 - 1 : 0, c1 = rr / ld0, c0 = rr - c1 * ld0;
+  } else if ((r -= FG.s[2] * FG.a[2]) < FG.s[1] * FG.a[1]) {
+    const int side = r / FG.a[1], rr = r - side * FG.a[1];
+    c1 = side ? ld1 - 1 : 0, c2 = rr / ld0, c0 = rr - c2 * ld0;
+    if (FG.s[2] && (c2 == 0 || c2 == ld2 - 1)) {
+      return; // taken by a z slab
+    }
+  } else {
+    r -= FG.s[1] * FG.a[1];
+    const int side = r / FG.a[0], rr = r - side * FG.a[0];
+    c0 = side ? ld0 - 1 : 0, c2 = rr / ld1, c1 = rr - c2 * ld1;
+    if ((FG.s[2] && (c2 == 0 || c2 == ld2 - 1)) || (f1 && (c1 == 0 || c1 == ld1 - 1))) {
+      return;
+    }
+  }
+  (void)f0;
+  const uint32_t g = (uint32_t)q * G.n_cells + (uint32_t)((c2 * ld1 + c1) * ld0 + c0);
+  uint32_t total = new_cnt[g];
+  fs_face_routes(G, nei_patch, nct, cnt, q, c0, c1, c2, total);
   new_cnt[g] = total;
 }
 
@@ -213,6 +267,9 @@ __device__ __forceinline__ void fs_cp_async16(uint32_t dst, const void* src)
 #ifndef SC_MINB
 #define SC_MINB 4
 #endif
+#ifndef SC_DEPTH
+#define SC_DEPTH 3 // stages of the per-warp chunk pipeline
+#endif
 __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
                const uint32_t* __restrict__ new_cell_off, const uint32_t* __restrict__ pre,
@@ -220,7 +277,10 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
                float4* __restrict__ xo, float4* __restrict__ po)
 {
   __shared__ uint32_t pre_s[SC_CELLS][33];
-  __shared__ float4 stage_s[SC_WARPS][2][32];
+  // SC_DEPTH - 1 chunks per warp are in flight while one is ranked: the pass is bound by
+  // memory latency x bytes in flight (profiles/r01_v5_fs_scatter_ncu.txt: long-scoreboard
+  // stalls, 46 % occupancy), not by issue slots
+  __shared__ float4 stage_s[SC_WARPS][SC_DEPTH][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t g0 = blockIdx.x * SC_CELLS;
@@ -229,12 +289,17 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   // the warp's first chunk is requested before anything else waits on memory
   const uint32_t myoff = n_cells_w ? __ldg(&cell_off[gw + min(lane, n_cells_w)]) : 0u;
   const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, n_cells_w);
-  const uint32_t stg = (uint32_t)__cvta_generic_to_shared(&stage_s[warp][0][lane]);
-  if (begin + lane < end) {
-    fs_cp_async16(stg, xi4 + begin + lane);
-    fs_cp_async16(stg + 32 * sizeof(float4), pxi4 + begin + lane);
+  const uint32_t stg0 = (uint32_t)__cvta_generic_to_shared(&stage_s[warp][0][0][lane]);
+  constexpr uint32_t STAGE_BYTES = 2 * 32 * sizeof(float4);
+#pragma unroll
+  for (int d = 0; d < SC_DEPTH - 1; d++) {
+    const uint32_t i0 = begin + 32 * d + lane;
+    if (i0 < end) {
+      fs_cp_async16(stg0 + d * STAGE_BYTES, xi4 + i0);
+      fs_cp_async16(stg0 + d * STAGE_BYTES + 32 * sizeof(float4), pxi4 + i0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int plane = warp; plane < 32; plane += SC_WARPS) {
     for (int c = lane; c < SC_CELLS; c += 32) {
       pre_s[c][plane] = (plane < 27 && g0 + c < nct) ? __ldg(&pre[(size_t)plane * nct + g0 + c]) : 0u;
@@ -251,16 +316,24 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   int cur = 0;
   uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
   uint32_t run = pre_s[warp * SC_CPW][lane];
+  int st = 0; // stage that holds the chunk at `base`
   for (uint32_t base = begin; base < end; base += 32) {
     const uint32_t i = base + lane;
     const bool act = i < end;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    float4 X = stage_s[warp][0][lane], U = stage_s[warp][1][lane];
-    if (i + 32 < end) {
-      fs_cp_async16(stg, xi4 + i + 32);
-      fs_cp_async16(stg + 32 * sizeof(float4), pxi4 + i + 32);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SC_DEPTH - 2) : "memory");
+    float4 X = stage_s[warp][st][0][lane], U = stage_s[warp][st][1][lane];
+    {
+      // the stage read SC_DEPTH - 1 iterations from now (each lane refills only the slots
+      // it reads itself: no warp barrier needed)
+      const int sf = st == 0 ? SC_DEPTH - 1 : st - 1;
+      const uint32_t inext = i + 32 * (SC_DEPTH - 1);
+      if (inext < end) {
+        fs_cp_async16(stg0 + sf * STAGE_BYTES, xi4 + inext);
+        fs_cp_async16(stg0 + sf * STAGE_BYTES + 32 * sizeof(float4), pxi4 + inext);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    st = st + 1 == SC_DEPTH ? 0 : st + 1;
     for (;;) {
       const bool mine = act && i >= cb && i < ce;
       int cls = CLS_NONE;
@@ -507,8 +580,28 @@ int fused_bnd_sort(Ctx* c)
   c->counts_valid = false;
   {
     KernelScope ks(c, "fsort_offsets");
-    k_fs_offsets<<<div_up(nct, 128), 128, 0, c->stream>>>(G, c->d_nei_patch, nct, cnt, new_cnt);
-    c->n_launches++;
+    k_fs_offsets_same<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt);
+    // faces towards a direction in which some patch has a neighbour (none along an
+    // invariant direction: Grid_ / MrcDomain)
+    FaceGeom FG{};
+    const int ld[3] = {G.ldims[0], G.ldims[1], G.ldims[2]};
+    for (int d = 0; d < 3; d++) {
+      bool any = false;
+      for (int p = 0; p < np && !any; p++) {
+        for (int di = 0; di < 27 && !any; di++) {
+          const int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+          any = dir[d] != 0 && c->h_nei_patch[p * 27 + di] >= 0;
+        }
+      }
+      FG.a[d] = G.n_cells / ld[d];
+      FG.s[d] = any ? (ld[d] > 1 ? 2 : 1) : 0;
+      FG.per_patch += FG.s[d] * FG.a[d];
+    }
+    if (FG.per_patch) {
+      k_fs_offsets_face<<<div_up((size_t)FG.per_patch * np, 128), 128, 0, c->stream>>>(G, FG, c->d_nei_patch, nct,
+                                                                                        cnt, new_cnt);
+    }
+    c->n_launches += 2;
   }
   uint32_t n_expected = c->n_prts;
   // ---- multi-rank: ship the leavers, merge the arrivals into the target cells' tails
@@ -651,29 +744,8 @@ __global__ void k_gap_offsets(GridDev G, const int* __restrict__ nei_patch, uint
   const int c0 = c % ld0, c1 = (c / ld0) % ld1, c2 = c / (ld0 * ld1);
   uint32_t total = 0, nl = 0, nc = 0;
   fs_route<true>(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total, &nl, &nc);
-  const bool lo0 = c0 == 0, hi0 = c0 == ld0 - 1, lo1 = c1 == 0, hi1 = c1 == ld1 - 1, lo2 = c2 == 0,
-             hi2 = c2 == ld2 - 1;
-  if (lo0 | hi0 | lo1 | hi1 | lo2 | hi2) {
-    for (int t2 = 1; t2 >= -1; t2--) {
-      if ((t2 == 1 && !lo2) || (t2 == -1 && !hi2)) {
-        continue;
-      }
-      for (int t1 = 1; t1 >= -1; t1--) {
-        if ((t1 == 1 && !lo1) || (t1 == -1 && !hi1)) {
-          continue;
-        }
-        for (int t0 = 1; t0 >= -1; t0--) {
-          if ((t0 == 1 && !lo0) || (t0 == -1 && !hi0) || (t0 == 0 && t1 == 0 && t2 == 0)) {
-            continue;
-          }
-          int dip = ((-t2 + 1) * 3 + (-t1 + 1)) * 3 + (-t0 + 1);
-          int ps = nei_patch[q * 27 + dip];
-          if (ps >= 0) {
-            fs_route(G, nct, cnt, ps, c0, c1, c2, t0, t1, t2, total);
-          }
-        }
-      }
-    }
+  if (c0 == 0 || c0 == ld0 - 1 || c1 == 0 || c1 == ld1 - 1 || c2 == 0 || c2 == ld2 - 1) {
+    fs_face_routes(G, nei_patch, nct, cnt, q, c0, c1, c2, total);
   }
   const uint32_t v0 = v[g], v1 = v[g + 1];
   new_start[g] = v0 + rl - nl; // (meaningless when nl > rl: the store is re-laid out then)
