@@ -436,7 +436,10 @@ void po_bnd_particles(const po_grid* g, const po_prt* prts_in,
   prt_vec* stay = calloc(np, sizeof(prt_vec));
   unsigned dropped = 0;
 
-  /* process_patch: bnd_particles_impl.hxx:93-218 */
+  /* process_patch: bnd_particles_impl.hxx:93-218.  Patches are independent (the
+   * reference runs them on different MPI ranks): one OpenMP task per patch, same
+   * results in any order. */
+#pragma omp parallel for schedule(dynamic) reduction(+ : dropped)
   for (int p = 0; p < np; p++) {
     int poff[3];
     po_patch_off(g, p, poff);
@@ -535,10 +538,47 @@ void po_bnd_particles(const po_grid* g, const po_prt* prts_in,
     }
   }
 
-  /* ddc_particles::comm (ddc_particles.hxx:283-478) */
-  unsigned cur = 0;
+  /* ddc_particles::comm (ddc_particles.hxx:283-478): first the size of every
+   * receiving patch (its stayers + what its neighbours send it), then the copies, one
+   * patch per task */
+  off_out[0] = 0;
   for (int p = 0; p < np; p++) {
-    off_out[p] = cur;
+    unsigned cnt = stay[p].n;
+    int my_rank = rank_of_patch ? rank_of_patch[p] : 0;
+    int dir[3];
+    for (dir[2] = -1; dir[2] <= 1; dir[2]++) {
+      for (dir[1] = -1; dir[1] <= 1; dir[1]++) {
+        for (dir[0] = -1; dir[0] <= 1; dir[0]++) {
+          if (dir[0] == 0 && dir[1] == 0 && dir[2] == 0) {
+            continue;
+          }
+          int nei = po_neighbor_patch(g, p, dir);
+          if (nei < 0 || (rank_of_patch ? rank_of_patch[nei] : 0) != my_rank) {
+            continue;
+          }
+          int dirneg[3] = {-dir[0], -dir[1], -dir[2]};
+          cnt += send[nei * 27 + dir2idx(dirneg)].n;
+        }
+      }
+    }
+    if (rank_of_patch) {
+      for (int q = 0; q < np; q++) {
+        if (rank_of_patch[q] == my_rank) {
+          continue;
+        }
+        for (int di = 0; di < 27; di++) {
+          int d3[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+          if (di != 13 && po_neighbor_patch(g, q, d3) == p) {
+            cnt += send[q * 27 + di].n;
+          }
+        }
+      }
+    }
+    off_out[p + 1] = off_out[p] + cnt;
+  }
+#pragma omp parallel for schedule(dynamic)
+  for (int p = 0; p < np; p++) {
+    unsigned cur = off_out[p];
     memcpy(prts_out + cur, stay[p].v, sizeof(po_prt) * stay[p].n);
     cur += stay[p].n;
     int my_rank = rank_of_patch ? rank_of_patch[p] : 0;
@@ -592,7 +632,6 @@ void po_bnd_particles(const po_grid* g, const po_prt* prts_in,
       }
     }
   }
-  off_out[np] = cur;
   if (n_dropped) {
     *n_dropped = dropped;
   }
