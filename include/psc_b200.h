@@ -168,6 +168,24 @@ int psc_b200_push_H(psc_b200_ctx* ctx, double dt_fac);
 int psc_b200_marder(psc_b200_ctx* ctx, double diffusion, int loop);
 /* ---- Moment_rho_1st_nc incl. ghost add (psc/moment.hxx:149-171) into comp 0 of field_id ---- */
 int psc_b200_moment_rho_1st_nc(psc_b200_ctx* ctx, int field_id);
+/* ---- the 1st-order moments a deck's diagnostics and injectors use
+ * (libpsc/psc_output_fields/fields_item_moments_1st.hxx:9-37 = ItemMoment<moment_*> of
+ * include/psc/moment.hxx:119-311): Moment_n_1st, Moment_v_1st, Moment_p_1st, Moment_T_1st,
+ * Moments_1st ("all": rho jx jy jz px py pz txx tyy tzz txy tyz tzx per kind) at cell
+ * centres, Moment_rho_1st_nc at nodes.  The field must have psc_b200_moment_n_comps()
+ * components; the result includes the reflecting-wall folds and the ghost add
+ * (include/fields_item.hxx:36-134), like the reference's. ---- */
+enum
+{
+  PSC_B200_MOMENT_N = 0,
+  PSC_B200_MOMENT_V = 1,
+  PSC_B200_MOMENT_P = 2,
+  PSC_B200_MOMENT_T = 3,
+  PSC_B200_MOMENT_ALL = 4,
+  PSC_B200_MOMENT_RHO_NC = 5
+};
+int psc_b200_moment_n_comps(psc_b200_ctx* ctx, int moment);
+int psc_b200_moment_1st(psc_b200_ctx* ctx, int field_id, int moment);
 /* ---- Checks (checks_impl.hxx:33-215) ---- */
 int psc_b200_check_continuity_begin(psc_b200_ctx* ctx);
 int psc_b200_check_continuity_end(psc_b200_ctx* ctx, double* max_err);

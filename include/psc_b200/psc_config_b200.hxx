@@ -42,6 +42,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <string>
 #include <vector>
 
 namespace psc_b200
@@ -569,6 +570,50 @@ struct MarderB200
   double diffusion_;
   int loop_;
 };
+
+// ItemMoment (include/fields_item.hxx:97-134) over the device-side 1st-order moments of
+// libpsc/psc_output_fields/fields_item_moments_1st.hxx:9-37: same call shape as the
+// reference's items -- construct from the grid, call on the particles, get the result
+// container (ghost add and reflecting folds done) -- so OutputFields / the flatfoil
+// injector can take them without a device -> host particle copy.
+template <typename GridT, int WHICH>
+class MomentB200
+{
+public:
+  using Mparticles = MparticlesB200<GridT>;
+  using Mfields = MfieldsB200<GridT>;
+
+  static std::string name()
+  {
+    static const char* names[] = {"n_1st_cc", "v_1st_cc", "p_1st_cc", "T_1st_cc", "all_1st_cc", "rho_1st_nc"};
+    return names[WHICH];
+  }
+  explicit MomentB200(const GridT& grid)
+    : mres_(grid, psc_b200_moment_n_comps(Context<GridT>::get(grid)->ctx(), WHICH))
+  {}
+  int n_comps() const { return mres_.n_comps(); }
+  Mfields& operator()(Mparticles& mprts)
+  {
+    PSC_B200_CHECK(psc_b200_moment_1st(mprts.ctx(), mres_.id(), WHICH));
+    return mres_;
+  }
+
+private:
+  Mfields mres_;
+};
+
+template <typename GridT>
+using Moment_n_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_N>;
+template <typename GridT>
+using Moment_v_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_V>;
+template <typename GridT>
+using Moment_p_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_P>;
+template <typename GridT>
+using Moment_T_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_T>;
+template <typename GridT>
+using Moments_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_ALL>;
+template <typename GridT>
+using Moment_rho_1st_nc_B200 = MomentB200<GridT, PSC_B200_MOMENT_RHO_NC>;
 
 // ChecksParams (checks_params.hxx): the cadence/threshold fields the step loop reads
 struct ChecksParamsB200

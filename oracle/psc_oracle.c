@@ -1104,6 +1104,184 @@ void po_moment_rho_1st_nc(const po_grid* g, const po_prt* prts,
   po_add_ghosts(g, rho, 1, 0, 1);
 }
 
+/* ---------------------------------------------------------------------- */
+/* the 1st-order moment family:
+ * Moment_n_1st / Moment_v_1st / Moment_p_1st / Moment_T_1st / Moments_1st
+ * (fields_item_moments_1st.hxx:9-30) = ItemMoment<moment_*<Deposit1stCc>>, and
+ * Moment_rho_1st_nc (:35-37).  psc/moment.hxx:119-311 (what is deposited, in which
+ * order), psc/deposit.hxx:24-65 (weights), :172-212 (cell / node centring), :262-285
+ * (code units: x / dx, fnqs * val), fields_item.hxx:36-134 (zeros, moment, reflecting
+ * folds, add_ghosts), add_ghosts_reflecting.hxx:7-70 (cc), :72-154 (nc). */
+
+int po_moment_n_comps(const po_grid* g, int which)
+{
+  switch (which) {
+    case PO_MOM_N: return g->n_kinds;
+    case PO_MOM_V: return 3 * g->n_kinds;
+    case PO_MOM_P: return 3 * g->n_kinds;
+    case PO_MOM_T: return 6 * g->n_kinds;
+    case PO_MOM_ALL: return 13 * g->n_kinds;
+    case PO_MOM_RHO_NC: return 1;
+  }
+  return 0;
+}
+
+/* add_ghosts_reflecting.hxx:7-70 (cell-centred), component m of a patch */
+static void add_ghosts_reflecting_cc(const po_grid* g, float* R, int m, int d, int hi)
+{
+  int b[3], e[3];
+  for (int a = 0; a < 3; a++) {
+    b[a] = g->ib[a];
+    e[a] = g->ldims[a] - g->ib[a];
+  }
+  if (!hi) {
+    b[d] = 0;
+    e[d] = -g->ib[d];
+  } else {
+    b[d] = g->ldims[d] + g->ib[d];
+    e[d] = g->ldims[d];
+  }
+  int idx[3];
+  for (idx[2] = b[2]; idx[2] < e[2]; idx[2]++) {
+    for (idx[1] = b[1]; idx[1] < e[1]; idx[1]++) {
+      for (idx[0] = b[0]; idx[0] < e[0]; idx[0]++) {
+        int r[3] = {idx[0], idx[1], idx[2]};
+        r[d] = hi ? 2 * g->ldims[d] - idx[d] - 1 : -idx[d] - 1;
+        FLD(R, g, m, idx[0], idx[1], idx[2]) += FLD(R, g, m, r[0], r[1], r[2]);
+      }
+    }
+  }
+}
+
+static void deposit_1st(const po_grid* g, float* R, int m, const int l[3], const float h[3],
+                        float value)
+{
+  if (g->invar[0]) {
+    FLD(R, g, m, 0, l[1] + 0, l[2] + 0) += value * (1.f - h[1]) * (1.f - h[2]);
+    FLD(R, g, m, 0, l[1] + 1, l[2] + 0) += value * h[1] * (1.f - h[2]);
+    FLD(R, g, m, 0, l[1] + 0, l[2] + 1) += value * (1.f - h[1]) * h[2];
+    FLD(R, g, m, 0, l[1] + 1, l[2] + 1) += value * h[1] * h[2];
+  } else {
+    /* clang-format off */
+    FLD(R, g, m, l[0] + 0, l[1] + 0, l[2] + 0) += value * (1.f - h[0]) * (1.f - h[1]) * (1.f - h[2]);
+    FLD(R, g, m, l[0] + 1, l[1] + 0, l[2] + 0) += value *        h[0]  * (1.f - h[1]) * (1.f - h[2]);
+    FLD(R, g, m, l[0] + 0, l[1] + 1, l[2] + 0) += value * (1.f - h[0]) *        h[1]  * (1.f - h[2]);
+    FLD(R, g, m, l[0] + 1, l[1] + 1, l[2] + 0) += value *        h[0]  *        h[1]  * (1.f - h[2]);
+    FLD(R, g, m, l[0] + 0, l[1] + 0, l[2] + 1) += value * (1.f - h[0]) * (1.f - h[1]) *        h[2];
+    FLD(R, g, m, l[0] + 1, l[1] + 0, l[2] + 1) += value *        h[0]  * (1.f - h[1]) *        h[2];
+    FLD(R, g, m, l[0] + 0, l[1] + 1, l[2] + 1) += value * (1.f - h[0]) *        h[1]  *        h[2];
+    FLD(R, g, m, l[0] + 1, l[1] + 1, l[2] + 1) += value *        h[0]  *        h[1]  *        h[2];
+    /* clang-format on */
+  }
+}
+
+void po_moment_1st(const po_grid* g, const po_prt* prts, const unsigned* off, int which,
+                   float* out)
+{
+  const int nc = po_moment_n_comps(g, which);
+  const long plen = po_fld_patch_len(g) * nc;
+  const int cc = which != PO_MOM_RHO_NC;
+  memset(out, 0, sizeof(float) * plen * g->n_patches);
+  float dxi[3];
+  for (int d = 0; d < 3; d++) {
+    dxi[d] = 1.f / (float)g->dx[d]; /* deposit.hxx:272 real_t(1.)/dx */
+  }
+  const float fnqs = (float)g->fnqs;
+  for (int p = 0; p < g->n_patches; p++) {
+    float* R = out + p * plen;
+    for (unsigned n = off[p]; n < off[p + 1]; n++) {
+      const po_prt* prt = &prts[n];
+      const int kind = prt->kind;
+      const float q = (float)g->q[kind], m = (float)g->m[kind];
+      const float w = prt->qni_wni / q; /* const_accessor_simple.hxx:60-63 */
+      const float* u = prt->u;
+      int l[3];
+      float h[3];
+      for (int d = 0; d < 3; d++) {
+        float x = prt->x[d] * dxi[d];
+        if (cc) {
+          l[d] = (int)floorf(x - .5f);
+          h[d] = x - .5f - (float)l[d];
+        } else {
+          l[d] = (int)floorf(x);
+          h[d] = x - (float)l[d];
+        }
+      }
+      float vxi[3];
+      {
+        float root = 1.f / sqrtf(1.f + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        for (int d = 0; d < 3; d++) {
+          vxi[d] = u[d] * root;
+        }
+      }
+      int mm[13];
+      float val[13];
+      int nv = 0;
+      switch (which) {
+        case PO_MOM_N: mm[0] = kind, val[0] = w, nv = 1; break;
+        case PO_MOM_RHO_NC: mm[0] = 0, val[0] = w * q, nv = 1; break;
+        case PO_MOM_V:
+          for (int d = 0; d < 3; d++) {
+            mm[d] = d + 3 * kind, val[d] = w * vxi[d];
+          }
+          nv = 3;
+          break;
+        case PO_MOM_P:
+          for (int d = 0; d < 3; d++) {
+            mm[d] = d + 3 * kind, val[d] = w * m * u[d];
+          }
+          nv = 3;
+          break;
+        case PO_MOM_T: {
+          const int a[6] = {0, 1, 2, 0, 0, 1}, b[6] = {0, 1, 2, 1, 2, 2};
+          for (int k = 0; k < 6; k++) {
+            mm[k] = 6 * kind + k, val[k] = w * m * u[a[k]] * vxi[b[k]];
+          }
+          nv = 6;
+          break;
+        }
+        case PO_MOM_ALL: {
+          const int a[6] = {0, 1, 2, 0, 1, 2}, b[6] = {0, 1, 2, 1, 2, 0};
+          mm[0] = 13 * kind, val[0] = w * q;
+          for (int d = 0; d < 3; d++) {
+            mm[1 + d] = 13 * kind + 1 + d, val[1 + d] = w * q * vxi[d];
+            mm[4 + d] = 13 * kind + 4 + d, val[4 + d] = w * m * u[d];
+          }
+          for (int k = 0; k < 6; k++) {
+            mm[7 + k] = 13 * kind + 7 + k, val[7 + k] = w * m * u[a[k]] * vxi[b[k]];
+          }
+          nv = 13;
+          break;
+        }
+      }
+      for (int k = 0; k < nv; k++) {
+        deposit_1st(g, R, mm[k], l, h, fnqs * val[k]);
+      }
+    }
+  }
+  /* ItemMomentBnd::add_ghosts, fields_item.hxx:36-90 */
+  for (int p = 0; p < g->n_patches; p++) {
+    float* R = out + p * plen;
+    for (int hi = 0; hi < 2; hi++) {
+      for (int d = 0; d < 3; d++) {
+        int at = hi ? at_boundary_hi(g, p, d) : at_boundary_lo(g, p, d);
+        int bc = hi ? g->bc_prt_hi[d] : g->bc_prt_lo[d];
+        if (!at || bc != PO_BND_PRT_REFLECTING) {
+          continue;
+        }
+        if (cc) {
+          for (int m = 0; m < nc; m++) {
+            add_ghosts_reflecting_cc(g, R, m, d, hi);
+          }
+        } else {
+          add_ghosts_reflecting_nc(g, R, d, hi);
+        }
+      }
+    }
+  }
+  po_add_ghosts(g, out, nc, 0, nc);
+}
+
 /* fields_item_fields.hxx:65-104: float difference, divided by double dx,
  * accumulated through the float result array axis by axis */
 void po_div_nc(const po_grid* g, const float* flds, int n_comps, int m0,

@@ -155,6 +155,21 @@ void po_bndf_add_ghosts_J(const po_grid* g, float* flds);
  * into a 1-component array with the grid's im/ib, INCLUDING the ghost add */
 void po_moment_rho_1st_nc(const po_grid* g, const po_prt* prts,
                           const unsigned* off, float* rho);
+/* the 1st-order moment family (fields_item_moments_1st.hxx:9-37): n, v, p, T, "all" (13 per
+ * kind) at cell centres, rho at nodes; out has po_moment_n_comps() components with the
+ * grid's im/ib; reflecting-wall folds and the ghost add included */
+enum
+{
+  PO_MOM_N = 0,
+  PO_MOM_V = 1,
+  PO_MOM_P = 2,
+  PO_MOM_T = 3,
+  PO_MOM_ALL = 4,
+  PO_MOM_RHO_NC = 5
+};
+int po_moment_n_comps(const po_grid* g, int which);
+void po_moment_1st(const po_grid* g, const po_prt* prts, const unsigned* off, int which,
+                   float* out);
 /* psc::item::div_nc (fields_item_fields.hxx:65-104) of components m0..m0+2 of
  * flds into a 1-component array (interior points only, ghosts left 0) */
 void po_div_nc(const po_grid* g, const float* flds, int n_comps, int m0,

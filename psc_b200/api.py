@@ -309,6 +309,35 @@ class PushFields:
         check(g.lib.psc_b200_push_H(g.ctx, dt_fac))
 
 
+MOMENT_N, MOMENT_V, MOMENT_P, MOMENT_T, MOMENT_ALL, MOMENT_RHO_NC = range(6)
+
+
+class Moment:
+    """ItemMoment (include/fields_item.hxx:97-134) for the 1st-order moments of
+    fields_item_moments_1st.hxx:9-37: Moment(grid, MOMENT_N)(mprts) -> Mfields with the
+    moment's components (ghost add and reflecting folds done), like Moment_n_1st{grid}(mprts)"""
+
+    NAMES = {MOMENT_N: "n_1st_cc", MOMENT_V: "v_1st_cc", MOMENT_P: "p_1st_cc", MOMENT_T: "T_1st_cc",
+             MOMENT_ALL: "all_1st_cc", MOMENT_RHO_NC: "rho_1st_nc"}
+
+    def __init__(self, grid, which):
+        self.grid_, self.which = grid, which
+        self.n_comps_ = grid.lib.psc_b200_moment_n_comps(grid.ctx, which)
+        if self.n_comps_ <= 0:
+            raise ValueError("unknown moment %r" % (which,))
+        self.mres = Mfields(grid, self.n_comps_)
+
+    def name(self):
+        return self.NAMES[self.which]
+
+    def n_comps(self):
+        return self.n_comps_
+
+    def __call__(self, mprts):
+        check(self.grid_.lib.psc_b200_moment_1st(self.grid_.ctx, self.mres.id, self.which))
+        return self.mres
+
+
 class Marder:
     """MarderB200 (marder_impl.hxx:150-264): Marder(grid, diffusion, loop, dump)"""
 

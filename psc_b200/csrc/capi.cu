@@ -582,6 +582,16 @@ int psc_b200_marder(psc_b200_ctx* ctx, double diffusion, int loop)
   GUARD(PSC_TRY(store_ready(c)); return marder(c, diffusion, loop);)
 }
 
+int psc_b200_moment_n_comps(psc_b200_ctx* ctx, int moment)
+{
+  return ctx ? moment_n_comps(CTX(ctx), moment) : -1;
+}
+
+int psc_b200_moment_1st(psc_b200_ctx* ctx, int field_id, int moment)
+{
+  GUARD(PSC_TRY(store_ready(c)); return moment_1st(c, field_id, moment);)
+}
+
 int psc_b200_moment_rho_1st_nc(psc_b200_ctx* ctx, int field_id)
 {
   GUARD(PSC_TRY(store_ready(c)); return moment_rho_1st_nc(c, field_id);)

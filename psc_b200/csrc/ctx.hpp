@@ -248,6 +248,8 @@ int bndf_add_ghosts_J(Ctx* c);
 int push_E(Ctx* c, double dt_fac);
 int push_H(Ctx* c, double dt_fac);
 int moment_rho_1st_nc(Ctx* c, int id);
+int moment_n_comps(const Ctx* c, int which);
+int moment_1st(Ctx* c, int id, int which);
 int marder(Ctx* c, double diffusion, int loop);
 int check_continuity_begin(Ctx* c);
 int check_continuity_end(Ctx* c, double* err);

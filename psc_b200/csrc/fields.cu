@@ -824,6 +824,223 @@ int push_H(Ctx* c, double dt_fac)
 
 // ---------------------------------------------------------------- moments / checks / Marder
 
+namespace
+{
+
+// ---- the 1st-order moment family (psc/moment.hxx:119-311, psc/deposit.hxx:24-65,
+// 172-212, 262-285): one thread per particle, up to 13 values per particle deposited
+// with the 1st-order weights to the cell centres (n, v, p, T, all) or the nodes (rho)
+struct MomentPrm
+{
+  int which; // PSC_B200_MOMENT_*
+  float fnqs;
+  float q[pm::MAX_KINDS], m[pm::MAX_KINDS];
+};
+
+__global__ void __launch_bounds__(256)
+  k_moment_1st(GridDev G, MomentPrm M, uint32_t n, const uint32_t* __restrict__ off,
+               const float4* __restrict__ xi4, const float4* __restrict__ pxi4, float* __restrict__ R,
+               long slot_len)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  const int p = patch_of(off, G.n_patches, i);
+  const float4 X = xi4[i], U = pxi4[i];
+  const int kind = __float_as_int(X.w);
+  const float q = M.q[kind], ms = M.m[kind];
+  const float w = U.w / q; // const_accessor_simple.hxx:60-63
+  const float u[3] = {U.x, U.y, U.z};
+  const float x[3] = {X.x, X.y, X.z};
+  const bool cc = M.which != PSC_B200_MOMENT_RHO_NC;
+  int l[3];
+  float h[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const float xn = x[d] * G.pc.dxi[d];
+    if (cc) {
+      l[d] = pm::fint(xn - .5f);
+      h[d] = xn - .5f - (float)l[d];
+    } else {
+      l[d] = pm::fint(xn);
+      h[d] = xn - (float)l[d];
+    }
+  }
+  float vxi[3];
+  {
+    const float root = pm::rsqrt_ref(1.f + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      vxi[d] = u[d] * root;
+    }
+  }
+  int m0 = 0, nv = 0;
+  float val[13];
+  switch (M.which) {
+    case PSC_B200_MOMENT_N: m0 = kind, val[0] = w, nv = 1; break;
+    case PSC_B200_MOMENT_RHO_NC: m0 = 0, val[0] = w * q, nv = 1; break;
+    case PSC_B200_MOMENT_V:
+      m0 = 3 * kind, nv = 3;
+      for (int d = 0; d < 3; d++) {
+        val[d] = w * vxi[d];
+      }
+      break;
+    case PSC_B200_MOMENT_P:
+      m0 = 3 * kind, nv = 3;
+      for (int d = 0; d < 3; d++) {
+        val[d] = w * ms * u[d];
+      }
+      break;
+    case PSC_B200_MOMENT_T: {
+      const int a[6] = {0, 1, 2, 0, 0, 1}, b[6] = {0, 1, 2, 1, 2, 2};
+      m0 = 6 * kind, nv = 6;
+      for (int k = 0; k < 6; k++) {
+        val[k] = w * ms * u[a[k]] * vxi[b[k]];
+      }
+      break;
+    }
+    default: { // PSC_B200_MOMENT_ALL
+      const int a[6] = {0, 1, 2, 0, 1, 2}, b[6] = {0, 1, 2, 1, 2, 0};
+      m0 = 13 * kind, nv = 13;
+      val[0] = w * q;
+      for (int d = 0; d < 3; d++) {
+        val[1 + d] = w * q * vxi[d];
+        val[4 + d] = w * ms * u[d];
+      }
+      for (int k = 0; k < 6; k++) {
+        val[7 + k] = w * ms * u[a[k]] * vxi[b[k]];
+      }
+    }
+  }
+  float* Rp = R + p * slot_len;
+  const bool yz = G.dim == pm::DIM_YZ;
+  // corner weights in the reference's association: value * wx * wy * wz
+  for (int k = 0; k < nv; k++) {
+    const float value = M.fnqs * val[k];
+    for (int c = yz ? 0 : 0; c < 8; c++) {
+      const int ox = c & 1, oy = (c >> 1) & 1, oz = c >> 2;
+      if (yz && ox) {
+        continue;
+      }
+      float wgt = value;
+      if (!yz) {
+        wgt = wgt * (ox ? h[0] : 1.f - h[0]);
+      }
+      wgt = wgt * (oy ? h[1] : 1.f - h[1]) * (oz ? h[2] : 1.f - h[2]);
+      atomicAdd(Rp + fld_off(G, m0 + k, yz ? 0 : l[0] + ox, l[1] + oy, l[2] + oz), wgt);
+    }
+  }
+}
+
+// add_ghosts_reflecting.hxx:7-70, cell-centred, one (d, hi) at a time, all components
+__global__ void k_reflect_cc(GridDev G, float* __restrict__ R, long slot_len, int n_comps, int d, int hi,
+                             const pm::PatchBnd* __restrict__ pbs)
+{
+  int b[3], e[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    b[a] = -G.ibn[a];
+    e[a] = G.ldims[a] + G.ibn[a];
+  }
+  if (!hi) {
+    b[d] = 0;
+    e[d] = G.ibn[d];
+  } else {
+    b[d] = G.ldims[d] - G.ibn[d];
+    e[d] = G.ldims[d];
+  }
+  const int n0 = max(e[0] - b[0], 0), n1 = max(e[1] - b[1], 0), n2 = max(e[2] - b[2], 0);
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * n_comps * n0 * n1 * n2) {
+    return;
+  }
+  int c[3];
+  c[0] = b[0] + (int)(idx % n0);
+  idx /= n0;
+  c[1] = b[1] + (int)(idx % n1);
+  idx /= n1;
+  c[2] = b[2] + (int)(idx % n2);
+  idx /= n2;
+  const int m = (int)(idx % n_comps);
+  const int p = (int)(idx / n_comps);
+  const pm::PatchBnd pb = pbs[p];
+  const bool at = ((hi ? pb.at_hi : pb.at_lo) >> d) & 1;
+  const int bc = hi ? pb.bc_hi[d] : pb.bc_lo[d];
+  if (!at || bc != pm::BND_PRT_REFLECTING) {
+    return;
+  }
+  int r[3] = {c[0], c[1], c[2]};
+  r[d] = hi ? 2 * G.ldims[d] - c[d] - 1 : -c[d] - 1;
+  float* Rp = R + p * slot_len;
+  Rp[fld_off(G, m, c[0], c[1], c[2])] += Rp[fld_off(G, m, r[0], r[1], r[2])];
+}
+
+} // namespace
+
+int moment_n_comps(const Ctx* c, int which)
+{
+  const int nk = c->g.desc.n_kinds;
+  switch (which) {
+    case PSC_B200_MOMENT_N: return nk;
+    case PSC_B200_MOMENT_V: return 3 * nk;
+    case PSC_B200_MOMENT_P: return 3 * nk;
+    case PSC_B200_MOMENT_T: return 6 * nk;
+    case PSC_B200_MOMENT_ALL: return 13 * nk;
+    case PSC_B200_MOMENT_RHO_NC: return 1;
+  }
+  return -1;
+}
+
+// ItemMoment::operator() (fields_item.hxx:117-129): zeros, moment, reflecting folds, add_ghosts
+int moment_1st(Ctx* c, int id, int which)
+{
+  const int nc = moment_n_comps(c, which);
+  if (nc < 0) {
+    return fail("moment_1st: unknown moment");
+  }
+  PSC_TRY(check_field(c, id, 0, nc));
+  if (c->flds[id].n_comps != nc) {
+    return fail("moment_1st: the field must have exactly the moment's components");
+  }
+  const GridDev& G = c->gd;
+  // local patches and proxies (they receive neighbours' ghost sums)
+  PSC_CUDA_TRY(cudaMemsetAsync(c->fld(id), 0, (size_t)c->n_slots * c->fld_slot_len(id) * sizeof(float),
+                               c->stream));
+  MomentPrm M{};
+  M.which = which;
+  M.fnqs = (float)c->g.desc.fnqs;
+  for (int k = 0; k < c->g.desc.n_kinds; k++) {
+    M.q[k] = (float)c->g.desc.q[k];
+    M.m[k] = (float)c->g.desc.m[k];
+  }
+  if (c->n_prts) {
+    KernelScope ks(c, "moment_1st");
+    k_moment_1st<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(G, M, c->n_prts, c->d_off, c->xi(), c->pxi(),
+                                                                c->fld(id), c->fld_slot_len(id));
+    c->n_launches++;
+  }
+  for (int hi = 0; hi < 2; hi++) {
+    for (int d = 0; d < 3; d++) {
+      const int bc = hi ? c->g.desc.bc_prt_hi[d] : c->g.desc.bc_prt_lo[d];
+      if (bc != PSC_B200_BND_PRT_REFLECTING || c->g.invar[d]) {
+        continue;
+      }
+      const size_t n = (size_t)G.n_patches * nc * G.fld_len;
+      if (which == PSC_B200_MOMENT_RHO_NC) {
+        k_reflect_nc<<<div_up(n, 256), 256, 0, c->stream>>>(G, c->fld(id), c->fld_slot_len(id), d, hi,
+                                                           c->d_patch_bnd);
+      } else {
+        k_reflect_cc<<<div_up(n, 256), 256, 0, c->stream>>>(G, c->fld(id), c->fld_slot_len(id), nc, d, hi,
+                                                           c->d_patch_bnd);
+      }
+      c->n_launches++;
+    }
+  }
+  PSC_TRY(check_launch(c, "moment_1st"));
+  return bnd_add_ghosts(c, id, 0, nc);
+}
+
 int moment_rho_1st_nc(Ctx* c, int id)
 {
   PSC_TRY(check_field(c, id, 0, 1));

@@ -88,11 +88,20 @@ struct GeoStatic
 {
   int nt_[3];
   static constexpr bool XYZ = DIM == pm::DIM_XYZ;
-  __host__ __device__ static constexpr int t(int d) { return XYZ ? 8 : (d == 0 ? 1 : 16); }
+#ifndef PUSH_TILE_X
+#define PUSH_TILE_X 8
+#define PUSH_TILE_Y 8
+#define PUSH_TILE_Z 8
+#endif
+  __host__ __device__ static constexpr int t(int d)
+  {
+    return XYZ ? (d == 0 ? PUSH_TILE_X : (d == 1 ? PUSH_TILE_Y : PUSH_TILE_Z)) : (d == 0 ? 1 : 16);
+  }
   __host__ __device__ int nt(int d) const { return nt_[d]; }
   __host__ __device__ static constexpr int f(int d)
   {
-    return XYZ ? (d == 0 ? 12 : 11) : (d == 0 ? 1 : (d == 1 ? 20 : 19));
+    return XYZ ? (d == 0 ? PUSH_TILE_X + 4 : (d == 1 ? PUSH_TILE_Y + 3 : PUSH_TILE_Z + 3))
+               : (d == 0 ? 1 : (d == 1 ? 20 : 19));
   }
   __host__ __device__ static constexpr int g(int d)
   {

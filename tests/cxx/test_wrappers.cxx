@@ -135,6 +135,22 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
   wr(flds1.data(), flds1.size() * 4);
   double tail[10] = {max_cont, sum_w, en[0], en[1], en[2], en[3], en[4], en[5], en[6], en[7]};
   wr(tail, sizeof(tail));
+  // device-side moments through the ItemMoment-shaped wrappers
+  // (fields_item_moments_1st.hxx:9-30): density per kind and the 13-component set
+  {
+    psc_b200::Moment_n_1st_B200<Grid> mom_n{grid};
+    psc_b200::Moments_1st_B200<Grid> mom_all{grid};
+    auto& mn = mom_n(mprts);
+    auto& ma = mom_all(mprts);
+    std::vector<float> hn = mn.download(0, mn.n_comps()), ha = ma.download(0, ma.n_comps());
+    int nn[2] = {(int)hn.size(), (int)ha.size()};
+    wr(nn, sizeof(nn));
+    wr(hn.data(), hn.size() * 4);
+    wr(ha.data(), ha.size() * 4);
+    if (mom_n.name() != "n_1st_cc" || mom_all.name() != "all_1st_cc" || mn.n_comps() != 2 || ma.n_comps() != 26) {
+      return 4;
+    }
+  }
   std::fclose(f);
   std::printf("ok: %zu particles, %d steps, continuity %.3g, sum w %.1f\n", prts1.size(), n_steps,
               max_cont, sum_w);

@@ -138,3 +138,55 @@ def rho_nc_norm(ldims, x, yz):
                          * (h[2] if dz else 1 - h[2]))
                     rho[l[2] + dz, l[1] + dy, l[0] + dx] += w
     return rho
+
+
+# ----------------------------------------------------------------------------
+# moments: src/libpsc/tests/test_moments.cxx:52-143 fixture (16^3 cells or 1 x 16 x 16,
+# L = 160 => dx = 10, one kind q = m = 1, nicell 200, one particle of weight .4) and the
+# expectations of its TYPED_TESTs: only component 0 is checked, over the patch interior,
+# tolerance eps = 1e-6
+MOMENT_W, MOMENT_NICELL = .4, 200
+MOMENT_CASES = [
+    # name, moment, particle x, u, expected (cell or node) -> value factor for xyz / yz
+    dict(name="Moment_n_1", which=ol.MOM_N, x=(5., 5., 5.), u=(0., 0., 1.), ref="test_moments.cxx:149-176",
+         xyz={(0, 0, 0): 1.}, yz={(0, 0, 0): 1.}),
+    dict(name="Moments_1st", which=ol.MOM_ALL, x=(5., 5., 5.), u=(0., 0., 1.), ref=":178-206",
+         xyz={(0, 0, 0): 1.}, yz={(0, 0, 0): 1.}),
+    dict(name="Moment_n_2", which=ol.MOM_N, x=(25., 5., 5.), u=(0., 0., 1.), ref=":236-264",
+         xyz={(2, 0, 0): 1.}, yz={(0, 0, 0): 1.}),
+    dict(name="Moment_v_1st", which=ol.MOM_V, x=(5., 5., 5.), u=(.001, .002, .003), ref=":266-292",
+         xyz={(0, 0, 0): .001}, yz={(0, 0, 0): .001}),
+    dict(name="Moment_p_1st", which=ol.MOM_P, x=(5., 5., 5.), u=(.001, .002, .003), ref=":294-320",
+         xyz={(0, 0, 0): .001}, yz={(0, 0, 0): .001}),
+    dict(name="Moment_rho_1st_nc_cc", which=ol.MOM_RHO_NC, x=(5., 5., 5.), u=(0., 0., 0.), ref=":322-364",
+         xyz={(i, j, k): 1. / 8. for i in (0, 1) for j in (0, 1) for k in (0, 1)},
+         yz={(0, j, k): 1. / 4. for j in (0, 1) for k in (0, 1)}),
+    dict(name="Moment_rho_1st_nc_nc", which=ol.MOM_RHO_NC, x=(10., 10., 10.), u=(0., 0., 0.), ref=":366-402",
+         xyz={(1, 1, 1): 1.}, yz={(0, 1, 1): 1.}),
+]
+
+
+def moment_case_grid(case, dim):
+    yz = dim == "yz"
+    g = ol.Grid(gdims=(1 if yz else 16, 16, 16), length=(160., 160., 160.), np_=(1, 1, 1), dt=1.,
+                kinds=((1., 1.),), nicell=MOMENT_NICELL)
+    prts = np.zeros(1, dtype=ol.PRT_DTYPE)
+    prts["x"][0] = case["x"]
+    prts["u"][0] = case["u"]
+    prts["kind"][0] = 0
+    prts["qni_wni"][0] = MOMENT_W  # q = 1
+    return g, prts, ol.off_from_counts([1])
+
+
+def moment_case_expected(case, dim, grid):
+    """component 0 over the interior, as the reference's loops check it"""
+    ld, ib = grid.ldims, grid.ib
+    exp = np.zeros((ld[2], ld[1], ld[0]))
+    for (i, j, k), f in case[dim].items():
+        exp[k, j, i] = MOMENT_W / MOMENT_NICELL * f
+    return exp
+
+
+def moment_interior_comp0(grid, arr):
+    ld, ib = grid.ldims, grid.ib
+    return arr[0, 0, -ib[2]:-ib[2] + ld[2], -ib[1]:-ib[1] + ld[1], -ib[0]:-ib[0] + ld[0]]

@@ -93,6 +93,8 @@ def lib():
         L.po_bndf_add_ghosts_J.argtypes = [G, P]
         L.po_moment_rho_1st_nc.argtypes = [G, P, P, P]
         L.po_div_nc.argtypes = [G, P, C.c_int, C.c_int, P]
+        L.po_moment_n_comps.argtypes = [G, C.c_int]
+        L.po_moment_1st.argtypes = [G, P, P, C.c_int, P]
         L.po_continuity.argtypes = [G, P, P, P]
         L.po_continuity.restype = C.c_double
         L.po_gauss.argtypes = [G, P, P]
@@ -299,6 +301,17 @@ def moment_rho(grid, prts, off):
     rho = grid.zeros_fields(1)
     lib().po_moment_rho_1st_nc(grid.byref(), ptr(prts), ptr(off), ptr(rho))
     return rho
+
+
+MOM_N, MOM_V, MOM_P, MOM_T, MOM_ALL, MOM_RHO_NC = range(6)
+
+
+def moment_1st(grid, prts, off, which):
+    """Moment_{n,v,p,T}_1st / Moments_1st (cell-centred) / Moment_rho_1st_nc"""
+    nc = lib().po_moment_n_comps(grid.byref(), which)
+    out = grid.zeros_fields(nc)
+    lib().po_moment_1st(grid.byref(), ptr(prts), ptr(off), which, ptr(out))
+    return out
 
 
 def div_nc(grid, flds, m0):

@@ -50,7 +50,10 @@ def _read_dump(path):
     prts1 = take(PRT_DTYPE, n1)
     flds1 = take(np.float32, nf)
     tail = take(np.float64, 10)
-    return hdr, off0, prts0, flds0, off1, prts1, flds1, tail
+    nn = take(np.int32, 2)
+    mom_n = take(np.float32, int(nn[0]))
+    mom_all = take(np.float32, int(nn[1]))
+    return hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all
 
 
 @pytest.mark.gpu
@@ -61,7 +64,7 @@ def test_wrappers_match_oracle(dim, fused, tmp_path):
     out = str(tmp_path / "dump.bin")
     r = subprocess.run([exe, out, dim, str(N_STEPS), str(fused)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    hdr, off0, prts0, flds0, off1, prts1, flds1, tail = _read_dump(out)
+    hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all = _read_dump(out)
     if dim == "yz":
         og = ol.Grid(gdims=(1, 16, 32), length=(1., 20., 30.), np_=(1, 2, 2), dt=0.3, kinds=KINDS, nicell=6)
     else:
@@ -94,3 +97,9 @@ def test_wrappers_match_oracle(dim, fused, tmp_path):
         assert np.abs(a["u"][ka] - b["u"][kb]).max() <= 1e-5
     ref_en = ol.energies(og, f, rp, ro)
     np.testing.assert_allclose(tail[2:10], ref_en, rtol=1e-4)
+    # Moment_n_1st / Moments_1st wrappers on the final particles (the dump's, so the inputs
+    # are identical; only the summation order differs: atomics)
+    for got, which in ((mom_n, ol.MOM_N), (mom_all, ol.MOM_ALL)):
+        ref = ol.moment_1st(og, prts1, off1, which)
+        got = got.reshape(ref.shape)
+        assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max()

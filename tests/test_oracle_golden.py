@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import golden_cases as gc
 import oracle_lib as ol
 from golden_cases import (GOLDEN, run_push_case, deposit_grid, rho_nc_norm,
                           push_fixture_grid, inject)
@@ -138,3 +139,14 @@ def test_sort_known_answer():
     offs = np.concatenate([[0], np.cumsum(cnt)])
     assert offs[1] == 2 and all(offs[2:10] == 6) and all(offs[10:83] == 9)
     assert offs[83] == 11 and all(offs[84:92] == 13) and all(offs[92:257] == 15)
+
+
+@pytest.mark.parametrize("dim", ["xyz", "yz"])
+@pytest.mark.parametrize("case", gc.MOMENT_CASES, ids=[c["name"] for c in gc.MOMENT_CASES])
+def test_oracle_moment_known_answers(case, dim):
+    """the oracle's moment family on the reference's known-answer cases
+    (src/libpsc/tests/test_moments.cxx:149-402, eps 1e-6)"""
+    og, prts, off = gc.moment_case_grid(case, dim)
+    got = gc.moment_interior_comp0(og, ol.moment_1st(og, prts, off, case["which"]))
+    exp = gc.moment_case_expected(case, dim, og)
+    assert np.abs(got - exp).max() < 1e-6
