@@ -72,9 +72,12 @@ def test_push_matches_oracle(name, vth, path, fma):
     jr, jg = f_ref[:, :3], f_gpu[:, :3]
     scale = np.abs(jr).max()
     assert scale > 0
-    # J sums thousands of +/- contributions per node; with FMA contraction each one may
-    # differ in the last bit, so the FMA build gets 3e-5 of max|J| (exact build: 1e-5)
-    assert np.abs(jg - jr).max() <= (1e-5 if fma == 0 else 3e-5) * scale
+    # exact build: only the summation order differs (measured 3-5e-7 of max|J|).  FMA build:
+    # x is held to the reference's rounding (pic_math.cuh advance), but u differs in the last
+    # bits, so ~0.1 % of the particles land one ULP off and each of those changes its own
+    # deposit by ~1e-4; at the 6-12 particles per cell of these cases that shows as up to
+    # 1.0e-5 of max|J| (tools/jerr_probe.py), less at production particle counts
+    assert np.abs(jg - jr).max() <= (1e-5 if fma == 0 else 1.5e-5) * scale
 
 
 @pytest.mark.parametrize("path", ["general", "tiled_warp"])
