@@ -290,6 +290,35 @@ static int push_mprts(Ctx* c)
   return c->opt_fma ? push_mprts_fast(c) : push_mprts_exact(c);
 }
 
+// ---- the particle operators as a deck calls them (psc.hxx:359, :389, :412), with the
+// keep_sorted policy: PSC's decks sort every 10th step because sorting pays for itself
+// slowly on a CPU; here the tiled push NEEDS the cell order (S3D: 27 ms against 156 ms
+// for the unordered store), and exchange + sort cost 14 ms as one fused pass.
+static int op_sort(Ctx* c)
+{
+  if (c->sorted) {
+    return 0; // a stable sort of a cell-ordered store is the identity
+  }
+  return sort_mprts(c);
+}
+
+static int op_push(Ctx* c)
+{
+  if (c->opt_keep_sorted && c->opt_tiled && !c->sorted && c->n_prts) {
+    PSC_TRY(sort_mprts(c));
+  }
+  c->want_counts = c->opt_keep_sorted && c->opt_fused_sort && c->sorted;
+  return push_mprts(c);
+}
+
+static int op_bnd_particles(Ctx* c)
+{
+  if (c->opt_keep_sorted && c->opt_fused_sort && c->pushed_from_sorted) {
+    return fused_bnd_sort(c);
+  }
+  return bnd_particles(c);
+}
+
 // psc.hxx:417-467 without Marder: J ghosts, then the Yee leapfrog with its ghost fills
 static int field_chain(Ctx* c, const psc_b200_step_params* prm)
 {
@@ -315,12 +344,13 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
 {
   // gapped store (gap.cuh): push + deposit + boundary exchange + sort are one pass over the
   // particles; the store stays gapped from step to step
-  bool gap_ok = prm->sort && c->opt_fused_sort && c->opt_gapped && c->opt_tiled && !c->comm &&
+  const bool do_sort = prm->sort || (c->opt_keep_sorted && c->opt_fused_sort && c->opt_tiled);
+  bool gap_ok = do_sort && c->opt_fused_sort && c->opt_gapped && c->opt_tiled && !c->comm &&
                 !prm->checks && prm->marder_loop <= 0 && c->n_prts > 0;
   if (!gap_ok) {
     PSC_TRY(store_ready(c));
   }
-  if (prm->sort && !c->sorted && !c->gapped) {
+  if (do_sort && !c->sorted && !c->gapped) {
     PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
   }
   if (gap_ok) {
@@ -342,9 +372,9 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
   if (prm->checks) {
     PSC_TRY(check_continuity_begin(c)); // :379-384
   }
-  c->want_counts = prm->sort && c->opt_fused_sort && c->sorted;
+  c->want_counts = do_sort && c->opt_fused_sort && c->sorted;
   PSC_TRY(push_mprts(c)); // :389
-  if (c->opt_overlap && prm->sort && c->opt_fused_sort && c->pushed_from_sorted && !c->comm && !prm->checks &&
+  if (c->opt_overlap && do_sort && c->opt_fused_sort && c->pushed_from_sorted && !c->comm && !prm->checks &&
       prm->marder_loop <= 0) {
     // The field chain (:417-467) touches only the field arrays, the fused exchange + sort
     // (:412, :356 of the next step) only the particles, and both depend only on the push:
@@ -363,7 +393,7 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
   }
   // :412 bndp_ -- when this step's store was cell-ordered, the exchange is fused with
   // the sort the next step would start with (same result, one pass over the particles)
-  if (prm->sort && c->opt_fused_sort && c->pushed_from_sorted) {
+  if (do_sort && c->opt_fused_sort && c->pushed_from_sorted) {
     PSC_TRY(fused_bnd_sort(c));
   } else {
     PSC_TRY(bnd_particles(c));
@@ -529,17 +559,17 @@ int psc_b200_mflds_fill(psc_b200_ctx* ctx, int id, int m, float value)
 
 int psc_b200_push_mprts(psc_b200_ctx* ctx)
 {
-  GUARD(PSC_TRY(store_ready(c)); return push_mprts(c);)
+  GUARD(PSC_TRY(store_ready(c)); return op_push(c);)
 }
 
 int psc_b200_sort(psc_b200_ctx* ctx)
 {
-  GUARD(PSC_TRY(store_ready(c)); return sort_mprts(c);)
+  GUARD(PSC_TRY(store_ready(c)); return op_sort(c);)
 }
 
 int psc_b200_bnd_particles(psc_b200_ctx* ctx)
 {
-  GUARD(PSC_TRY(store_ready(c)); return bnd_particles(c);)
+  GUARD(PSC_TRY(store_ready(c)); return op_bnd_particles(c);)
 }
 
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
@@ -678,6 +708,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "tile_z") { c->opt_tile[2] = v; }
     else if (n == "profile") { c->opt_profile = v; }
     else if (n == "fused_sort") { c->opt_fused_sort = v; }
+    else if (n == "keep_sorted") { c->opt_keep_sorted = v; }
     else if (n == "overlap") { c->opt_overlap = v; }
     else if (n == "gapped") { c->opt_gapped = v; }
     else if (n == "gap_slack") { c->opt_gap_slack = v; }

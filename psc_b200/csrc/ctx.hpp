@@ -102,6 +102,10 @@ struct Ctx
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
   int opt_profile = 0;
   int opt_fused_sort = 1;  // step(): fuse boundary exchange and sort when possible
+  int opt_keep_sorted = 1; // keep the store cell-ordered on every step, whatever the deck's sort_interval:
+                           // the push sorts an unordered store first, the exchange after a sorted push is
+                           // the fused exchange + sort.  Same physics (only the particle order differs from
+                           // a run that sorts every 10th step); the unsorted-store push is 6x slower.
   int opt_overlap = 0;     // step(): J ghosts + Yee on a second (high-priority) stream next to the particle
                            // sort; measured +0.2 % only (the field kernels fill the GPU while they run)
   int opt_gapped = 0;      // step(): gapped store (gap.cuh), no sort pass; needs fused_sort.  Off: its push
