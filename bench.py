@@ -179,10 +179,17 @@ def run_b200(args, rank, world, local_rank):
 
     n, ppc, pe = args.cells, args.ppc, args.patch
     npd = n // pe
-    gdims = (n, n, n * world)
-    grid = pb.Grid(gdims=gdims, length=tuple(float(g) for g in gdims), np=(npd, npd, npd * world),
-                   dt=0.75 / np.sqrt(3.), kinds=KINDS, nicell=ppc // 2, rank=rank, n_ranks=world,
-                   device=local_rank, max_n_prts=int(n ** 3 * ppc * 1.02))
+    yz = args.dim == "yz"
+    if yz:
+        # S2D-thermal: 1 x n x n cells per GPU, stacked along z
+        gdims, np3 = (1, n, n * world), (1, npd, npd * world)
+        n_cells_gpu, dt = n * n, 0.75 / np.sqrt(2.)
+    else:
+        gdims, np3 = (n, n, n * world), (npd, npd, npd * world)
+        n_cells_gpu, dt = n ** 3, 0.75 / np.sqrt(3.)
+    grid = pb.Grid(gdims=gdims, length=tuple(float(g) for g in gdims), np=np3,
+                   dt=dt, kinds=KINDS, nicell=ppc // 2, rank=rank, n_ranks=world,
+                   device=local_rank, max_n_prts=int(n_cells_gpu * ppc * 1.02))
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -200,7 +207,7 @@ def run_b200(args, rank, world, local_rank):
         grid.set_option("min_blocks", args.min_blocks)
     mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
     mprts.setup_thermal(ppc // 2, list(VTH), seed=1234)
-    mflds.fill(pb.HZ, 0.1)
+    mflds.fill(pb.HX if yz else pb.HZ, 0.1)
     n_prts = mprts.size()
     psc = pb.Psc(grid, mflds, mprts, sort_interval=args.sort_interval, fused=True)
     psc.initialize()
@@ -320,10 +327,11 @@ def run_b200(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "S3D-thermal: %d^3 cells x %d ppc per GPU, %d^3-cell patches, periodic, "
+        "config": {"workload": ("S2D-thermal (yz): 1 x %d^2 cells x %d ppc per GPU, %d^2-cell patches, periodic, "
+                                if yz else "S3D-thermal: %d^3 cells x %d ppc per GPU, %d^3-cell patches, periodic, ")
                                "full Psc::step (sort+push+deposit+exchange+J ghosts+Yee E/H), sort every %s"
                                % (n, ppc, pe, "step" if args.sort_interval == 1 else "%d steps" % args.sort_interval),
-                   "particles_per_gpu": n_prts, "cells_per_gpu": n ** 3, "parallelism": "slabs along z, %d rank(s)" % world,
+                   "particles_per_gpu": n_prts, "cells_per_gpu": n_cells_gpu, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
                    "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma, "warp_reduce": args.warp_reduce,
                                                 "fused_sort": args.fused_sort, "gapped": args.gapped, "overlap": args.overlap}},
@@ -340,6 +348,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dim", default="xyz", choices=["xyz", "yz"],
+                    help="xyz: the headline S3D workload; yz: S2D-thermal (use --cells 4096 --ppc 100)")
     ap.add_argument("--cells", type=int, default=256, help="cells per GPU edge")
     ap.add_argument("--patch", type=int, default=32, help="cells per patch edge")
     ap.add_argument("--ppc", type=int, default=64)
