@@ -327,9 +327,10 @@ def run_b200(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": ("S2D-thermal (yz): 1 x %d^2 cells x %d ppc per GPU, %d^2-cell patches, periodic, "
-                                if yz else "S3D-thermal: %d^3 cells x %d ppc per GPU, %d^3-cell patches, periodic, ")
-                               "full Psc::step (sort+push+deposit+exchange+J ghosts+Yee E/H), sort every %s"
+        "config": {"workload": (("S2D-thermal (yz): 1 x %d^2 cells x %d ppc per GPU, %d^2-cell patches, periodic, "
+                                 if yz else
+                                 "S3D-thermal: %d^3 cells x %d ppc per GPU, %d^3-cell patches, periodic, ")
+                                + "full Psc::step (sort+push+deposit+exchange+J ghosts+Yee E/H), sort every %s")
                                % (n, ppc, pe, "step" if args.sort_interval == 1 else "%d steps" % args.sort_interval),
                    "particles_per_gpu": n_prts, "cells_per_gpu": n_cells_gpu, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
