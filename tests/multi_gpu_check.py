@@ -96,8 +96,10 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
             # the operator types re-attach to the new decomposition (psc_balance_generation_cnt)
             mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
             psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=fused)
-    if fused:
-        L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None)  # the fused step already did the next sort
+    # the fused step already did the next sort, and so did the separate operators (keep_sorted:
+    # the exchange after a sorted push is the fused exchange + sort); Sort is then a no-op
+    L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None)
+    pb.Sort()(mprts)
     gp, go = mprts.get()
     gf = mflds.download()
     en = pb.energies(grid)
