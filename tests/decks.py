@@ -27,7 +27,6 @@ def setup_fields(og, func, comps=range(3, 9)):
     coordinates), ghosts included"""
     f = og.zeros_fields()
     dx, ib, im = og.dx, og.ib, og.im
-    corner = [og.g.corner[d] for d in range(3)]
     for p in range(og.n_patches):
         xb = og.patch_xb(p)
         for m in comps:
@@ -36,29 +35,36 @@ def setup_fields(og, func, comps=range(3, 9)):
             for d in range(3):
                 idx = np.arange(im[d]) + ib[d]
                 st = 0. if og.g.invar[d] else s[d]
-                ax.append(corner[d] + xb[d] + (idx + st) * dx[d])
+                ax.append(xb[d] + (idx + st) * dx[d])  # patch_xb is a global coordinate
             z, y, x = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
             f[p, m] = func(m, x, y, z).astype(np.float32)
     return f
 
 
-def setup_particles(og, nicell, npt, seed):
-    """npt(kind, x, y, z) -> (n, p[3], T[3]) arrays over the cell centres of a patch"""
+def setup_particles(og, nicell, npt, seed, neutralizing=None):
+    """npt(kind, x, y, z) -> (n, p[3], T[3]) arrays over the cell centres of a patch;
+    neutralizing: the (last) kind whose particle count per cell balances the charge of the
+    others (setup_particles.hxx:176-186)"""
     rng = np.random.default_rng(seed)
     ld, dx = og.ldims, og.dx
-    corner = [og.g.corner[d] for d in range(3)]
     chunks, counts = [], []
     for p in range(og.n_patches):
         xb = og.patch_xb(p)
         ax = [(np.arange(ld[d]) + .5) * dx[d] for d in range(3)]
         zc, yc, xc = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
         loc = np.stack([xc.ravel(), yc.ravel(), zc.ravel()], axis=1)
-        glob = loc + np.array([corner[d] + xb[d] for d in range(3)])
+        glob = loc + np.array([xb[d] for d in range(3)])  # patch_xb is a global coordinate
         per_kind = []
+        n_q_in_cell = np.zeros(len(loc), dtype=np.int64)
         for kind, (q, m) in enumerate(og.kinds):
             n, pd, T = npt(kind, glob[:, 0], glob[:, 1], glob[:, 2])
             n = np.broadcast_to(np.asarray(n, dtype=np.float64), (len(loc),))
-            n_in_cell = np.where(n > 0, np.maximum(1, (n * nicell + .5).astype(np.int64)), 0)
+            if kind == neutralizing:
+                assert kind == len(og.kinds) - 1
+                n_in_cell = (-n_q_in_cell / q).astype(np.int64)
+            else:
+                n_in_cell = np.where(n > 0, np.maximum(1, (n * nicell + .5).astype(np.int64)), 0)
+                n_q_in_cell += (q * n_in_cell).astype(np.int64)
             w = np.where(n_in_cell > 0, n * nicell / np.maximum(n_in_cell, 1), 0.)
             rep = np.repeat(np.arange(len(loc)), n_in_cell)
             a = np.zeros(len(rep), dtype=PRT_DTYPE)
@@ -212,4 +218,34 @@ def kh_xyz(nicell=8, seed=3):
     return dict(og=og, flds=flds, prts=prts, off=off, sort_interval=10, marder_interval=0)
 
 
-DECKS = {"bubble_yz": bubble_yz, "harris_yz": harris_yz, "kelvin_helmholtz_xyz": kh_xyz}
+def flatfoil_yz(nicell=25, seed=4):
+    """psc_flatfoil_yz (src/psc_flatfoil_yz.cxx:258-279 parameters, :289-343 grid: periodic
+    yz, three kinds he_e / e / i with the ions neutralizing, :352-386 background + foil
+    target, :110-161 InjectFoil, :461,501 cadence), 1 x 32 x 96 cells instead of the deck's
+    1 x 80 x 240 (CASE_2D_SMALL); heating, injection and collisions off.  No
+    initial fields (BB = 0): the field energy is noise, the particle energy is the signal."""
+    mass_ratio, target_n, he_ratio = 100., 2.5, .01
+    T_target, bg_n, bg_T = .001, .002, .001
+    d_i = np.sqrt(mass_ratio)
+    zw = 1. * d_i
+    Ly, Lz = 32., 96.
+    og = _grid(gdims=(1, 32, 96), length=(1., Ly, Lz), corner=(-.5, -.5 * Ly, -.5 * Lz), np_=(1, 2, 6),
+               kinds=((-1., 1.), (-1., 1.), (1., mass_ratio)), nicell=nicell)
+
+    def npt(kind, x, y, z):
+        inside = np.abs(z) <= zw
+        if kind == 2:      # ions
+            n = np.where(inside, target_n, bg_n)
+        elif kind == 0:    # high-energy electrons: only in the foil
+            n = np.where(inside, he_ratio * target_n, 0.)
+        else:
+            n = np.where(inside, (1. - he_ratio) * target_n, bg_n)
+        T = np.where(inside, T_target, bg_T)
+        return n, (0., 0., 0.), (T, T, T)
+
+    flds = og.zeros_fields()
+    prts, off = setup_particles(og, nicell, npt, seed, neutralizing=2)
+    return dict(og=og, flds=flds, prts=prts, off=off, sort_interval=10, marder_interval=100)
+
+
+DECKS = {"flatfoil_yz": flatfoil_yz, "bubble_yz": bubble_yz, "harris_yz": harris_yz, "kelvin_helmholtz_xyz": kh_xyz}

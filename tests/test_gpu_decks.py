@@ -11,7 +11,9 @@ inside each patch (only the summation order of J changes), differs from itself b
 1.6 % in that quantity after 1000 steps (0.1 % in the particle energies; measured with this
 file's _oracle_run), and the device's atomics change the summation order from run to run.
 That one quantity is therefore held to 1 % of the TOTAL energy plus a 10 % gross-error
-bound on itself; every other quantity to the 1 % of the contract."""
+bound on itself; every other quantity to the 1 % of the contract.  The flatfoil starts
+without fields (BB = 0): its field energy is pure noise (0.1 % of the total) and gets the
+same treatment with a 50 % gross bound."""
 import functools
 
 import numpy as np
@@ -23,8 +25,8 @@ from decks import DECKS
 
 pytestmark = pytest.mark.gpu
 
-N_STEPS = {"bubble_yz": 1000, "harris_yz": 1000, "kelvin_helmholtz_xyz": 1000}
-FIELD_RTOL = {"bubble_yz": 1e-1, "harris_yz": 1e-2, "kelvin_helmholtz_xyz": 1e-2}
+N_STEPS = {"flatfoil_yz": 1000, "bubble_yz": 1000, "harris_yz": 1000, "kelvin_helmholtz_xyz": 1000}
+FIELD_RTOL = {"flatfoil_yz": 5e-1, "bubble_yz": 1e-1, "harris_yz": 1e-2, "kelvin_helmholtz_xyz": 1e-2}
 EVERY = 100
 
 
@@ -84,7 +86,7 @@ def test_deck_energies_1000_steps(name, fma):
     np.testing.assert_allclose(got[0], ref[0], rtol=1e-6, atol=1e-12)
     # field energy (sum and every component against the sum), particle energy per species
     fld_g, fld_r = got[:, :6].sum(axis=1), ref[:, :6].sum(axis=1)
-    assert np.abs(fld_g / fld_r - 1).max() < FIELD_RTOL[name], (fld_g, fld_r)
+    assert np.all(np.abs(fld_g - fld_r) <= FIELD_RTOL[name] * fld_r), (fld_g, fld_r)
     assert np.abs(fld_g - fld_r).max() < 1e-2 * ref.sum(axis=1).min()
     assert np.abs(got[:, :6] - ref[:, :6]).max() < FIELD_RTOL[name] * fld_r.max()
     # particle energy: the sum to the contract's 1 % (observed < 0.1 %); each species -- the

@@ -24,6 +24,6 @@ for name in t.DECKS:
         grid.close()
         fg, fr = got[:, :6].sum(1), ref[:, :6].sum(1)
         print("%-22s field rel %.4f  field/total %.5f  comp/fieldmax %.4f  prt rel %.5f  total rel %.5f" % (
-            name, np.abs(fg / fr - 1).max(), (np.abs(fg - fr) / ref.sum(1).min()).max(),
+            name, np.abs(fg[1:] / fr[1:] - 1).max(), (np.abs(fg - fr) / ref.sum(1).min()).max(),
             np.abs(got[:, :6] - ref[:, :6]).max() / fr.max(), np.abs(got[:, 6:] / ref[:, 6:] - 1).max(),
             np.abs(got.sum(1) / ref.sum(1) - 1).max()))
