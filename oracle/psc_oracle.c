@@ -1376,12 +1376,43 @@ double po_gauss(const po_grid* g, const float* rho, const float* flds)
   return err;
 }
 
+/* psc::marder::correct (libpsc/psc_push_fields/marder_impl.hxx:26-61):
+ * E_d += (res[+1_d] - res) * fac_d over the patch interior,
+ * fac = .5f * real_t(dt) * diffusion * Real3(dx_inv); res has 1 component */
+void po_marder_apply(const po_grid* g, float* flds, const float* res, double diffusion)
+{
+  long plen1 = po_fld_patch_len(g);
+  long plen = plen1 * PO_NR_FIELDS;
+  float diff_f = (float)diffusion;
+  float s = .5f * (float)g->dt * diff_f;
+  for (int p = 0; p < g->n_patches; p++) {
+    float* F = flds + p * plen;
+    const float* R = res + p * plen1;
+    for (int d = 0; d < 3; d++) {
+      if (g->invar[d]) {
+        continue;
+      }
+      float fac = s * (float)g->dx_inv[d];
+      for (int k = 0; k < g->ldims[2]; k++) {
+        for (int j = 0; j < g->ldims[1]; j++) {
+          for (int i = 0; i < g->ldims[0]; i++) {
+            int ip[3] = {i, j, k};
+            ip[d] += 1;
+            FLD(F, g, PO_EX + d, i, j, k) =
+              FLD(F, g, PO_EX + d, i, j, k) +
+              (SC(R, g, ip[0], ip[1], ip[2]) - SC(R, g, i, j, k)) * fac;
+          }
+        }
+      }
+    }
+  }
+}
+
 /* marder_impl.hxx:197-264 + 26-61 */
 void po_marder_correct(const po_grid* g, float* flds, const po_prt* prts,
                        const unsigned* off, double diffusion_, int loop)
 {
   long plen1 = po_fld_patch_len(g);
-  long plen = plen1 * PO_NR_FIELDS;
   long ntot = plen1 * g->n_patches;
 
   double inv_sum = 0.;
@@ -1439,30 +1470,7 @@ void po_marder_correct(const po_grid* g, float* flds, const po_prt* prts,
     }
     po_fill_ghosts(g, res, 1, 0, 1);
 
-    /* psc::marder::correct, :26-61 */
-    float diff_f = (float)diffusion;
-    float s = .5f * (float)g->dt * diff_f;
-    for (int p = 0; p < g->n_patches; p++) {
-      float* F = flds + p * plen;
-      const float* R = res + p * plen1;
-      for (int d = 0; d < 3; d++) {
-        if (g->invar[d]) {
-          continue;
-        }
-        float fac = s * (float)g->dx_inv[d];
-        for (int k = 0; k < g->ldims[2]; k++) {
-          for (int j = 0; j < g->ldims[1]; j++) {
-            for (int i = 0; i < g->ldims[0]; i++) {
-              int ip[3] = {i, j, k};
-              ip[d] += 1;
-              FLD(F, g, PO_EX + d, i, j, k) =
-                FLD(F, g, PO_EX + d, i, j, k) +
-                (SC(R, g, ip[0], ip[1], ip[2]) - SC(R, g, i, j, k)) * fac;
-            }
-          }
-        }
-      }
-    }
+    po_marder_apply(g, flds, res, diffusion);
   }
   po_fill_ghosts(g, flds, PO_NR_FIELDS, PO_EX, PO_EX + 3);
   free(rho);

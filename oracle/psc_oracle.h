@@ -180,6 +180,8 @@ double po_continuity(const po_grid* g, const float* rho_m, const float* rho_p,
 /* checks_impl.hxx:137-215 : max |div E - rho| */
 double po_gauss(const po_grid* g, const float* rho, const float* flds);
 /* marder_impl.hxx:26-61,197-264 */
+/* psc::marder::correct alone (marder_impl.hxx:26-61): E += grad(res) * .5 dt diffusion */
+void po_marder_apply(const po_grid* g, float* flds, const float* res, double diffusion);
 void po_marder_correct(const po_grid* g, float* flds, const po_prt* prts,
                        const unsigned* off, double diffusion, int loop);
 

@@ -190,3 +190,148 @@ def moment_case_expected(case, dim, grid):
 def moment_interior_comp0(grid, arr):
     ld, ib = grid.ldims, grid.ib
     return arr[0, 0, -ib[2]:-ib[2] + ld[2], -ib[1]:-ib[1] + ld[1], -ib[0]:-ib[0] + ld[0]]
+
+
+# ----------------------------------------------------------------------------
+# field operators: src/libpsc/tests/test_push_fields.cxx (fixture testing.hxx:137-170:
+# 16^3 or 1 x 16 x 16 cells, L = 160, dt = 1, periodic) and test_bnd.cxx (gdims (2|1) x 8 x 4,
+# dx = 10, patches {1, 2, 1}, B = 2 ghosts).  Each case returns (got, expected, tolerance)
+# for an `ops` object with push_E / push_H / div_nc / marder_apply / fill_ghosts /
+# add_ghosts working on numpy arrays in the oracle's layout.
+
+def _interior(grid, a):
+    ld, ib = grid.ldims, grid.ib
+    return a[..., -ib[2]:-ib[2] + ld[2], -ib[1]:-ib[1] + ld[1], -ib[0]:-ib[0] + ld[0]]
+
+
+def _coords(grid, p, stagger):
+    """global coordinates (z, y, x meshgrid, ghosts included) of points with the given
+    per-direction stagger (0 = node, .5 = cell centre)"""
+    xb, dx, ib, im = grid.patch_xb(p), grid.dx, grid.ib, grid.im
+    ax = [xb[d] + (np.arange(im[d]) + ib[d] + stagger[d]) * dx[d] for d in range(3)]
+    return np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+
+
+def field_case_pushf1(dim, ops):
+    """test_push_fields.cxx:26-64: EY = sin(kz z), push_H(1) -> HX = kz cos(kz z_cc), eps 1e-2"""
+    import decks
+    g = push_fixture_grid(dim)
+    kz = 2. * np.pi / g.length[2]
+    f = decks.setup_fields(g, lambda m, x, y, z: np.sin(kz * z) if m == 4 else np.zeros(z.shape))
+    ops.push_H(g, f, 1.)
+    z, _, _ = _coords(g, 0, (0, 0, .5))
+    return _interior(g, f[0, 6]), _interior(g, kz * np.cos(kz * z)), 1e-2
+
+
+def field_case_pushf2(dim, ops):
+    """:66-110: HX = cos(ky y), push_E(1) -> EZ = ky sin(ky y_cc), eps 1e-2"""
+    import decks
+    g = push_fixture_grid(dim)
+    ky = 2. * np.pi / g.length[1]
+    f = decks.setup_fields(g, lambda m, x, y, z: np.cos(ky * y) if m == 6 else np.zeros(y.shape))
+    ops.push_E(g, f, 1.)
+    _, y, _ = _coords(g, 0, (0, .5, 0))
+    return _interior(g, f[0, 5]), _interior(g, ky * np.sin(ky * y)), 1e-2
+
+
+def field_case_marder_correct(dim, ops):
+    """:123-172: EZ = sin(kz z), phi = sin(kz z_node), correct(diffusion 5) ->
+    EZ = sin(kz z) + .5 dt diffusion kz cos(kz z) at the EZ points, norm_linf < 1e-3"""
+    import decks
+    g = push_fixture_grid(dim)
+    kz = 2. * np.pi / g.length[2]
+    diffusion = 5.
+    f = decks.setup_fields(g, lambda m, x, y, z: np.sin(kz * z) if m == 5 else np.zeros(z.shape))
+    ref = decks.setup_fields(
+        g, lambda m, x, y, z: (np.sin(kz * z) + .5 * g.dt * diffusion * kz * np.cos(kz * z)) if m == 5
+        else np.zeros(z.shape))
+    z, _, _ = _coords(g, 0, (0, 0, 0))
+    # init_phi (:112-121): z = (k - bnd) * dz, i.e. the patch-local node coordinate
+    phi = np.sin(kz * (z - g.patch_xb(0)[2])).astype(np.float32)[None, None]
+    assert np.abs(_interior(g, f) - _interior(g, ref)).max() > 1e-3
+    ops.marder_apply(g, f, np.ascontiguousarray(phi), diffusion)
+    return _interior(g, f[0, 3:6]), _interior(g, ref[0, 3:6]), 1e-3
+
+
+def field_case_div(dim, ops, m0):
+    """:191-260 ItemDivE (m0 = EX) / ItemDivJ (m0 = JXI): Y-comp = cos(ky y), Z-comp = sin(kz z) ->
+    div = -ky sin(ky y) + kz cos(kz z) at the nodes, norm_linf < 1e-2"""
+    import decks
+    g = push_fixture_grid(dim)
+    ky, kz = 2. * np.pi / g.length[1], 2. * np.pi / g.length[2]
+    f = decks.setup_fields(
+        g, lambda m, x, y, z: np.cos(ky * y) if m == m0 + 1 else (np.sin(kz * z) if m == m0 + 2 else np.zeros(z.shape)),
+        comps=range(m0, m0 + 3))
+    got = ops.div_nc(g, f, m0)
+    z, y, _ = _coords(g, 0, (0, 0, 0))
+    return _interior(g, got[0, 0]), _interior(g, -ky * np.sin(ky * y) + kz * np.cos(kz * z)), 1e-2
+
+
+def bnd_grid(dim):
+    """test_bnd.cxx:15-41"""
+    yz = dim == "yz"
+    return ol.Grid(gdims=(1 if yz else 2, 8, 4), length=(10. if yz else 20., 80., 40.), np_=(1, 2, 1), dt=.1,
+                   kinds=((1., 1.),), nicell=1)
+
+
+def bnd_case_fill_ghosts(dim, ops):
+    """test_bnd.cxx:104-174: interior = 100 ii + 10 jj + kk (global indices), fill_ghosts ->
+    every point holds the value of its periodic image; exact"""
+    g = bnd_grid(dim)
+    gd, ld, ib, im = g.gdims, g.ldims, g.ib, g.im
+    f = g.zeros_fields(1)
+    exp = g.zeros_fields(1)
+    for p in range(g.n_patches):
+        off = g.patch_off(p)
+        idx = [np.arange(im[d]) + ib[d] + off[d] for d in range(3)]
+        kk, jj, ii = np.meshgrid(idx[2], idx[1], idx[0], indexing="ij")
+        full = 100 * (ii % gd[0]) + 10 * (jj % gd[1]) + (kk % gd[2])
+        exp[p, 0] = full
+        inner = np.zeros(full.shape, dtype=bool)
+        inner[-ib[2]:-ib[2] + ld[2], -ib[1]:-ib[1] + ld[1], -ib[0]:-ib[0] + ld[0]] = True
+        f[p, 0] = np.where(inner, full, 0)
+    ops.fill_ghosts(g, f)
+    ops.fill_ghosts(g, f)  # "let's do it again" (:173)
+    return f, exp, 0.
+
+
+def bnd_case_add_ghosts(dim, ops):
+    """test_bnd.cxx:232-303: every point (ghosts included) = 1, add_ghosts -> interior points
+    hold 1 + the number of ghost images that fold onto them, ghosts keep 1; exact"""
+    g = bnd_grid(dim)
+    ld, ib, im = g.ldims, g.ib, g.im
+    f = g.zeros_fields(1)
+    f[:] = 1
+    exp = np.ones_like(f)
+    B = 2
+    for p in range(g.n_patches):
+        for k in range(ld[2]):
+            for j in range(ld[1]):
+                for i in range(ld[0]):
+                    nx = 0 if dim == "yz" else int(i < B) + int(i >= ld[0] - B)
+                    ny = int(j < B) + int(j >= ld[1] - B)
+                    nz = int(k < B) + int(k >= ld[2] - B)
+                    exp[p, 0, k - ib[2], j - ib[1], i - ib[0]] = (nx + 1) * (ny + 1) * (nz + 1)
+    ops.add_ghosts(g, f)
+    return f, exp, 0.
+
+
+FIELD_CASES = {
+    "Pushf1": field_case_pushf1,
+    "Pushf2": field_case_pushf2,
+    "MarderCorrect": field_case_marder_correct,
+    "ItemDivE": lambda dim, ops: field_case_div(dim, ops, 3),
+    "ItemDivJ": lambda dim, ops: field_case_div(dim, ops, 0),
+    "BndFillGhosts": bnd_case_fill_ghosts,
+    "BndAddGhosts": bnd_case_add_ghosts,
+}
+
+
+class OracleFieldOps:
+    """the field operators of the CPU oracle on numpy arrays"""
+    push_E = staticmethod(lambda g, f, dt_fac: ol.push_E(g, f, dt_fac))
+    push_H = staticmethod(lambda g, f, dt_fac: ol.push_H(g, f, dt_fac))
+    div_nc = staticmethod(lambda g, f, m0: ol.div_nc(g, f, m0))
+    marder_apply = staticmethod(lambda g, f, res, diffusion: ol.lib().po_marder_apply(g.byref(), ol.ptr(f), ol.ptr(res), diffusion))
+    fill_ghosts = staticmethod(lambda g, f: ol.fill_ghosts(g, f, 0, f.shape[1]))
+    add_ghosts = staticmethod(lambda g, f: ol.add_ghosts(g, f, 0, f.shape[1]))

@@ -100,6 +100,7 @@ def lib():
         L.po_gauss.argtypes = [G, P, P]
         L.po_gauss.restype = C.c_double
         L.po_marder_correct.argtypes = [G, P, P, P, C.c_double, C.c_int]
+        L.po_marder_apply.argtypes = [G, P, P, C.c_double]
         L.po_energies.argtypes = [G, P, P, P, P]
         L.po_best_mapping.argtypes = [C.c_int, P, C.c_int, P, P]
         L.po_get_loads.argtypes = [G, P, C.c_double, P]

@@ -150,3 +150,15 @@ def test_oracle_moment_known_answers(case, dim):
     got = gc.moment_interior_comp0(og, ol.moment_1st(og, prts, off, case["which"]))
     exp = gc.moment_case_expected(case, dim, og)
     assert np.abs(got - exp).max() < 1e-6
+
+
+@pytest.mark.parametrize("dim", ["xyz", "yz"])
+@pytest.mark.parametrize("name", list(gc.FIELD_CASES))
+def test_oracle_field_known_answers(name, dim):
+    """the oracle's Yee / Marder-correct / div / ghost operators on the reference's own
+    known-answer tests (src/libpsc/tests/test_push_fields.cxx:26-260, test_bnd.cxx:104-303)"""
+    got, exp, tol = gc.FIELD_CASES[name](dim, gc.OracleFieldOps)
+    if tol == 0.:
+        assert np.array_equal(got, exp)
+    else:
+        assert np.abs(got - exp).max() < tol
