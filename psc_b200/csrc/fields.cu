@@ -176,21 +176,31 @@ __global__ void k_add_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long 
     lo[d] = c[d] < G.ibn[d];
     hi[d] = c[d] >= G.ldims[d] - G.ibn[d] && G.ibn[d] > 0;
   }
+  // which of the 26 neighbour images fold onto this point (directions are compile-time
+  // here: a few ANDs of the lo / hi flags each) ...
+  unsigned members = 0;
+#pragma unroll
+  for (int di = 0; di < 27; di++) {
+    if (di == 13) {
+      continue;
+    }
+    const int d0 = di % 3 - 1, d1 = (di / 3) % 3 - 1, d2 = di / 9 - 1;
+    const bool mem = (d0 == 0 || (d0 < 0 ? lo[0] : hi[0])) && (d1 == 0 || (d1 < 0 ? lo[1] : hi[1])) &&
+                     (d2 == 0 || (d2 < 0 ? lo[2] : hi[2]));
+    members |= (mem ? 1u : 0u) << di;
+  }
   float* dst = F + p * slot_len + fld_off(G, m, i, j, k);
   float acc = *dst;
-  for (int o = 0; o < 26; o++) {
-    int di = add_order[p * 26 + o];
+  // ... summed in the reference's order (mrc_ddc_multi.c:519-538); most points have one
+  for (int o = 0; o < 26 && members; o++) {
+    const int di = add_order[p * 26 + o];
     if (di < 0) {
       break;
     }
-    int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
-    bool member = true;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      member = member && (dir[d] == 0 || (dir[d] < 0 ? lo[d] : hi[d]));
-    }
-    if (member) {
-      int slot = nei_slot[p * 27 + di];
+    if ((members >> di) & 1u) {
+      members &= ~(1u << di);
+      const int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+      const int slot = nei_slot[p * 27 + di];
       acc += F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
                                           k - dir[2] * G.ldims[2])];
     }
