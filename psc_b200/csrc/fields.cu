@@ -129,47 +129,48 @@ __device__ __forceinline__ void band_decode(const BandGeom& B, int idx, int& x, 
 __global__ void k_fill_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long slot_len, int mb,
                               int me, const int* __restrict__ nei_slot)
 {
+  // grid.x walks the ghost points of one (patch, component), grid.y strides over the pairs:
+  // the point is decoded once and everything stays in 32-bit arithmetic
   const int nb = B.n2 + B.n1 + B.n0;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int n_m = me - mb;
-  if (idx >= (size_t)G.n_patches * n_m * nb) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nb) {
     return;
   }
+  const int n_m = me - mb;
   int x, y, z;
-  band_decode(B, (int)(idx % nb), x, y, z);
-  idx /= nb;
-  int m = mb + (int)(idx % n_m);
-  int p = (int)(idx / n_m);
-  int i = x - G.ibn[0], j = y - G.ibn[1], k = z - G.ibn[2];
+  band_decode(B, r, x, y, z);
+  const int i = x - G.ibn[0], j = y - G.ibn[1], k = z - G.ibn[2];
   int dir[3];
   dir[0] = i < 0 ? -1 : (i >= G.ldims[0] ? 1 : 0);
   dir[1] = j < 0 ? -1 : (j >= G.ldims[1] ? 1 : 0);
   dir[2] = k < 0 ? -1 : (k >= G.ldims[2] ? 1 : 0);
-  int slot = nei_slot[p * 27 + pm::dir2idx(dir)];
-  if (slot < 0) {
-    return;
+  const int di = pm::dir2idx(dir);
+  const long dst_off = fld_off(G, 0, i, j, k);
+  const long src_off = fld_off(G, 0, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1], k - dir[2] * G.ldims[2]);
+  for (int pc = blockIdx.y; pc < G.n_patches * n_m; pc += gridDim.y) {
+    const int p = pc / n_m, m = mb + (pc - p * n_m);
+    const int slot = nei_slot[p * 27 + di];
+    if (slot >= 0) {
+      F[p * slot_len + m * G.fld_len + dst_off] = F[slot * slot_len + m * G.fld_len + src_off];
+    }
   }
-  F[p * slot_len + fld_off(G, m, i, j, k)] =
-    F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
-                                k - dir[2] * G.ldims[2])];
 }
 
 __global__ void k_add_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long slot_len, int mb,
                              int me, const int* __restrict__ nei_slot,
                              const int8_t* __restrict__ add_order)
 {
+  // grid.x walks the boundary-band points of one (patch, component), grid.y strides over
+  // the pairs (32-bit arithmetic, the point and its member set are decoded once)
   const int nb = B.n2 + B.n1 + B.n0;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int n_m = me - mb;
-  if (idx >= (size_t)G.n_patches * n_m * nb) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nb) {
     return;
   }
+  const int n_m = me - mb;
   int i, j, k;
-  band_decode(B, (int)(idx % nb), i, j, k);
-  idx /= nb;
-  int m = mb + (int)(idx % n_m);
-  int p = (int)(idx / n_m);
-  int c[3] = {i, j, k};
+  band_decode(B, r, i, j, k);
+  const int c[3] = {i, j, k};
   bool lo[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; d++) {
@@ -178,7 +179,7 @@ __global__ void k_add_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long 
   }
   // which of the 26 neighbour images fold onto this point (directions are compile-time
   // here: a few ANDs of the lo / hi flags each) ...
-  unsigned members = 0;
+  unsigned members0 = 0;
 #pragma unroll
   for (int di = 0; di < 27; di++) {
     if (di == 13) {
@@ -187,25 +188,30 @@ __global__ void k_add_ghosts(GridDev G, BandGeom B, float* __restrict__ F, long 
     const int d0 = di % 3 - 1, d1 = (di / 3) % 3 - 1, d2 = di / 9 - 1;
     const bool mem = (d0 == 0 || (d0 < 0 ? lo[0] : hi[0])) && (d1 == 0 || (d1 < 0 ? lo[1] : hi[1])) &&
                      (d2 == 0 || (d2 < 0 ? lo[2] : hi[2]));
-    members |= (mem ? 1u : 0u) << di;
+    members0 |= (mem ? 1u : 0u) << di;
   }
-  float* dst = F + p * slot_len + fld_off(G, m, i, j, k);
-  float acc = *dst;
-  // ... summed in the reference's order (mrc_ddc_multi.c:519-538); most points have one
-  for (int o = 0; o < 26 && members; o++) {
-    const int di = add_order[p * 26 + o];
-    if (di < 0) {
-      break;
+  const long dst_off = fld_off(G, 0, i, j, k);
+  for (int pc = blockIdx.y; pc < G.n_patches * n_m; pc += gridDim.y) {
+    const int p = pc / n_m, m = mb + (pc - p * n_m);
+    float* dst = F + p * slot_len + m * G.fld_len + dst_off;
+    float acc = *dst;
+    unsigned members = members0;
+    // ... summed in the reference's order (mrc_ddc_multi.c:519-538); most points have one
+    for (int o = 0; o < 26 && members; o++) {
+      const int di = add_order[p * 26 + o];
+      if (di < 0) {
+        break;
+      }
+      if ((members >> di) & 1u) {
+        members &= ~(1u << di);
+        const int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
+        const int slot = nei_slot[p * 27 + di];
+        acc += F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
+                                            k - dir[2] * G.ldims[2])];
+      }
     }
-    if ((members >> di) & 1u) {
-      members &= ~(1u << di);
-      const int dir[3] = {di % 3 - 1, (di / 3) % 3 - 1, di / 9 - 1};
-      const int slot = nei_slot[p * 27 + di];
-      acc += F[slot * slot_len + fld_off(G, m, i - dir[0] * G.ldims[0], j - dir[1] * G.ldims[1],
-                                          k - dir[2] * G.ldims[2])];
-    }
+    *dst = acc;
   }
-  *dst = acc;
 }
 
 // ---------------------------------------------------------------- Yee
@@ -738,8 +744,11 @@ int bnd_fill_ghosts(Ctx* c, int id, int mb, int me)
     return 0;
   }
   KernelScope ks(c, "fill_ghosts");
-  k_fill_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id),
-                                                      mb, me, c->d_nei_slot);
+  {
+    const int nb = B.n2 + B.n1 + B.n0;
+    dim3 grid(div_up(nb, 128), (unsigned)std::min(c->gd.n_patches * (me - mb), 32768));
+    k_fill_ghosts<<<grid, 128, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id), mb, me, c->d_nei_slot);
+  }
   c->n_launches++;
   return check_launch(c, "fill_ghosts");
 }
@@ -756,8 +765,12 @@ int bnd_add_ghosts(Ctx* c, int id, int mb, int me)
     return 0;
   }
   KernelScope ks(c, "add_ghosts");
-  k_add_ghosts<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id), mb,
-                                                     me, c->d_nei_slot, c->d_add_order);
+  {
+    const int nb = B.n2 + B.n1 + B.n0;
+    dim3 grid(div_up(nb, 128), (unsigned)std::min(c->gd.n_patches * (me - mb), 32768));
+    k_add_ghosts<<<grid, 128, 0, c->stream>>>(c->gd, B, c->fld(id), c->fld_slot_len(id), mb, me, c->d_nei_slot,
+                                              c->d_add_order);
+  }
   c->n_launches++;
   return check_launch(c, "add_ghosts");
 }
