@@ -11,6 +11,11 @@ namespace psc_b200
 
 constexpr int CLS_CENTER = 13, CLS_DROP = 27, CLS_BAD = 28, CLS_REMOTE = 29, CLS_NONE = 31;
 constexpr int FS_PLANES = 27; // cnt[class][cell], class = ((dz+1)*3 + dy+1)*3 + dx+1
+// Every entry of the planes is bounded by the population of one cell (a count of its
+// particles, later their offset inside the target cell): 16 bits.  A cell with more than
+// 65535 particles raises the "precondition broken" flag and the step takes the general path.
+using cnt_t = uint16_t;
+constexpr uint32_t CNT_MAX = 0xffffu;
 
 struct FsTables
 {

@@ -45,7 +45,7 @@ constexpr int FS_CELLS = 32; // source cells per CTA
 // that k_fs_offsets (one thread per target cell) reads and rewrites them coalesced.
 __global__ void __launch_bounds__(FS_WARPS * 32)
   k_fs_count(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
-             const float4* __restrict__ xi4, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags)
+             const float4* __restrict__ xi4, cnt_t* __restrict__ cnt, uint32_t* __restrict__ flags)
 {
   __shared__ uint32_t cnt_s[FS_CELLS][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
   __syncthreads();
   if (g0 + lane < nct) {
     for (int plane = warp; plane < 27; plane += FS_WARPS) {
-      cnt[(size_t)plane * nct + g0 + lane] = cnt_s[lane][plane];
+      cnt[(size_t)plane * nct + g0 + lane] = (cnt_t)cnt_s[lane][plane];
+      if (cnt_s[lane][plane] > CNT_MAX) {
+        atomicExch(&flags[0], 1u);
+      }
     }
   }
 }
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32)
 // first one is rewritten, so the (up to 27) loads are in flight together instead of
 // forming a load -> store -> load chain (the array is updated in place).
 template <bool CENTER_INFO = false>
-__device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_t* __restrict__ cnt,
+__device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, cnt_t* __restrict__ cnt,
                                          int ps, int c0, int c1, int c2, int t0, int t1, int t2,
                                          uint32_t& total, uint32_t* n_lower = nullptr,
                                          uint32_t* n_center = nullptr)
@@ -139,7 +142,7 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_
     if ((ok >> k) & 1) {
       int z = c2 - e2 + t2 * ld2, y = c1 - e1 + t1 * ld1, x = c0 - e0 + t0 * ld0;
       cnt[(size_t)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct + pbase +
-          (size_t)((z * ld1 + y) * ld0 + x)] = total;
+          (size_t)((z * ld1 + y) * ld0 + x)] = (cnt_t)total; // (a target cell beyond CNT_MAX is flagged by the caller)
       if (CENTER_INFO && k == 13) {
         *n_lower = total;
         *n_center = n[k];
@@ -160,7 +163,8 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, uint32_
 // only (one thread per face cell; the face slabs are enumerated z, y, x and a cell that
 // lies in several is taken by the first).
 __global__ void __launch_bounds__(256, 4)
-  k_fs_offsets_same(GridDev G, uint32_t nct, uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
+  k_fs_offsets_same(GridDev G, uint32_t nct, cnt_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt,
+                    uint32_t* __restrict__ flags)
 {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nct) {
@@ -173,10 +177,13 @@ __global__ void __launch_bounds__(256, 4)
   uint32_t total = 0;
   fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
   new_cnt[g] = total;
+  if (total > CNT_MAX) {
+    atomicExch(&flags[0], 1u); // offsets inside this cell do not fit the 16-bit planes
+  }
 }
 
 __device__ __forceinline__ void fs_face_routes(const GridDev& G, const int* __restrict__ nei_patch, uint32_t nct,
-                                               uint32_t* __restrict__ cnt, int q, int c0, int c1, int c2,
+                                               cnt_t* __restrict__ cnt, int q, int c0, int c1, int c2,
                                                uint32_t& total)
 {
   const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
@@ -215,7 +222,7 @@ struct FaceGeom
 
 __global__ void __launch_bounds__(128)
   k_fs_offsets_face(GridDev G, FaceGeom FG, const int* __restrict__ nei_patch, uint32_t nct,
-                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt)
+                    cnt_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt, uint32_t* __restrict__ flags)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = t / FG.per_patch;
@@ -248,6 +255,9 @@ __global__ void __launch_bounds__(128)
   uint32_t total = new_cnt[g];
   fs_face_routes(G, nei_patch, nct, cnt, q, c0, c1, c2, total);
   new_cnt[g] = total;
+  if (total > CNT_MAX) {
+    atomicExch(&flags[0], 1u);
+  }
 }
 
 // Scatter: one warp walks SC_CPW consecutive source cells.  Like the push kernel it
@@ -272,7 +282,7 @@ __device__ __forceinline__ void fs_cp_async16(uint32_t dst, const void* src)
 #endif
 __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
-               const uint32_t* __restrict__ new_cell_off, const uint32_t* __restrict__ pre,
+               const uint32_t* __restrict__ new_cell_off, const cnt_t* __restrict__ pre,
                const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
                float4* __restrict__ xo, float4* __restrict__ po)
 {
@@ -562,10 +572,10 @@ int fused_bnd_sort(Ctx* c)
   const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
   const int np = G.n_patches;
   const bool multi = c->comm != nullptr;
-  PSC_TRY(c->scr[9].reserve((size_t)nct * FS_PLANES * sizeof(uint32_t)));
+  PSC_TRY(c->scr[9].reserve((size_t)nct * FS_PLANES * sizeof(cnt_t)));
   PSC_TRY(c->scr[10].reserve(((size_t)nct + 1) * sizeof(uint32_t)));
   PSC_TRY(c->scr[11].reserve((np + 1 + 4) * sizeof(uint32_t)));
-  uint32_t* cnt = c->scr[9].as<uint32_t>();
+  cnt_t* cnt = c->scr[9].as<cnt_t>();
   uint32_t* new_cnt = c->scr[10].as<uint32_t>();
   uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, dropped, remote, counter, new patch offsets...]
   uint32_t* d_new_off = flags + 4;
@@ -580,7 +590,7 @@ int fused_bnd_sort(Ctx* c)
   c->counts_valid = false;
   {
     KernelScope ks(c, "fsort_offsets");
-    k_fs_offsets_same<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt);
+    k_fs_offsets_same<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags);
     // faces towards a direction in which some patch has a neighbour (none along an
     // invariant direction: Grid_ / MrcDomain)
     FaceGeom FG{};
@@ -599,7 +609,7 @@ int fused_bnd_sort(Ctx* c)
     }
     if (FG.per_patch) {
       k_fs_offsets_face<<<div_up((size_t)FG.per_patch * np, 128), 128, 0, c->stream>>>(G, FG, c->d_nei_patch, nct,
-                                                                                        cnt, new_cnt);
+                                                                                        cnt, new_cnt, flags);
     }
     c->n_launches += 2;
   }
@@ -730,7 +740,7 @@ namespace
 // cell's run, the run is anchored so that the stayers (already written by the push) sit at
 // V + RL, and a slab that cannot take its arrivals is flagged
 __global__ void k_gap_offsets(GridDev G, const int* __restrict__ nei_patch, uint32_t nct,
-                              uint32_t* __restrict__ cnt, const uint32_t* __restrict__ v, uint32_t rl,
+                              cnt_t* __restrict__ cnt, const uint32_t* __restrict__ v, uint32_t rl,
                               uint32_t* __restrict__ new_start, uint32_t* __restrict__ new_n,
                               uint32_t* __restrict__ nstay, uint32_t* __restrict__ ctl)
 {
@@ -756,6 +766,9 @@ __global__ void k_gap_offsets(GridDev G, const int* __restrict__ nei_patch, uint
   }
   if (nl > rl) {
     atomicMax(&ctl[GAP_CTL_MAX_NL], nl);
+  }
+  if (total > CNT_MAX) {
+    atomicExch(&ctl[GAP_CTL_M_FULL], 1u); // 16-bit planes: the step is redone on the eager path
   }
 }
 
@@ -790,7 +803,7 @@ __global__ void __launch_bounds__(256)
 // cell, class) group inside the target's run + its rank inside the group
 __global__ void k_gap_place(uint32_t n_slots, const uint4* __restrict__ mtag, const float4* __restrict__ mx,
                             const float4* __restrict__ mp, const uint32_t* __restrict__ start,
-                            const uint32_t* __restrict__ rel, float4* __restrict__ xo,
+                            const cnt_t* __restrict__ rel, float4* __restrict__ xo,
                             float4* __restrict__ po)
 {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -975,7 +988,7 @@ int gap_finish(Ctx* c, bool* redo)
   const size_t nct = (size_t)G.n_cells * G.n_patches;
   const int np = G.n_patches;
   *redo = false;
-  uint32_t* cnt = c->scr[9].as<uint32_t>();
+  cnt_t* cnt = c->scr[9].as<cnt_t>();
   uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, dropped, remote, -, new patch sizes...]
   {
     KernelScope ks(c, "gap_offsets");

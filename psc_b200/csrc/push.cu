@@ -387,7 +387,7 @@ struct PushArgs
   // counting hook (COUNT): cnt[class][cell] planes (every entry is written exactly once,
   // no memset needed), flags[0] = precondition broken, flags[1] = dropped particles,
   // flags[2] = particles leaving for another rank
-  uint32_t* cnt;
+  cnt_t* cnt;
   uint32_t* flags;
   uint32_t nct;
   int same_dxi; // 1/float(dx) == float(dx_inv) bitwise: the pusher's cell = the indexer's cell
@@ -920,7 +920,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         }
         if (COUNT && !GAP) {
           if (lane < FS_PLANES) {
-            A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur)] = mycount;
+            A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur)] = (cnt_t)mycount;
+            if (mycount > CNT_MAX) {
+              atomicExch(&A.flags[0], 1u);
+            }
           } else if (mycount) {
             if (lane == CLS_BAD) {
               atomicExch(&A.flags[0], 1u);
@@ -949,7 +952,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
         const uint32_t left = __reduce_add_sync(FULL, lane == CLS_CENTER ? 0u : v);
         const uint32_t nj = __shfl_sync(FULL, myoff, j + 1) - __shfl_sync(FULL, myoff, j);
         if (lane < FS_PLANES) {
-          A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + j)] = lane == CLS_CENTER ? nj - left : v;
+          const uint32_t cv = lane == CLS_CENTER ? nj - left : v;
+          A.cnt[(size_t)lane * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + j)] = (cnt_t)cv;
+          if (cv > CNT_MAX) {
+            atomicExch(&A.flags[0], 1u);
+          }
         } else {
           special += v;
         }
@@ -1107,9 +1114,9 @@ static int push_dim(Ctx* c, bool gap)
     bool count = c->want_counts || gap;
     if (count) {
       // the kernel writes every cnt[class][cell] entry exactly once: no memset
-      PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(uint32_t)));
+      PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(cnt_t)));
       PSC_TRY(c->scr[11].reserve((G.n_patches + 1 + 4) * sizeof(uint32_t)));
-      A.cnt = c->scr[9].as<uint32_t>();
+      A.cnt = c->scr[9].as<cnt_t>();
       A.flags = c->scr[11].as<uint32_t>();
       PSC_CUDA_TRY(cudaMemsetAsync(A.flags, 0, 4 * sizeof(uint32_t), c->stream));
     }

@@ -211,3 +211,39 @@ def test_keep_sorted_deck_cadence(dim):
         # the others: bit-identical records
         assert a[ka].tobytes() == b[kb].tobytes()
     assert np.abs(j0 - j1).max() <= 1e-5 * np.abs(j0).max()
+
+
+def test_fused_sort_falls_back_for_a_huge_cell():
+    """the destination-count planes are 16 bit: a cell with more than 65535 particles breaks
+    the fused pass's precondition and the step takes the general exchange + sort -- same
+    result (bit-exact against the oracle), counted as a fallback"""
+    import ctypes as C
+    import psc_b200 as pb
+    from gen import random_fields
+    og = ol.Grid(gdims=(8, 8, 8), length=(8., 8., 8.), np_=(1, 1, 1), dt=0.3, kinds=KINDS, nicell=4)
+    flds = random_fields(og, seed=1)
+    prts, off = thermal_plasma(og, ppc=2, seed=2, vth=(0.2, 0.02))
+    rng = np.random.default_rng(3)
+    n_big = 70000
+    big = np.zeros(n_big, dtype=prts.dtype)
+    big["x"] = (np.array([3., 4., 5.]) + 0.05 + 0.9 * rng.random((n_big, 3))).astype(np.float32)
+    big["u"] = (0.2 * rng.standard_normal((n_big, 3))).astype(np.float32)
+    big["kind"] = 0
+    big["qni_wni"] = np.float32(-1.)
+    prts = np.concatenate([prts, big])
+    off = ol.off_from_counts([len(prts)])
+    grid, mprts, mflds = gpu_state(og, flds, prts, off)
+    prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=0, checks=0)
+    rp, ro = prts.copy(), off.copy()
+    L, G = ol.lib(), og.byref()
+    for _ in range(2):
+        pb.check(grid.lib.psc_b200_step(grid.ctx, C.byref(prm)))
+        assert L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None) == 0
+        L.po_push_mprts(G, ol.ptr(flds.copy()), ol.ptr(rp), ol.ptr(ro))
+        rp, ro, _ = ol.bnd_particles(og, rp, ro)
+    assert L.po_sort(G, ol.ptr(rp), ol.ptr(ro), None) == 0
+    assert grid.get_stat("fused_fallbacks") >= 1
+    got, got_off = mprts.get()
+    assert np.array_equal(got_off, ro)
+    assert got.tobytes() == rp.tobytes()
+    grid.close()
