@@ -218,6 +218,11 @@ int psc_b200_best_mapping(int n_ranks, const double* capability, int n_patches,
 /* ---- options, measurement ---- */
 /* "keep_sorted" (0/1), "tile" (cells per tile edge), "warp_reduce" (0/1),
  * "threads" (CTA size of the push kernel), "profile" (0/1) */
+/* Self-test of the exact build's device arithmetic: compares the guard-free 1/sqrt(x) and
+ * 1/x sequences the push uses for arguments >= 1 with the compiler's correctly rounded
+ * forms (= the reference's host arithmetic, cuda_compat.h:26-30) on every float in
+ * [1, 2^80); *n_mismatch must come back 0. */
+int psc_b200_selftest_math(psc_b200_ctx* ctx, uint64_t* n_mismatch);
 int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value);
 int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value);
 /* CUDA-event timer on the context's stream */

@@ -96,6 +96,7 @@ def load():
         "psc_b200_marder": [CTX, C.c_double, C.c_int],
         "psc_b200_moment_rho_1st_nc": [CTX, C.c_int],
         "psc_b200_moment_n_comps": [CTX, C.c_int],
+        "psc_b200_selftest_math": [CTX, C.POINTER(C.c_uint64)],
         "psc_b200_moment_1st": [CTX, C.c_int, C.c_int],
         "psc_b200_check_continuity_begin": [CTX],
         "psc_b200_check_continuity_end": [CTX, C.POINTER(C.c_double)],

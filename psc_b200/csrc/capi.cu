@@ -692,6 +692,11 @@ int psc_b200_best_mapping(int n_ranks, const double* capability, int n_patches,
   }
 }
 
+int psc_b200_selftest_math(psc_b200_ctx* ctx, uint64_t* n_mismatch)
+{
+  GUARD(return selftest_math(c, n_mismatch);)
+}
+
 int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
 {
   GUARD(

@@ -212,6 +212,7 @@ int prts_get(Ctx* c, void* aos, uint32_t* off);
 int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed);
 int prts_upload_off(Ctx* c);
 int prts_energies(Ctx* c, double out2[2]);
+int selftest_math(Ctx* c, uint64_t* n_bad);
 
 // ---- push.cu (two builds of the same source: exact = -fmad=false, fast = FMA)
 int push_mprts_exact(Ctx* c);

@@ -350,6 +350,38 @@ int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed)
   return prts_upload_off(c);
 }
 
+// every float in [1, 2^80): the guard-free sequences of pic_math.cuh against the
+// compiler's correctly rounded 1.f / sqrtf(x) and 1.f / x
+__global__ void k_selftest_math(unsigned long long* n_bad)
+{
+  const uint32_t lo = 0x3f800000u, hi = 0x3f800000u + (80u << 23);
+  unsigned long long bad = 0;
+  for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < hi;
+       b += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)b);
+    const float a0 = 1.f / sqrtf(x), a1 = pm::rsqrt_ref(x);
+    const float b0 = 1.f / x, b1 = pm::rcp_ref(x);
+    bad += (__float_as_uint(a0) != __float_as_uint(a1)) + (__float_as_uint(b0) != __float_as_uint(b1));
+  }
+  if (bad) {
+    atomicAdd(n_bad, bad);
+  }
+}
+
+int selftest_math(Ctx* c, uint64_t* n_bad)
+{
+  PSC_TRY(c->scr[0].reserve(sizeof(unsigned long long)));
+  unsigned long long* d = c->scr[0].as<unsigned long long>();
+  PSC_CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->stream));
+  k_selftest_math<<<148 * 16, 256, 0, c->stream>>>(d);
+  c->n_launches++;
+  unsigned long long h = 0;
+  PSC_CUDA_TRY(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *n_bad = h;
+  return check_launch(c, "selftest_math");
+}
+
 int prts_energies(Ctx* c, double out2[2])
 {
   const GridHost& g = c->g;

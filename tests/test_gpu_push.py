@@ -110,3 +110,17 @@ def test_continuity_large():
         assert psc.checks.continuity.last_max_err < 2e-5, psc.checks.continuity.last_max_err
     assert mprts.size() == n0
     grid.close()
+
+
+@pytest.mark.gpu
+def test_guard_free_ieee_sequences_exhaustive():
+    """the exact build issues nvcc's correctly rounded 1/sqrt(x), 1/x fast paths without
+    their range guard (arguments are >= 1): bit-identical to the guarded forms on every
+    float in [1, 2^80)"""
+    import ctypes as C
+    import psc_b200 as pb
+    grid = pb.Grid(gdims=(8, 8, 8), length=(8., 8., 8.), np=(1, 1, 1), dt=0.1, kinds=((-1., 1.),), nicell=1)
+    n = C.c_uint64(12345)
+    pb.check(grid.lib.psc_b200_selftest_math(grid.ctx, C.byref(n)))
+    assert n.value == 0
+    grid.close()
