@@ -1017,9 +1017,12 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, bool gap, 
     return -1; // a row's cell boundaries are held one per lane
   }
   // register budget variants (launch bounds); odd geometries get the roomy one only
-  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)  3: (384, 2)  4: (192, 3)
+  int lb = 1; // 0: (256, 3)  1: (256, 2)  2: (512, 1)  3: (384, 2)  4: (192, 3)  5: (192, 4)
   if (TUNE) {
-    lb = threads > 384 ? 2 : (threads == 384 ? 3 : (threads == 192 ? 4 : (c->opt_min_blocks == 2 ? 1 : 0)));
+    lb = threads > 384 ? 2
+                       : (threads == 384 ? 3
+                                         : (threads == 192 ? (c->opt_min_blocks == 4 ? 5 : 4)
+                                                           : (c->opt_min_blocks == 2 ? 1 : 0)));
   } else {
     threads = std::min(threads, 256);
   }
@@ -1050,6 +1053,8 @@ static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, bool gap, 
         PSC_LAUNCH(TM, CN, GP, 384, 2);                                                           \
       } else if (lb == 4) {                                                                       \
         PSC_LAUNCH(TM, CN, GP, 192, 3);                                                           \
+      } else if (lb == 5) {                                                                       \
+        PSC_LAUNCH(TM, CN, GP, 192, 4);                                                           \
       } else {                                                                                    \
         PSC_LAUNCH(TM, CN, GP, 256, 2);                                                           \
       }                                                                                           \
