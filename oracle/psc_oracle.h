@@ -10,9 +10,15 @@
  *     test_current_deposition.cxx (tests/golden/ JSON fixtures).
  *   - sort: pinned by the 15-particle vector of test_collision_cuda.cxx:145-190
  *     plus the stable-counting-sort definition (no CPU test exists upstream).
- *   - ghost fill/add: test_bnd.cxx value pattern; Yee: test_push_fields.cxx.
- *   - particle migration order, Var1 vs Split on yz, energies: parity unpinned
- *     by upstream tests; pinned here only against _ref where _ref covers it.
+ *   - ghost fill/add: the exact FillGhosts / AddGhosts patterns of test_bnd.cxx:104-303;
+ *     Yee, Marder correct, div: Pushf1/2, MarderCorrect, ItemDivE/J of
+ *     test_push_fields.cxx:26-260; the 1st-order moments: the 14 known-answer cases of
+ *     test_moments.cxx:149-402; push + exchange + J ghosts + continuity over many steps:
+ *     Accel / Cyclo of test_push_particles_2.cxx:23-170 (tests/golden_cases.py,
+ *     tests/test_oracle_golden.py, tests/test_accel_cyclo.py).
+ *   - particle migration order, Var1 vs Split on yz, the balancer mapping, energies over
+ *     1000 steps: parity unpinned by upstream tests; pinned here only against _ref where
+ *     _ref covers it.
  *
  * All arrays use PSC's layouts:
  *   fields   : float [p][m][iz][iy][ix], ix fastest, dims im = ldims + 2*ibn,
