@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cells, ppc = 32, 64
+    cells, ppc = args.ref_cells, 64
     # ~4 patches per thread keeps a step around a few seconds
     val, ms, sample, used = cpu_arm(cells, ppc, max(4, 2 * cores), args.steps, min(args.warmup, 1), cores)
     line = {
@@ -368,6 +368,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--min-blocks", dest="min_blocks", type=int, default=0)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
+    ap.add_argument("--ref-cells", dest="ref_cells", type=int, default=32,
+                    help="--impl reference: cells per patch edge of the bounded sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
