@@ -19,6 +19,9 @@
 //   Marder         MarderB200           ~ MarderCommon      (marder_impl.hxx:197-264)
 //   Checks         ChecksB200           ~ Checks_           (checks_impl.hxx:33-215)
 //   Balance        BalanceB200          ~ Balance_          (psc_balance_impl.hxx:770-1026)
+//   Collision      CollisionB200        (type only: collisions are out of scope; CollisionViaHostB200
+//                                        = PSC's CollisionCudaHost round trip for a host operator)
+//   moments        Moment_n_1st_B200 ...~ ItemMoment<moment_*> (fields_item_moments_1st.hxx:9-37)
 //
 // Every method is one call into libpsc_b200.so (include/psc_b200.h); nothing is computed
 // on the host and there is no CPU fallback.  Error behaviour is PSC's: a failed call
@@ -615,6 +618,64 @@ using Moments_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_ALL>;
 template <typename GridT>
 using Moment_rho_1st_nc_B200 = MomentB200<GridT, PSC_B200_MOMENT_RHO_NC>;
 
+// Collision (psc.hxx:111,363-366; decks: `Collision collision{grid, interval, nu}`, e.g.
+// psc_bubble_yz.cxx:303-306).  Binary collisions are not part of this backend; the
+// type exists so that Psc<PscConfig> instantiates.  A deck that leaves collisions off (interval <= 0, the
+// default of the parity runs) is unaffected; asking this type to collide stops the run with a message
+// instead of silently skipping physics.  To keep PSC's host collision operator, use
+// CollisionViaHostB200 below -- the round trip PSC's own CUDA build makes in CollisionCudaHost
+// (libpsc/cuda/collision_cuda_host_impl.hxx:16-33).
+template <typename GridT>
+struct CollisionB200
+{
+  using Mparticles = MparticlesB200<GridT>;
+  CollisionB200(const GridT&, int interval, double nu) : interval_(interval), nu_(nu) {}
+  int interval() const { return interval_; }
+  double nu() const { return nu_; }
+  void operator()(Mparticles&)
+  {
+    std::fprintf(stderr,
+                 "psc_b200: binary collisions are not implemented on the device; set the collision interval "
+                 "to 0 or plug a host operator in through CollisionViaHostB200\n");
+    std::abort();
+  }
+
+private:
+  int interval_;
+  double nu_;
+};
+
+// Host round trip: the particles come back as PSC's 32-byte records (patch by patch, off[p]..off[p+1]),
+// `collide(prts, off)` changes momenta in place (a lambda around Collision_<MparticlesSingle, ...>), the
+// records go back.  Counts per patch must not change.
+template <typename GridT, typename HostCollide>
+struct CollisionViaHostB200
+{
+  using Mparticles = MparticlesB200<GridT>;
+  CollisionViaHostB200(const GridT&, int interval, double nu, HostCollide collide)
+    : interval_(interval), nu_(nu), collide_(collide)
+  {}
+  int interval() const { return interval_; }
+  double nu() const { return nu_; }
+  void operator()(Mparticles& mprts)
+  {
+    std::vector<Particle> prts;
+    std::vector<uint32_t> off;
+    mprts.get(prts, off);
+    collide_(prts, off);
+    std::vector<uint32_t> n_by_patch(off.size() - 1);
+    for (size_t p = 0; p + 1 < off.size(); p++) {
+      n_by_patch[p] = off[p + 1] - off[p];
+    }
+    mprts.set(prts, n_by_patch);
+  }
+
+private:
+  int interval_;
+  double nu_;
+  HostCollide collide_;
+};
+
 // ChecksParams (checks_params.hxx): the cadence/threshold fields the step loop reads
 struct ChecksParamsB200
 {
@@ -725,6 +786,11 @@ struct PscConfig
   using Balance = BalanceB200<GridT>;
   using Checks = ChecksB200<GridT>;
   using Marder = MarderB200<GridT>;
+  using Collision = CollisionB200<GridT>; // psc.hxx:111 (see CollisionViaHostB200 for PSC's host operator)
+#ifdef PSC_B200_WITH_PSC_GRID
+  // PSC's own particle output works through accessor() (psc_config.hxx:94)
+  using OutputParticles = OutputParticlesDefault<Mparticles>;
+#endif
 };
 
 // ----------------------------------------------------------------------

@@ -135,6 +135,28 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
   wr(flds1.data(), flds1.size() * 4);
   double tail[10] = {max_cont, sum_w, en[0], en[1], en[2], en[3], en[4], en[5], en[6], en[7]};
   wr(tail, sizeof(tail));
+  // Collision as Psc<PscConfig> uses it (psc.hxx:363-366): off in this run; the host round
+  // trip (PSC's CollisionCudaHost pattern) with an operator that leaves the momenta alone
+  // must hand back exactly the same store
+  {
+    typename Config::Collision collision{grid, 0, 0.1};
+    if (collision.interval() > 0) {
+      return 5;
+    }
+    auto nop = [](std::vector<psc_b200::Particle>& prts, const std::vector<uint32_t>& off) {
+      (void)prts;
+      (void)off;
+    };
+    psc_b200::CollisionViaHostB200<Grid, decltype(nop)> coll_host{grid, 10, 0.1, nop};
+    coll_host(mprts);
+    std::vector<psc_b200::Particle> prts2;
+    std::vector<uint32_t> off2;
+    mprts.get(prts2, off2);
+    if (off2 != off1 || std::memcmp(prts2.data(), prts1.data(), prts1.size() * sizeof(prts1[0])) != 0) {
+      std::fprintf(stderr, "host round trip changed the store\n");
+      return 6;
+    }
+  }
   // device-side moments through the ItemMoment-shaped wrappers
   // (fields_item_moments_1st.hxx:9-30): density per kind and the 13-component set
   {
