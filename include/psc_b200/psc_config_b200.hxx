@@ -708,6 +708,12 @@ struct ChecksB200
         PSC_B200_CHECK(psc_b200_check_continuity_begin(mprts.ctx()));
       }
     }
+    // the shape Psc::step uses (psc.hxx:379-383): the caller has tested should_do_check(timestep)
+    void before_particle_push(Mparticles& mprts)
+    {
+      armed = true;
+      PSC_B200_CHECK(psc_b200_check_continuity_begin(mprts.ctx()));
+    }
     void after_particle_push(Mparticles& mprts, MfieldsState&)
     {
       if (armed) {
@@ -731,11 +737,24 @@ struct ChecksB200
         assert(last_max_err < threshold); // checks_impl.hxx:211
       }
     }
+    // the shape Psc::step uses (psc.hxx:234-237,478-482): the caller has tested should_do_check
+    void operator()(Mparticles& mprts, MfieldsState&)
+    {
+      PSC_B200_CHECK(psc_b200_check_gauss(mprts.ctx(), &last_max_err));
+      assert(last_max_err < threshold);
+    }
   };
 
   ChecksB200(const GridT&, const ChecksParamsB200& prm)
     : continuity{prm.continuity_every_step, prm.continuity_threshold},
       gauss{prm.gauss_every_step, prm.gauss_threshold}
+  {}
+  // a deck's `Checks checks{grid, MPI_COMM_WORLD, checks_params}` with PSC's ChecksParams
+  // (include/checks_params.hxx:3-42: continuity / gauss . check_interval, err_threshold)
+  template <typename Comm, typename PscChecksParams>
+  ChecksB200(const GridT&, Comm, const PscChecksParams& prm)
+    : continuity{prm.continuity.check_interval, prm.continuity.err_threshold},
+      gauss{prm.gauss.check_interval, prm.gauss.err_threshold}
   {}
 
   Continuity continuity;

@@ -174,6 +174,62 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
     }
   }
   std::fclose(f);
+
+  // one more step written with the exact call shapes of Psc::step (psc.hxx:340-486) and of a
+  // deck's constructors (psc_bubble_yz.cxx:296-320) -- a compile-and-run check that the
+  // operator types are source-compatible with it
+  {
+    struct PscCheckParams
+    {
+      int check_interval = 1;
+      double err_threshold = 1e-4;
+    };
+    struct PscChecksParams
+    {
+      PscCheckParams continuity, gauss;
+    } checks_params;
+    checks_params.gauss.err_threshold = 1e30; // the random start is not Gauss-consistent
+    typename Config::Checks checks_{grid, 0 /* MPI_Comm */, checks_params};
+    typename Config::Collision collision_{grid, 0, 0.1};
+    typename Config::Sort sort_;
+    typename Config::PushParticles pushp_;
+    typename Config::BndParticles bndp_{grid};
+    typename Config::Bnd bnd_;
+    typename Config::BndFields bndf;
+    typename Config::PushFields pushf_;
+    const int timestep = n_steps + 1;
+    sort_(mprts);
+    if (collision_.interval() > 0 && timestep % collision_.interval() == 0) {
+      collision_(mprts);
+    }
+    if (checks_.continuity.should_do_check(timestep)) {
+      checks_.continuity.before_particle_push(mprts);
+    }
+    pushp_.push_mprts(mprts, mflds);
+    bndp_(mprts);
+    bndf.add_ghosts_J(mflds);
+    bnd_.add_ghosts(mflds, PSC_B200_JXI, PSC_B200_JXI + 3);
+    bnd_.fill_ghosts(mflds, PSC_B200_JXI, PSC_B200_JXI + 3);
+    pushf_.push_H(mflds, .5, Dim{});
+    bndf.fill_ghosts_H(mflds);
+    bnd_.fill_ghosts(mflds, PSC_B200_HX, PSC_B200_HX + 3);
+    pushf_.push_E(mflds, 1., Dim{});
+    bndf.fill_ghosts_E(mflds);
+    bnd_.fill_ghosts(mflds, PSC_B200_EX, PSC_B200_EX + 3);
+    pushf_.push_H(mflds, .5, Dim{});
+    bndf.fill_ghosts_H(mflds);
+    bnd_.fill_ghosts(mflds, PSC_B200_HX, PSC_B200_HX + 3);
+    if (checks_.continuity.should_do_check(timestep)) {
+      checks_.continuity.after_particle_push(mprts, mflds);
+    }
+    if (checks_.gauss.should_do_check(timestep)) {
+      checks_.gauss(mprts, mflds);
+    }
+    if (!(checks_.continuity.last_max_err < 1e-4) || (size_t)mprts.size() != prts1.size()) {
+      std::fprintf(stderr, "Psc::step-shaped step: continuity %g\n", checks_.continuity.last_max_err);
+      return 7;
+    }
+  }
   std::printf("ok: %zu particles, %d steps, continuity %.3g, sum w %.1f\n", prts1.size(), n_steps,
               max_cont, sum_w);
   return 0;
