@@ -197,7 +197,7 @@ def run_b200(args, rank, world, local_rank):
         dist.broadcast(idt, 0)
         grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
     for k, v in (("fma", args.fma), ("tiled", args.tiled), ("tma", args.tma),
-                 ("warp_reduce", args.warp_reduce), ("fused_sort", args.fused_sort), ("gapped", args.gapped), ("gap_slack", args.gap_slack), ("overlap", args.overlap)):
+                 ("fused_sort", args.fused_sort), ("gapped", args.gapped), ("gap_slack", args.gap_slack), ("overlap", args.overlap)):
         grid.set_option(k, v)
     if args.tile:
         grid.set_option("tile", args.tile)
@@ -334,7 +334,7 @@ def run_b200(args, rank, world, local_rank):
                                % (n, ppc, pe, "step" if args.sort_interval == 1 else "%d steps" % args.sort_interval),
                    "particles_per_gpu": n_prts, "cells_per_gpu": n_cells_gpu, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
-                   "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma, "warp_reduce": args.warp_reduce,
+                   "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma,
                                                 "fused_sort": args.fused_sort, "gapped": args.gapped, "overlap": args.overlap}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "kernels": kernels,
@@ -357,7 +357,6 @@ def main():
     ap.add_argument("--fma", type=int, default=0)
     ap.add_argument("--tiled", type=int, default=1)
     ap.add_argument("--tma", type=int, default=1)
-    ap.add_argument("--warp-reduce", dest="warp_reduce", type=int, default=1)
     ap.add_argument("--fused-sort", dest="fused_sort", type=int, default=1)
     ap.add_argument("--sort-interval", dest="sort_interval", type=int, default=1,
                     help="PscParams::sort_interval; the headline metric sorts every step, PSC's decks every 10th")

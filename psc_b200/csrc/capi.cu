@@ -702,7 +702,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
   GUARD(
     std::string n(name); int v = (int)value;
     if (n == "tiled") { c->opt_tiled = v; }
-    else if (n == "warp_reduce") { c->opt_warp_reduce = v; }
+    else if (n == "warp_reduce") { (void)v; } // accepted for old scripts: the per-cell warp reduction is always on
     else if (n == "fma") { c->opt_fma = v; }
     else if (n == "tma") { c->opt_tma = v; }
     else if (n == "threads") { c->opt_threads = v; }

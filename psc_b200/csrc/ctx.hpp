@@ -94,7 +94,6 @@ struct Ctx
 
   // ---- options (psc_b200_set_option)
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
-  int opt_warp_reduce = 1; // warp-level pre-reduction of deposits in the tiled push
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with cp.async.bulk (TMA) instead of LDG/STS
   int opt_threads = 256;   // CTA size of the tiled push

@@ -23,10 +23,10 @@ CASES = {
 }
 PATHS = {
     "general": (dict(tiled=0), False),
-    "tiled": (dict(tiled=1, warp_reduce=0, tma=0, keep_sorted=0), True),  # the variant without the class counts
-    "tiled_warp": (dict(tiled=1, warp_reduce=1, tma=0), True),
-    "tiled_warp_tma": (dict(tiled=1, warp_reduce=1, tma=1), True),
-    "tiled_small": (dict(tiled=1, warp_reduce=1, tma=1, tile=4, threads=128), True),
+    "tiled": (dict(tiled=1, tma=0, keep_sorted=0), True),  # the variant without the class counts
+    "tiled_warp": (dict(tiled=1, tma=0), True),            # ... with them, tile staged by LDG/STS
+    "tiled_warp_tma": (dict(tiled=1, tma=1), True),        # ... tile staged by TMA bulk copies
+    "tiled_small": (dict(tiled=1, tma=1, tile=4, threads=128), True),  # run-time tile geometry
 }
 
 
