@@ -43,6 +43,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -773,7 +774,31 @@ struct BalanceB200
     PSC_B200_CHECK(psc_b200_balance(mprts.ctx(), factor_fields_, &changed));
     return changed != 0;
   }
+
+  // The shape Psc::step uses (psc.hxx:346-350): balance_(grid_, mprts_).  The patches (particles
+  // and every field container) move between the GPUs inside the library; PSC additionally expects
+  // its host Grid_t to be REPLACED by one for the new decomposition (psc_balance_impl.hxx:893-1016).
+  // That part is the deck's: `regrid(old_grid, first_local_patch, n_local_patches)` returns the new
+  // grid (in a PSC tree: new Grid_t{domain, bc, kinds, norm, dt, n_patches, ibn}); it is only called
+  // when something moved.
+  using Regrid = std::function<GridT*(GridT*, int, int)>;
+  void set_regrid(Regrid regrid) { regrid_ = std::move(regrid); }
+  void operator()(GridT*& grid_ptr, MparticlesB200<GridT>& mprts)
+  {
+    if (!(*this)(mprts)) {
+      return;
+    }
+    if (!regrid_) {
+      std::fprintf(stderr, "psc_b200: patches were rebalanced but no regrid hook is installed "
+                           "(BalanceB200::set_regrid): the host grid no longer matches the device\n");
+      std::abort();
+    }
+    grid_ptr = regrid_(grid_ptr, psc_b200_patch_begin(mprts.ctx()), psc_b200_n_patches(mprts.ctx()));
+    mprts.reset(*grid_ptr);
+  }
+
   double factor_fields_;
+  Regrid regrid_;
 };
 
 // DiagEnergies (DiagEnergiesField.h:19-42, DiagEnergiesParticle.h:15-40)

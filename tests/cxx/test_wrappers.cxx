@@ -198,6 +198,15 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
     typename Config::BndFields bndf;
     typename Config::PushFields pushf_;
     const int timestep = n_steps + 1;
+    {
+      // psc.hxx:346: balance_(grid_, mprts_) -- one rank: nothing moves, the grid stays
+      typename Config::Balance balance_{1.};
+      Grid* grid_ptr = &grid;
+      balance_(grid_ptr, mprts);
+      if (grid_ptr != &grid) {
+        return 8;
+      }
+    }
     sort_(mprts);
     if (collision_.interval() > 0 && timestep % collision_.interval() == 0) {
       collision_(mprts);
