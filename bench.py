@@ -60,16 +60,32 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_ev, self.th = index, [], threading.Event(), None
+        self.index, self.rows, self.stop_ev, self.th, self.proc = index, [], threading.Event(), None, None
 
     def _run(self):
+        # one streaming nvidia-smi (a sample every 100 ms) instead of one process per sample;
+        # falls back to polling if the loop mode is not available
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_ev.is_set():
+                    break
+            if self.rows or self.stop_ev.is_set():
+                return
+        except Exception:
+            pass
         while not self.stop_ev.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([s.strip() for s in out.split(",")])
+                    self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
             self.stop_ev.wait(0.2)
@@ -77,9 +93,15 @@ class ClockSampler:
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
+        time.sleep(0.15)  # let the stream deliver its first sample before the timed region
 
     def stop(self):
         self.stop_ev.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         if self.th:
             self.th.join(timeout=6)
         sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
@@ -222,10 +244,10 @@ def run_b200(args, rank, world, local_rank):
         psc.step()
     grid.set_option("profile", 1)
     grid.profile_reset()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the barrier: its start-up must not delay rank 0 inside the timed region
+    barrier()
     l0 = grid.get_stat("n_launches")
     grid.timer_start()
     for _ in range(args.steps):
