@@ -4,6 +4,8 @@
 // fallback: without a CUDA device psc_b200_create fails.
 #include "dev_util.cuh"
 
+#include <cuda.h> // CUtensorMap and its enums (types only)
+
 #include <algorithm>
 #include <cstring>
 #include <exception>
@@ -104,6 +106,50 @@ static void prof_collect(Ctx* c)
     cudaEventDestroy(e.second.second);
   }
   c->prof_pending.clear();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link)
+int field_tile_tensor_map(Ctx* c, int id, int rank, const int* box, TensorMap128* out)
+{
+  using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PSC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      return fail("cuTensorMapEncodeTiled is not available from this driver");
+    }
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  const GridDev& G = c->gd;
+  const cuuint64_t comps = (cuuint64_t)c->flds[id].n_comps * (cuuint64_t)c->n_slots;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  if (rank == 4) {
+    dims[0] = G.im[0], dims[1] = G.im[1], dims[2] = G.im[2], dims[3] = comps;
+    strides[0] = (cuuint64_t)G.im[0] * 4, strides[1] = (cuuint64_t)G.im[0] * G.im[1] * 4;
+    strides[2] = (cuuint64_t)G.fld_len * 4;
+  } else if (rank == 3 && G.im[0] == 1) {
+    dims[0] = G.im[1], dims[1] = G.im[2], dims[2] = comps;
+    strides[0] = (cuuint64_t)G.im[1] * 4, strides[1] = (cuuint64_t)G.fld_len * 4;
+  } else {
+    return fail("field_tile_tensor_map: unsupported rank");
+  }
+  for (int d = 0; d < rank; d++) {
+    bx[d] = (cuuint32_t)box[d];
+  }
+  static_assert(sizeof(CUtensorMap) == sizeof(TensorMap128), "");
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                      c->flds[id].d, dims, strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  }
+  return 0;
 }
 
 // neighbour / boundary tables of this rank's patches
@@ -705,6 +751,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "warp_reduce") { (void)v; } // accepted for old scripts: the per-cell warp reduction is always on
     else if (n == "fma") { c->opt_fma = v; }
     else if (n == "tma") { c->opt_tma = v; }
+    else if (n == "lean") { c->opt_lean = v; }
     else if (n == "threads") { c->opt_threads = v; }
     else if (n == "min_blocks") { c->opt_min_blocks = v; }
     else if (n == "tile") { c->opt_tile[0] = c->opt_tile[1] = c->opt_tile[2] = v; }

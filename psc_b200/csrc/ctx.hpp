@@ -95,7 +95,8 @@ struct Ctx
   // ---- options (psc_b200_set_option)
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
-  int opt_tma = 1;         // stage the E/B tile with cp.async.bulk (TMA) instead of LDG/STS
+  int opt_tma = 1;         // stage the E/B tile with TMA (tensor map / cp.async.bulk) instead of LDG/STS
+  int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time
   int opt_threads = 256;   // CTA size of the tiled push
   int opt_min_blocks = 3;  // resident CTAs per SM the tiled push is compiled for
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default
@@ -277,6 +278,15 @@ int comm_allreduce_sum(Ctx* c, double* v, int n);
 
 // ---- tables
 int build_patch_tables(Ctx* c);
+
+// a CUtensorMap (cuda.h) over field array `id`, seen as (x, y, z, component x slot) -- or
+// (y, z, component x slot) for rank 3 -- with the given box; encoded through the driver entry
+// point the runtime hands out (no link against libcuda)
+struct alignas(64) TensorMap128
+{
+  unsigned char b[128];
+};
+int field_tile_tensor_map(Ctx* c, int id, int rank, const int* box, TensorMap128* out);
 
 // ---- balance (comm.cu)
 int balance(Ctx* c, double factor_fields, int* changed);

@@ -34,7 +34,10 @@
 // (namespace fast, within a few ULP).
 #include "gap.cuh"
 
+#include <cuda.h> // CUtensorMap (the type only: the encoder is fetched through the runtime, ctx.hpp)
+
 #include <algorithm>
+#include <cstring>
 
 #ifndef PUSH_VARIANT
 #define PUSH_VARIANT exact
@@ -1005,7 +1008,50 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
   }
 }
 
+#include "push_lean.cuh"
+
 // ---------------------------------------------------------------- host side
+
+// k_push_lean: compile-time geometry, tensor-map TMA, no gapped store
+template <int DIM, int DEPOSIT>
+static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, const PushArgs& A)
+{
+  const GridDev& G = c->gd;
+  constexpr bool XYZ = DIM == pm::DIM_XYZ;
+  const int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
+  const size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
+                            (size_t)lean::NW * (lean::QC * 2 + 64) * sizeof(float4);
+  TensorMap128 tm128;
+  const int box[4] = {XYZ ? geo.f(0) : geo.f(1), XYZ ? geo.f(1) : geo.f(2), XYZ ? geo.f(2) : 6, 6};
+  PSC_TRY(field_tile_tensor_map(c, 0, XYZ ? 4 : 3, box, &tm128));
+  CUtensorMap tm;
+  static_assert(sizeof(tm) == sizeof(tm128), "");
+  memcpy(&tm, &tm128, sizeof(tm));
+#define PSC_LEAN(CN, SM)                                                                          \
+  do {                                                                                            \
+    auto kern = lean::k_push_lean<DIM, DEPOSIT, CN, SM>;                                          \
+    PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                      (int)smem_bytes));                                          \
+    kern<<<tiles, lean::NW * 32, smem_bytes, c->stream>>>(tm, G, geo, A);                         \
+  } while (0)
+  if (count) {
+    // the planes are added to (leavers one by one, stayers once per cell)
+    PSC_CUDA_TRY(cudaMemsetAsync(A.cnt, 0, (size_t)A.nct * FS_PLANES * sizeof(cnt_t), c->stream));
+    if (A.same_dxi) {
+      PSC_LEAN(true, true);
+    } else {
+      PSC_LEAN(true, false);
+    }
+  } else {
+    if (A.same_dxi) {
+      PSC_LEAN(false, true);
+    } else {
+      PSC_LEAN(false, false);
+    }
+  }
+#undef PSC_LEAN
+  return 0;
+}
 
 template <int DIM, int DEPOSIT, typename GEO, bool TUNE>
 static int launch_tiled(Ctx* c, const GEO& geo, bool tma, bool count, bool gap, const PushArgs& A)
@@ -1151,7 +1197,12 @@ static int push_dim(Ctx* c, bool gap)
       stat = stat && (inv || (G.ibn[d] == 2 && G.ldims[d] % gs.t(d) == 0));
     }
     int rc = -1;
-    if (stat) {
+    if (stat && !gap && c->opt_lean && c->opt_tma && G.im[xyz ? 0 : 1] % 4 == 0) {
+      // (tensor-map strides are multiples of 16 bytes)
+      KernelScope ks(c, "push_lean");
+      rc = launch_lean<DIM, DEPOSIT>(c, gs, count, A);
+    }
+    if (rc == -1 && stat) {
       // bulk copies: contiguous rows (x in 3D, y in yz) must be 16-byte aligned
       int cd = xyz ? 0 : 1;
       bool tma = c->opt_tma && (G.im[cd] % 4 == 0) && (c->fld_slot_len(0) % 4 == 0) &&

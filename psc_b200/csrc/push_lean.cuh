@@ -1,0 +1,451 @@
+// psc_b200: k_push_lean -- the tiled push + deposit kernel for a cell-ordered store and a
+// compile-time tile geometry (included by push.cu inside namespace PUSH_VARIANT).
+//
+// Same tiling as k_push_tiled (one CTA = one tile of cells of one patch, E/B tile + halo in
+// shared memory, J tile in shared memory flushed with global red.add, warps walk rows of
+// cells in 32-particle chunks, cell-crossing trajectories parked in a per-warp queue and
+// walked 32 at a time).  What differs, all of it to cut issue slots per particle
+// (profiles/r01_v10_push_tiled_ncu.txt: 609 warp instructions per chunk, 40 % of them FP):
+//
+//  * the E/B tile arrives with ONE tensor-map TMA (cp.async.bulk.tensor over
+//    (x, y, z, component x patch)); out-of-range rows are zero-filled by the unit, so there
+//    is no alignment fallback inside the kernel
+//  * a particle that stays in its cell deposits through per-cell MOMENTS instead of leaf
+//    values: with m_d = q dx_d and (a, b) the centred offsets in the two other directions,
+//    the four values of component d are linear in  S = sum m_d, Sa = sum m_d a,
+//    Sb = sum m_d b, Sab = sum (m_d a b + q h):
+//        v(0,0) = S - Sa - Sb + Sab   v(1,0) = Sa - Sab   v(0,1) = Sb - Sab   v(1,1) = Sab
+//    (calc_j2_one_cell + CurrentDeposition1vb, inc_curr_1vb_split.cxx:25-33,
+//    psc/current_deposition.hxx:17-40; curr_3d_vb_cell, inc_curr_1vb_var1.cxx:62-89).
+//    Per particle that is 6 FMA-class operations per component instead of 18; the
+//    combination runs once per cell after the warp reduction.  J is compared at 1e-5 of
+//    max|J| (summation order is free: the reference sums sequentially, we sum by warp), the
+//    particle update itself keeps the reference's operation order bit for bit.
+//  * destination classes (the input of the fused boundary exchange + sort) are counted only
+//    for the particles that left their cell: a particle whose trajectory is one segment is
+//    in class CENTER by construction.  The count planes are cleared before the launch; the
+//    queue walk adds one per leaver (32-bit red on the 16-bit planes), the row walk adds
+//    (population - leavers) to the CENTER plane once per cell.
+//  * the pass loop over the cells a chunk touches carries warp-uniform lane masks only.
+#pragma once
+
+namespace lean
+{
+
+constexpr int NW = 8;   // warps per CTA
+constexpr int QC = 56;  // queue entries per warp
+
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                              uint64_t* bar, bool four_d)
+{
+  if (four_d) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+  } else {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+
+// after warp_transpose_reduce every lane holds one moment of the cell; combine the moments
+// of a component into the leaf value that lane deposits (header comment)
+template <int DIM>
+__device__ __forceinline__ float moments_to_leaf(float v, int lane)
+{
+  if (DIM == pm::DIM_XYZ) {
+    // slot = lane >> 1 = 4 * component + k, k = 0: S, 1: Sa, 2: Sb, 3: Sab
+    const int k = (lane >> 1) & 3;
+    const int b = lane & ~6;
+    const float sab = __shfl_sync(FULL, v, lane | 6);
+    const float sa = __shfl_sync(FULL, v, b | 2);
+    const float sb = __shfl_sync(FULL, v, b | 4);
+    float r = v - (k == 0 ? sa : (k == 3 ? 0.f : sab));
+    if (k == 0) {
+      r = (r - sb) + sab;
+    }
+    return r;
+  } else {
+    // slot = lane >> 2: jx S, Sa, Sb, Sab | jy S, Sb | jz S, Sa
+    const int s = lane >> 2;
+    const float m1 = __shfl_sync(FULL, v, 4), m2 = __shfl_sync(FULL, v, 8), m3 = __shfl_sync(FULL, v, 12);
+    const float m5 = __shfl_sync(FULL, v, 20), m7 = __shfl_sync(FULL, v, 28);
+    float r = v;
+    if (s == 0) {
+      r = ((v - m1) - m2) + m3;
+    } else if (s == 1 || s == 2) {
+      r = v - m3;
+    } else if (s == 4) {
+      r = v - m5;
+    } else if (s == 6) {
+      r = v - m7;
+    }
+    return r;
+  }
+}
+
+template <int DIM, int DEPOSIT, bool COUNT, bool SAME>
+__global__ void __launch_bounds__(NW * 32, 3)
+  k_push_lean(const __grid_constant__ CUtensorMap tm, GridDev G, GeoStatic<DIM> geo, PushArgs A)
+{
+  constexpr bool XYZ = DIM == pm::DIM_XYZ;
+  constexpr int NM = XYZ ? 12 : 8;   // moments per cell = leaf values per cell
+  constexpr int NVP = XYZ ? 16 : 8;  // padded to the butterfly width
+  constexpr int NODES = GeoStatic<DIM>::sm();
+  constexpr int SY = GeoStatic<DIM>::sy(), SZ = GeoStatic<DIM>::sz();
+  constexpr int RD = XYZ ? 0 : 1;    // direction a row of cells runs along
+  constexpr int ROW_STRIDE = XYZ ? 1 : SY;
+  extern __shared__ __align__(128) float smem[];
+  float* sEM = smem;             // [6][f2][f1][f0]
+  float* sJ = smem + 6 * NODES;  // [3][f2][f1][f0]
+  float4* sQ = reinterpret_cast<float4*>(smem + ((9 * NODES + 3) & ~3)); // [NW][QC][2]
+  float4* sP = sQ + NW * QC * 2;                                         // [NW][2][32] next chunk
+  __shared__ uint64_t bar;
+  __shared__ int row_ctr; // rows are handed out dynamically (balances the warps)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int tiles_per_patch = geo.nt(0) * geo.nt(1) * geo.nt(2);
+  const int p = blockIdx.x / tiles_per_patch;
+  const int tt = blockIdx.x - p * tiles_per_patch;
+  const int o0 = (tt % geo.nt(0)) * geo.t(0);
+  const int o1 = ((tt / geo.nt(0)) % geo.nt(1)) * geo.t(1);
+  const int o2 = (tt / (geo.nt(0) * geo.nt(1))) * geo.t(2);
+  float* F = A.flds + p * A.slot_len;
+  // global index of tile node 0
+  const int n0 = o0 - geo.g(0), n1 = o1 - geo.g(1), n2 = o2 - geo.g(2);
+
+  // ---- stage E/B (one TMA), zero J
+  if (tid == 0) {
+    row_ctr = NW;
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, 6u * NODES * sizeof(float));
+    if (XYZ) {
+      tma_load_tile(sEM, &tm, n0 + 2, n1 + 2, n2 + 2, p * 9 + pm::EX, &bar, true);
+    } else {
+      tma_load_tile(sEM, &tm, n1 + 2, n2 + 2, p * 9 + pm::EX, 0, &bar, false);
+    }
+  }
+  for (int idx = tid; idx < 3 * NODES; idx += NW * 32) {
+    sJ[idx] = 0.f;
+  }
+  if (warp == 0) {
+    mbar_wait(&bar, 0);
+  }
+  __syncthreads();
+
+  FldTile<GeoStatic<DIM>> EM{sEM, geo, n0, n1, n2};
+  float4* const myQ = sQ + warp * QC * 2;
+  const uint32_t myP = smem_u32(sP + warp * 64 + lane);
+  int qn = 0; // queued trajectories of this warp (warp-uniform)
+
+  // what this lane deposits when a cell is flushed: its slot of the leaf, scaled
+  const int my_slot = slot_of_lane<NVP>(lane);
+  const bool writer = (my_slot < NM) && ((lane & (NVP == 16 ? 1 : 3)) == 0);
+  const int my_comp = XYZ ? (my_slot >> 2) : (my_slot < 4 ? 0 : (my_slot < 6 ? 1 : 2));
+  const float my_fnq = DEPOSIT == pm::DEPOSIT_SPLIT ? G.pc.fnqs_split[my_comp % 3] : G.pc.fnq_var1[my_comp % 3];
+  const int myJ = my_slot < NM ? leaf_lin<DIM>(my_slot, SY, SZ, NODES) : 0;
+  uint32_t* const cnt32 = reinterpret_cast<uint32_t*>(A.cnt);
+
+  // split + deposit `cnt` queued trajectories (entries [qn - cnt, qn)), one per lane; COUNT:
+  // add each one to the plane of its destination class
+  auto drain = [&](int cnt) {
+    const bool a2 = lane < cnt;
+    Walker<DIM, DEPOSIT> w;
+    float val[NM];
+    int ci[3] = {0, 0, 0};
+    bool more = false;
+    float qw = 0.f;
+    if (a2) {
+      const float4 A0 = myQ[2 * (qn - cnt + lane)], A1 = myQ[2 * (qn - cnt + lane) + 1];
+      pm::Trajectory t;
+      int sc[3], dc[3]; // the indexer's source and destination cells
+      float xn[3];      // pushed position (SAME: read back when needed)
+      if constexpr (SAME) {
+        t.xm[0] = XYZ ? A0.x : 0.f, t.xm[1] = A0.y, t.xm[2] = A0.z;
+        t.xp[0] = XYZ ? A1.x : 0.f, t.xp[1] = A1.y, t.xp[2] = A1.z;
+      } else {
+        xn[0] = A1.x, xn[1] = A1.y, xn[2] = A1.z;
+        const float xo[3] = {A0.x, A0.y, A0.z};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          t.xm[d] = xo[d] * G.pc.dxi[d];
+          t.xp[d] = xn[d] * G.pc.dxi[d];
+          sc[d] = pm::cell_position(G.pc, xo[d], d);
+          dc[d] = pm::cell_position(G.pc, xn[d], d);
+        }
+      }
+      t.v[0] = XYZ ? 0.f : A1.w, t.v[1] = 0.f, t.v[2] = 0.f;
+      qw = A0.w;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        t.lg[d] = pm::fint(t.xm[d]);
+        t.lf[d] = pm::fint(t.xp[d]);
+        if constexpr (SAME) {
+          sc[d] = t.lg[d], dc[d] = t.lf[d];
+        }
+      }
+      if constexpr (COUNT) {
+        const int d0 = dc[0] - sc[0], d1 = dc[1] - sc[1], d2 = dc[2] - sc[2];
+        const bool ok = (unsigned)dc[0] < (unsigned)G.ldims[0] && (unsigned)dc[1] < (unsigned)G.ldims[1] &&
+                        (unsigned)dc[2] < (unsigned)G.ldims[2] && (unsigned)(d0 + 1) <= 2u &&
+                        (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
+        int cls;
+        if (ok) {
+          cls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
+        } else {
+          // patch boundary (or further than one cell): the pushed record decides
+          if constexpr (SAME) {
+            const uint32_t i = (uint32_t)__float_as_int(XYZ ? A1.w : A0.x);
+            const float4 Xr = A.xi4[i];
+            xn[0] = Xr.x, xn[1] = Xr.y, xn[2] = Xr.z;
+          }
+          float uu[3] = {0.f, 0.f, 0.f};
+          int q, c;
+          cls = fs_classify(G, A.tab, p, sc[0], sc[1], sc[2], xn, uu, q, c);
+        }
+        if (cls < FS_PLANES) {
+          const size_t e = (size_t)cls * A.nct + (size_t)p * G.n_cells +
+                           (size_t)((sc[2] * G.ldims[1] + sc[1]) * G.ldims[0] + sc[0]);
+          atomicAdd(cnt32 + (e >> 1), 1u << (16 * (e & 1)));
+        } else if (cls == CLS_BAD) {
+          atomicExch(&A.flags[0], 1u);
+        } else if (cls == CLS_DROP) {
+          atomicAdd(&A.flags[1], 1u);
+        } else if (cls == CLS_REMOTE) {
+          atomicAdd(&A.flags[2], 1u);
+        }
+      }
+      more = w.first(G.pc, t, qw, ci, val);
+      leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+    }
+    while (__any_sync(FULL, more)) {
+      if (more) {
+        more = w.next(G.pc, qw, ci, val);
+        leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+      }
+    }
+    qn -= cnt;
+    __syncwarp();
+  };
+
+  // ---- particle runs: rows of cells along the first non-invariant dim
+  constexpr int N_ROWS = XYZ ? GeoStatic<DIM>::t(1) * GeoStatic<DIM>::t(2) : GeoStatic<DIM>::t(2);
+  constexpr int RUN = GeoStatic<DIM>::t(RD); // cells per row, <= 31
+  const uint32_t* const coff = A.cell_off + (size_t)p * G.n_cells;
+  for (int row = warp; row < N_ROWS;) {
+    int c0, rs1, rs2; // first cell of the row; row coordinates
+    if (XYZ) {
+      const int ry = row % geo.t(1), rz = row / geo.t(1);
+      rs1 = o1 + ry, rs2 = o2 + rz;
+      c0 = (rs2 * G.ldims[1] + rs1) * G.ldims[0] + o0;
+    } else {
+      rs1 = o1, rs2 = o2 + row;
+      c0 = rs2 * G.ldims[1] + o1;
+    }
+    // lane j holds the offset of the row's j-th cell boundary
+    const uint32_t myoff = __ldg(&coff[c0 + min(lane, RUN)]);
+    const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, RUN);
+    // shared J of the row's first cell, as seen by this lane's leaf slot
+    const int jrow = myJ + (rs2 - n2) * SZ + (XYZ ? (rs1 - n1) * SY + (o0 - n0) : (o1 - n1) * SY);
+    if (begin < end) {
+      int cur = 0;                                           // cell of the row the passes are at
+      uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
+      uint32_t n_left = 0;                                   // ... and how many of them left it so far
+      float acc[NM];                                         // this lane's share of the cell's moments
+#pragma unroll
+      for (int n = 0; n < NM; n++) {
+        acc[n] = 0.f;
+      }
+      // warp-sum the moments, turn them into leaf values, add those to the shared J at `at`
+      auto flush_moments = [&](int at) {
+        float v[NVP];
+#pragma unroll
+        for (int n = 0; n < NVP; n++) {
+          v[n] = n < NM ? acc[n] : 0.f;
+        }
+        warp_transpose_reduce<NVP>(v, lane);
+        const float leaf = moments_to_leaf<DIM>(v[0], lane) * my_fnq;
+        if (writer) {
+          atomicAdd(&sJ[at], leaf);
+        }
+#pragma unroll
+        for (int n = 0; n < NM; n++) {
+          acc[n] = 0.f;
+        }
+      };
+      // the next chunk travels global -> shared with cp.async while this one is computed
+      if (begin + lane < end) {
+        cp_async16(myP, A.xi4 + begin + lane);
+        cp_async16(myP + 32 * sizeof(float4), A.pxi4 + begin + lane);
+      }
+      cp_async_commit();
+      uint32_t base = begin;
+      do {
+        const uint32_t i = base + lane;
+        const bool act = i < end;
+        if (qn > QC - 32) {
+          // the queue may not take another chunk: walk it now.  The cell's moments so far are
+          // flushed first (they are additive), so that nothing but the row state is live
+          // across the walk
+          flush_moments(jrow + cur * ROW_STRIDE);
+          drain(min(qn, 32));
+        }
+        cp_async_wait_all();
+        const float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
+        if (i + 32 < end) {
+          cp_async16(myP, A.xi4 + i + 32);
+          cp_async16(myP + 32 * sizeof(float4), A.pxi4 + i + 32);
+        }
+        cp_async_commit();
+        // ---- gather, Boris, move (the reference's arithmetic, pic_math.cuh)
+        bool cross = false;
+        float dx[3] = {0.f, 0.f, 0.f}, xa[3] = {0.f, 0.f, 0.f}; // displacement, centred offset
+        float q = 0.f;                                         // q w of a particle that stayed in its cell
+        pm::Trajectory t;
+        float x[3] = {X.x, X.y, X.z};
+        if (act) {
+          float u[3] = {U.x, U.y, U.z};
+          pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
+          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+          cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
+          if constexpr (!SAME) {
+            // 1/float(dx) and float(dx_inv) may disagree at a cell edge: such a particle is
+            // walked like a crossing one (its leaf is not the run's cell)
+            const float xo[3] = {X.x, X.y, X.z};
+#pragma unroll
+            for (int d = XYZ ? 0 : 1; d < 3; d++) {
+              cross = cross || pm::cell_position(G.pc, xo[d], d) != t.lg[d];
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            dx[d] = t.xp[d] - t.xm[d];
+            xa[d] = __fmaf_rn(.5f, t.xp[d] + t.xm[d], -(float)t.lg[d]);
+          }
+          if (!XYZ) {
+            dx[0] = t.v[0] * G.pc.dt * G.pc.dxi_idx[0];
+          }
+          q = cross ? 0.f : U.w;
+        }
+        // park cell-crossing particles for the split/deposit walk
+        const unsigned cm = __ballot_sync(FULL, cross);
+        if (cm) {
+          if (cross) {
+            const int slot = qn + __popc(cm & lt);
+            const float fi = __int_as_float((int)i);
+            if constexpr (SAME) {
+              // (xm | i, qw), (xp, i | vx)
+              myQ[2 * slot] = make_float4(XYZ ? t.xm[0] : fi, t.xm[1], t.xm[2], U.w);
+              myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], XYZ ? fi : t.v[0]);
+            } else {
+              // (x_old, qw), (x_new, - | vx)
+              myQ[2 * slot] = make_float4(X.x, X.y, X.z, U.w);
+              myQ[2 * slot + 1] = make_float4(x[0], x[1], x[2], XYZ ? 0.f : t.v[0]);
+            }
+          }
+          qn += __popc(cm);
+          __syncwarp();
+        }
+        const float h12 = (1.f / 12.f) * dx[0] * dx[1] * dx[2];
+        // ---- one pass per cell that has particles in this chunk
+        for (;;) {
+          // lanes of this chunk that belong to the cell (warp-uniform mask)
+          const uint32_t hi = min(ce - base, 32u), lo = cb > base ? cb - base : 0u;
+          const unsigned mm = (hi >= 32u ? FULL : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+          const float qe = (mm >> lane) & 1u ? q : 0.f;
+          if (COUNT) {
+            n_left += __popc(cm & mm);
+          }
+          {
+            const float qh = qe * h12;
+            if (XYZ) {
+#pragma unroll
+              for (int d = 0; d < 3; d++) {
+                const float m = qe * dx[d];
+                const float a = xa[(d + 1) % 3], b = xa[(d + 2) % 3];
+                const float ma = m * a;
+                acc[4 * d + 0] += m;
+                acc[4 * d + 1] += ma;
+                acc[4 * d + 2] = __fmaf_rn(m, b, acc[4 * d + 2]);
+                acc[4 * d + 3] = __fmaf_rn(ma, b, acc[4 * d + 3] + qh);
+              }
+            } else {
+              const float m0 = qe * dx[0], m1 = qe * dx[1], m2 = qe * dx[2];
+              const float ma = m0 * xa[1];
+              acc[0] += m0;
+              acc[1] += ma;
+              acc[2] = __fmaf_rn(m0, xa[2], acc[2]);
+              acc[3] = __fmaf_rn(ma, xa[2], acc[3] + qh);
+              acc[4] += m1;
+              acc[5] = __fmaf_rn(m1, xa[2], acc[5]);
+              acc[6] += m2;
+              acc[7] = __fmaf_rn(m2, xa[1], acc[7]);
+            }
+          }
+          if (ce > base + 32) {
+            break; // the cell continues in the next chunk
+          }
+          // ---- the cell is complete: flush its moments as leaf values, count its stayers
+          if (ce > cb) {
+            flush_moments(jrow + cur * ROW_STRIDE);
+            if (COUNT) {
+              const uint32_t pop = ce - cb;
+              if (lane == 0) {
+                const size_t e = (size_t)CLS_CENTER * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur);
+                atomicAdd(cnt32 + (e >> 1), (pop - n_left) << (16 * (e & 1)));
+                if (pop > CNT_MAX) {
+                  atomicExch(&A.flags[0], 1u);
+                }
+              }
+              n_left = 0;
+            }
+          }
+          if (++cur == RUN) {
+            break;
+          }
+          cb = ce;
+          ce = __shfl_sync(FULL, myoff, cur + 1);
+          if (cb >= base + 32) {
+            break; // the next cell starts in the next chunk
+          }
+        }
+        base += 32;
+      } while (base < end);
+    }
+    if (lane == 0) {
+      row = atomicAdd(&row_ctr, 1);
+    }
+    row = __shfl_sync(FULL, row, 0);
+  }
+  while (qn > 0) {
+    drain(min(qn, 32));
+  }
+  __syncthreads();
+
+  // ---- flush the J tile (halo included) with global reductions
+  for (int idx = tid; idx < 3 * NODES; idx += NW * 32) {
+    const float v = sJ[idx];
+    if (v != 0.f) {
+      const int m = idx / NODES;
+      int rem = idx - m * NODES;
+      const int kz = rem / SZ;
+      rem -= kz * SZ;
+      const int ky = rem / SY, kx = rem - ky * SY;
+      const int gi = n0 + kx, gj = n1 + ky, gk = n2 + kz;
+      if (gi < G.ldims[0] + G.ibn[0] && gj < G.ldims[1] + G.ibn[1] && gk < G.ldims[2] + G.ibn[2]) {
+        atomicAdd(F + fld_off(G, m, gi, gj, gk), v);
+      }
+    }
+  }
+}
+
+} // namespace lean
