@@ -120,9 +120,16 @@ def cpu_arm(cells, ppc, n_patches_target, steps, warmup, threads):
     """the reference's CPU 1vb path (oracle port: push_particles_1vb.hxx + psc_sort_impl.hxx
     + bnd_particles_impl.hxx restated in oracle/psc_oracle.c), patches spread over host
     threads the way PSC spreads them over MPI ranks"""
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the oracle's OpenMP loops (boundary
+    # exchange) must see the cores this process may use, whatever the launcher set
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     import oracle_lib as ol
     from gen import thermal_plasma
     from concurrent.futures import ThreadPoolExecutor
+    try:
+        C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL).omp_set_num_threads(int(threads))
+    except OSError:
+        pass
     pz = max(1, n_patches_target // 4)
     og = ol.Grid(gdims=(cells * 2, cells * 2, cells * pz), length=(2. * cells, 2. * cells, 1. * cells * pz),
                  np_=(2, 2, pz), dt=0.75 / np.sqrt(3.), kinds=KINDS, nicell=ppc // 2)
@@ -141,10 +148,31 @@ def cpu_arm(cells, ppc, n_patches_target, steps, warmup, threads):
     spare = [np.zeros_like(prts), np.zeros_like(off)]
     nd = np.zeros(1, dtype=np.uint32)
 
+    # the push + deposit is the reference's own code (oracle/_ref: push_particles_1vb.hxx and
+    # the headers it pulls in, compiled unmodified) whenever that library was built; sort and
+    # boundary exchange are the plain-C restatement either way
+    use_ref = ol.ref_available()
+    if use_ref:
+        R = ol.ref()
+        g = og.g
+        qk = np.array([k[0] for k in og.kinds], dtype=np.float64)
+        mk = np.array([k[1] for k in og.kinds], dtype=np.float64)
+        slot_len = int(np.prod(flds.shape[1:]))
+
+        def push_range(prts, off, p0, p1):
+            fl = flds[p0:p1]
+            rc = R.psc_ref_push_mprts(0, g.deposit, g.gdims, g.length, g.dt, g.fnqs, g.eta, g.n_kinds,
+                                      ol.ptr(qk), ol.ptr(mk), ol.ptr(fl), g.im, g.ib, p1 - p0, ol.ptr(prts),
+                                      ol.ptr(off[p0:p1 + 1]))
+            assert rc == 0
+    else:
+        def push_range(prts, off, p0, p1):
+            L.po_push_mprts_range(G, ol.ptr(flds), ol.ptr(prts), ol.ptr(off), p0, p1)
+
     def one_step(prts, off):
         def work(b):
             L.po_sort_range(G, ol.ptr(prts), ol.ptr(off), None, b[0], b[1])
-            L.po_push_mprts_range(G, ol.ptr(flds), ol.ptr(prts), ol.ptr(off), b[0], b[1])
+            push_range(prts, off, b[0], b[1])
         list(pool.map(work, bounds))
         p2, o2 = spare
         L.po_bnd_particles(G, ol.ptr(prts), ol.ptr(off), ol.ptr(p2), ol.ptr(o2), None, ol.ptr(nd))  # OpenMP over patches
@@ -159,9 +187,12 @@ def cpu_arm(cells, ppc, n_patches_target, steps, warmup, threads):
         prts, off = one_step(prts, off)
     dt = time.perf_counter() - t0
     pool.shutdown()
+    kind = "_ref+port" if use_ref else "port"
     sample = ("%d patches of %d^3 cells x %d ppc = %d particles, %d steps of sort+push+deposit+"
-              "boundary exchange, %d host threads over patches" % (npch, cells, ppc, n, steps, threads))
-    return n * steps / dt, dt / steps * 1e3, sample, threads
+              "boundary exchange, %d host threads over patches; push+deposit = %s" %
+              (npch, cells, ppc, n, steps, threads,
+               "the reference's own headers (oracle/_ref)" if use_ref else "plain-C port"))
+    return n * steps / dt, dt / steps * 1e3, sample, threads, kind
 
 
 def run_reference(args, rank, world):
@@ -170,19 +201,103 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cells, ppc = args.ref_cells, 64
     # ~4 patches per thread keeps a step around a few seconds
-    val, ms, sample, used = cpu_arm(cells, ppc, max(4, 2 * cores), args.steps, min(args.warmup, 1), cores)
+    val, ms, sample, used, kind = cpu_arm(cells, ppc, max(4, 2 * cores), args.steps, min(args.warmup, 1), cores)
     line = {
         "impl": "reference", "metric": "particle-steps/sec (push+deposit+sort)", "value": val,
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "S3D-thermal (SURVEY.md 8d), bounded sample: " + sample},
-        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": used, "kind": "port",
+        "config": {"workload": "S3D-thermal (SURVEY.md 8d), bounded sample: " + sample,
+                   "scope": "all host cores of the box, whatever --gpus says: the CPU arm does not scale with N"},
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": used, "kind": kind,
                          "sample": sample},
         "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- load balancing
+
+def balance_phase(args, rank, world, local_rank, dist, torch):
+    """BASELINE.json configs[3] / north_star "load balancing redistributes patches by particle
+    count": a non-uniform plasma (density bump along z, centred in rank 0's slab) on an even
+    patch split, stepped, rebalanced with psc_b200_balance (Balance_::operator(),
+    psc_balance_impl.hxx:770-1026: load = n_prts + factor_fields * n_cells, recursive bisection
+    of the patch list, whole patches moved GPU to GPU over NCCL), stepped again."""
+    import psc_b200 as pb
+    n, pe = args.balance_cells, 32
+    npd = n // pe
+    gdims, np3 = (n, n, n * world), (npd, npd, npd * world)
+    grid = pb.Grid(gdims=gdims, length=tuple(float(g) for g in gdims), np=np3, dt=0.75 / np.sqrt(3.),
+                   kinds=KINDS, nicell=32, rank=rank, n_ranks=world, device=local_rank)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(pb.Grid.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    grid.nccl_init(bytes(idt.cpu().numpy().tobytes()))
+    # density by patch: 12 + 84 exp(-((z - z0) / w)^2) particles per cell and kind, z0 = middle
+    # of rank 0's slab, w = 0.35 slabs
+    p0, npl = grid.patch_begin(), grid.n_patches()
+    iz = (p0 + np.arange(npl)) // (npd * npd)
+    zc = (iz + .5) * pe
+    ppc = np.round(12 + 84 * np.exp(-((zc - .5 * n) / (.35 * n)) ** 2)).astype(np.int32)
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    mprts.setup_thermal(ppc, list(VTH), seed=99)
+    mflds.fill(pb.HZ, 0.1)
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=True)
+    psc.initialize()
+
+    def gather(v):
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = float(v)
+        dist.all_reduce(t)
+        return [float(x) for x in t.cpu()]
+
+    def timed_steps(k):
+        for _ in range(2):
+            psc.step()
+        grid.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        grid.timer_start()
+        for _ in range(k):
+            psc.step()
+        ms = grid.timer_stop()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / k
+
+    n_before, patches_before = gather(mprts.size()), gather(grid.n_patches())
+    ms_before = timed_steps(5)
+    grid.sync()
+    dist.barrier()
+    t0 = time.perf_counter()
+    changed = grid.balance(1.0)
+    grid.sync()
+    dist.barrier()
+    ms_balance = (time.perf_counter() - t0) * 1e3
+    # the operator types re-attach to the new decomposition (psc_balance_generation_cnt)
+    mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
+    psc = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=True)
+    n_after, patches_after = gather(mprts.size()), gather(grid.n_patches())
+    ms_after = timed_steps(5)
+    n_end = gather(mprts.size())
+    grid.close()
+    tot = sum(n_before)
+    moved = int(sum(abs(a - b) for a, b in zip(patches_before, patches_after)) // 2)
+    return {
+        "workload": "density bump along z on %d^3 cells per GPU, %d^3-cell patches: %d..%d particles per cell; "
+                    "even patch split, 5 timed steps, psc_b200_balance(factor_fields=1), 5 timed steps" %
+                    (n, pe, 2 * 12, 2 * 96),
+        "changed": bool(changed), "particles_total": int(tot), "particles_conserved": int(sum(n_end)) == int(tot),
+        "particles_by_rank_before": [int(x) for x in n_before], "particles_by_rank_after": [int(x) for x in n_after],
+        "patches_by_rank_before": [int(x) for x in patches_before], "patches_by_rank_after": [int(x) for x in patches_after],
+        "patches_moved": moved,
+        "imbalance_before": max(n_before) / (tot / world), "imbalance_after": max(n_after) / (tot / world),
+        "ms_per_step_before": ms_before, "ms_per_step_after": ms_after, "ms_balance": ms_balance,
+        "particle_steps_per_s_before": tot / (ms_before * 1e-3), "particle_steps_per_s_after": tot / (ms_after * 1e-3),
+    }
 
 
 # ---------------------------------------------------------------------------- GPU arm
@@ -198,6 +313,15 @@ def run_b200(args, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- multi-rank parity, ahead of the timed region: small grids through the same NCCL
+    # halo / migration / balance paths, compared with the CPU oracle run on the whole domain
+    parity = None
+    if world > 1 and not args.no_parity:
+        import multi_gpu_check as mgc
+        p_ok, p_cases = mgc.bench_parity_cases(rank, world, local_rank)
+        parity = {"pass": bool(p_ok), "cases": len(p_cases), "detail": p_cases,
+                  "what": "tests/multi_gpu_check.py cases vs the CPU oracle on the whole domain (rank 0 gathers)"}
 
     n, ppc, pe = args.cells, args.ppc, args.patch
     npd = n // pe
@@ -227,6 +351,11 @@ def run_b200(args, rank, world, local_rank):
         grid.set_option("threads", args.threads)
     if args.min_blocks:
         grid.set_option("min_blocks", args.min_blocks)
+    extra_opts = {}
+    for kv in args.opt:
+        k, v = kv.split("=")
+        extra_opts[k] = float(v)
+        grid.set_option(k, float(v))
     mprts, mflds = pb.Mparticles(grid), pb.MfieldsState(grid)
     mprts.setup_thermal(ppc // 2, list(VTH), seed=1234)
     mflds.fill(pb.HX if yz else pb.HZ, 0.1)
@@ -312,13 +441,24 @@ def run_b200(args, rank, world, local_rank):
                "what": "per step: upload E,B (6 comps, all patches) from pinned host memory, "
                        "psc_b200_step, download J (3 comps) + energies"}
 
-    if rank != 0:
+    grid_closed = False
+    balance = None
+    if world > 1 and not args.no_balance:
+        # (after the timed region; the headline context is released first: both do not fit)
         grid.close()
+        grid_closed = True
+        try:
+            balance = balance_phase(args, rank, world, local_rank, dist, torch)
+        except Exception as e:  # reported, never fatal for the headline line
+            balance = {"error": str(e)[:300]}
+    if rank != 0:
+        if not grid_closed:
+            grid.close()
         return
     peak, peak_src = measured_peak()
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                for k, v in prof.items()}
-    push_key = next((k for k in ("push_gap", "push_tiled_tma", "push_tiled", "push_general") if k in prof), None)
+    push_key = next((k for k in ("push_lean", "push_gap", "push_tiled_tma", "push_tiled", "push_general") if k in prof), None)
     roofline = None
     if push_key:
         t_push = prof[push_key][0] / max(1, prof[push_key][1]) * 1e-3
@@ -342,8 +482,8 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if not args.no_cpu:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        v, _, sample, used = cpu_arm(32, 64, max(4, 2 * cores), 2, 1, cores)
-        cpu = {"value": v, "unit": "particle-steps/s", "cores": used, "kind": "port", "sample": sample}
+        v, _, sample, used, kind = cpu_arm(32, 64, max(4, 2 * cores), 2, 1, cores)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": used, "kind": kind, "sample": sample}
     line = {
         "metric": "particle-steps/sec (push+deposit+sort)", "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -357,12 +497,18 @@ def run_b200(args, rank, world, local_rank):
                    "particles_per_gpu": n_prts, "cells_per_gpu": n_cells_gpu, "parallelism": "slabs along z, %d rank(s)" % world,
                    "l2": "working set (%.1f GB of particles per GPU) >> 126 MB L2, no flush needed" % (n_prts * 32 / 1e9),
                    "fma": args.fma, "options": {"tiled": args.tiled, "tma": args.tma,
-                                                "fused_sort": args.fused_sort, "gapped": args.gapped, "overlap": args.overlap}},
+                                                "fused_sort": args.fused_sort, "gapped": args.gapped, "overlap": args.overlap,
+                                                **extra_opts}},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "kernels": kernels,
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if balance is not None:
+        line["balance"] = balance
     print(json.dumps(line), flush=True)
-    grid.close()
+    if not grid_closed:
+        grid.close()
 
 
 def main():
@@ -391,6 +537,14 @@ def main():
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
     ap.add_argument("--ref-cells", dest="ref_cells", type=int, default=32,
                     help="--impl reference: cells per patch edge of the bounded sample")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="psc_b200_set_option(NAME, VALUE), repeatable (e.g. --opt lean=0)")
+    ap.add_argument("--no-balance", dest="no_balance", action="store_true",
+                    help="world > 1: skip the load-balancing measurement that runs after the timed region")
+    ap.add_argument("--balance-cells", dest="balance_cells", type=int, default=128,
+                    help="cells per GPU edge of the load-balancing workload")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true",
+                    help="world > 1: skip the multi-rank oracle comparison that runs ahead of the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -136,6 +136,10 @@ int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts_aos32, uint32_t* off);
  * ppc particles per cell for each kind, u ~ N(0, vth[kind]), w = 1, sorted by cell */
 int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth,
                                  uint64_t seed);
+/* ... with a density profile by patch: local patch p gets ppc_by_patch[p] particles per cell
+ * and kind (the non-uniform state the load-balancing measurement of bench.py starts from) */
+int psc_b200_mprts_setup_thermal_by_patch(psc_b200_ctx* ctx, const int* ppc_by_patch,
+                                          const double* vth, uint64_t seed);
 
 /* ---- MfieldsState / Mfields (src/include/fields3d.hxx:321-464) ---- */
 /* field 0 is the 9-component state; further scratch fields via _create */

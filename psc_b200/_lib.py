@@ -78,6 +78,7 @@ def load():
         "psc_b200_mprts_size_by_patch": [CTX, P],
         "psc_b200_mprts_get": [CTX, P, P],
         "psc_b200_mprts_setup_thermal": [CTX, C.c_int, P, C.c_uint64],
+        "psc_b200_mprts_setup_thermal_by_patch": [CTX, P, P, C.c_uint64],
         "psc_b200_mflds_create": [CTX, C.c_int, C.POINTER(C.c_int)],
         "psc_b200_mflds_upload": [CTX, C.c_int, C.c_int, C.c_int, P],
         "psc_b200_mflds_download": [CTX, C.c_int, C.c_int, C.c_int, P],

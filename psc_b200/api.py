@@ -187,7 +187,12 @@ class Mparticles:
     def setup_thermal(self, ppc, vth, seed=0):
         v = np.ascontiguousarray(vth, dtype=np.float64)
         assert len(v) == len(self.grid_.kinds)
-        check(self.grid_.lib.psc_b200_mprts_setup_thermal(self.grid_.ctx, ppc, _ptr(v), seed))
+        if np.ndim(ppc) == 0:
+            check(self.grid_.lib.psc_b200_mprts_setup_thermal(self.grid_.ctx, int(ppc), _ptr(v), seed))
+        else:  # one value per local patch
+            pp = np.ascontiguousarray(ppc, dtype=np.int32)
+            assert len(pp) == self.n_patches()
+            check(self.grid_.lib.psc_b200_mprts_setup_thermal_by_patch(self.grid_.ctx, _ptr(pp), _ptr(v), seed))
 
 
 class Mfields:

@@ -575,7 +575,14 @@ int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts, uint32_t* off)
 
 int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth, uint64_t seed)
 {
-  GUARD(c->gapped = false; return prts_setup_thermal(c, ppc, vth, seed);)
+  GUARD(c->gapped = false; return prts_setup_thermal(c, ppc, nullptr, vth, seed);)
+}
+
+int psc_b200_mprts_setup_thermal_by_patch(psc_b200_ctx* ctx, const int* ppc_by_patch, const double* vth,
+                                          uint64_t seed)
+{
+  GUARD(c->gapped = false; if (!ppc_by_patch) { return fail("null ppc_by_patch"); }
+        return prts_setup_thermal(c, 0, ppc_by_patch, vth, seed);)
 }
 
 int psc_b200_mflds_create(psc_b200_ctx* ctx, int n_comps, int* field_id)

@@ -209,7 +209,7 @@ int prts_reserve(Ctx* c, size_t n);
 int prts_set(Ctx* c, const void* aos, const uint32_t* n_by_patch);
 int prts_inject(Ctx* c, const void* aos, const uint32_t* n_by_patch);
 int prts_get(Ctx* c, void* aos, uint32_t* off);
-int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed);
+int prts_setup_thermal(Ctx* c, int ppc, const int* ppc_by_patch, const double* vth, uint64_t seed);
 int prts_upload_off(Ctx* c);
 int prts_energies(Ctx* c, double out2[2]);
 int selftest_math(Ctx* c, uint64_t* n_bad);

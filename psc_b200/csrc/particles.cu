@@ -88,17 +88,26 @@ struct ThermalPrm
   uint64_t id0; // global id of this rank's first particle
 };
 
-__global__ void k_setup_thermal(GridDev G, ThermalPrm T, uint32_t n, float4* __restrict__ xi4,
+// ppc_by_patch == nullptr: T.ppc particles per cell and kind everywhere; else patch p holds
+// ppc_by_patch[p] per cell and kind and starts at off[p] (a density profile by patch)
+__global__ void k_setup_thermal(GridDev G, ThermalPrm T, uint32_t n, const int* __restrict__ ppc_by_patch,
+                                const uint32_t* __restrict__ off, float4* __restrict__ xi4,
                                 float4* __restrict__ pxi4)
 {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) {
     return;
   }
-  uint32_t per_cell = T.ppc * T.n_kinds;
-  uint32_t cell_g = i / per_cell; // patch * n_cells + cell
-  uint32_t r = i - cell_g * per_cell;
-  int kind = r / T.ppc;
+  uint32_t ppc = T.ppc, il = i;
+  if (ppc_by_patch) {
+    const int p = patch_of(off, G.n_patches, i);
+    ppc = ppc_by_patch[p];
+    il = i - off[p];
+  }
+  uint32_t per_cell = ppc * T.n_kinds;
+  uint32_t cell_g = il / per_cell; // (patch * n_cells +) cell
+  uint32_t r = il - cell_g * per_cell;
+  int kind = r / ppc;
   uint32_t cell = cell_g % G.n_cells;
   int c[3];
   c[0] = cell % G.ldims[0];
@@ -133,6 +142,19 @@ __global__ void k_iota_cell_off(uint32_t n_cells_total, uint32_t per_cell, uint3
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= n_cells_total) {
     cell_off[i] = i * per_cell;
+  }
+}
+
+__global__ void k_profile_cell_off(uint32_t n_cells_total, uint32_t n_cells, int n_kinds,
+                                   const int* __restrict__ ppc_by_patch, const uint32_t* __restrict__ off,
+                                   uint32_t* cell_off)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cells_total) {
+    const uint32_t p = i / n_cells;
+    cell_off[i] = off[p] + (i - p * n_cells) * (uint32_t)(ppc_by_patch[p] * n_kinds);
+  } else if (i == n_cells_total) {
+    cell_off[i] = off[n_cells_total / n_cells];
   }
 }
 
@@ -310,13 +332,26 @@ int prts_get(Ctx* c, void* aos, uint32_t* off)
   return check_launch(c, "prts_get");
 }
 
-int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed)
+int prts_setup_thermal(Ctx* c, int ppc, const int* ppc_by_patch, const double* vth, uint64_t seed)
 {
   const GridHost& g = c->g;
-  size_t per_patch = (size_t)g.n_cells * ppc * g.desc.n_kinds;
-  size_t n = per_patch * g.n_patches;
-  if (n >= (size_t(1) << 32)) {
-    return fail("setup_thermal: more than 2^32 particles on one rank");
+  std::vector<uint32_t> off(g.n_patches + 1, 0);
+  size_t n = 0, id0 = 0;
+  for (int p = 0; p < g.n_patches; p++) {
+    const int pp = ppc_by_patch ? ppc_by_patch[p] : ppc;
+    if (pp < 0) {
+      return fail("setup_thermal: negative particle count");
+    }
+    n += (size_t)g.n_cells * pp * g.desc.n_kinds;
+    if (n >= (size_t(1) << 32)) {
+      return fail("setup_thermal: more than 2^32 particles on one rank");
+    }
+    off[p + 1] = (uint32_t)n;
+  }
+  if (!ppc_by_patch) {
+    id0 = (size_t)g.patch_begin * g.n_cells * ppc * g.desc.n_kinds;
+  } else {
+    id0 = (size_t)g.patch_begin << 32; // (distinct streams per rank; ids need not be dense)
   }
   PSC_TRY(prts_reserve(c, n));
   ThermalPrm T{};
@@ -330,24 +365,38 @@ int prts_setup_thermal(Ctx* c, int ppc, const double* vth, uint64_t seed)
     T.dx[d] = (float)g.dx[d];
   }
   T.seed = seed;
-  T.id0 = (uint64_t)g.patch_begin * per_patch;
-  {
-    KernelScope ks(c, "setup_thermal");
-    k_setup_thermal<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, T, (uint32_t)n, c->xi(),
-                                                          c->pxi());
-    uint32_t nct = (uint32_t)g.n_cells * g.n_patches;
-    k_iota_cell_off<<<div_up(nct + 1, 256), 256, 0, c->stream>>>(
-      nct, (uint32_t)(ppc * g.desc.n_kinds), c->d_cell_off);
-  }
-  c->n_launches += 2;
-  for (int p = 0; p <= g.n_patches; p++) {
-    c->h_off[p] = (uint32_t)(p * per_patch);
-  }
+  T.id0 = id0;
+  c->h_off = off;
   c->n_prts = (uint32_t)n;
+  PSC_TRY(prts_upload_off(c));
+  const int* d_ppc = nullptr;
+  if (ppc_by_patch) {
+    PSC_TRY(c->scr[0].reserve(g.n_patches * sizeof(int)));
+    PSC_CUDA_TRY(cudaMemcpyAsync(c->scr[0].p, ppc_by_patch, g.n_patches * sizeof(int), cudaMemcpyHostToDevice,
+                                 c->stream));
+    d_ppc = c->scr[0].as<int>();
+  }
+  if (n) {
+    KernelScope ks(c, "setup_thermal");
+    k_setup_thermal<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, T, (uint32_t)n, d_ppc, c->d_off, c->xi(),
+                                                          c->pxi());
+    c->n_launches++;
+  }
+  {
+    uint32_t nct = (uint32_t)g.n_cells * g.n_patches;
+    if (ppc_by_patch) {
+      k_profile_cell_off<<<div_up(nct + 1, 256), 256, 0, c->stream>>>(nct, (uint32_t)g.n_cells, g.desc.n_kinds,
+                                                                      d_ppc, c->d_off, c->d_cell_off);
+    } else {
+      k_iota_cell_off<<<div_up(nct + 1, 256), 256, 0, c->stream>>>(nct, (uint32_t)(ppc * g.desc.n_kinds),
+                                                                   c->d_cell_off);
+    }
+    c->n_launches++;
+  }
   c->sorted = true;
   c->pushed_from_sorted = false;
-  PSC_TRY(check_launch(c, "setup_thermal"));
-  return prts_upload_off(c);
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream)); // (ppc_by_patch is the caller's)
+  return check_launch(c, "setup_thermal");
 }
 
 // every float in [1, 2^80): the guard-free sequences of pic_math.cuh against the

@@ -1019,20 +1019,39 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, const Push
   const GridDev& G = c->gd;
   constexpr bool XYZ = DIM == pm::DIM_XYZ;
   const int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
+  // particles per lane.  2 = the update on the packed FP32 pipe (FADD2 / FFMA2): 18 % fewer
+  // warp instructions, but 128 registers => 16 warps per SM instead of 24, and the kernel
+  // loses more to latency than it gains in issue slots (S3D: 18.9 ms against 17.7 ms,
+  // DESIGN.md 3.1): opt-in.  The FMA build always takes W = 1 (ptxas contracts the packed
+  // products on its own terms, which leaves the 4-ULP contract).
+#ifdef PM_FAST_MATH
+  const int W = 1;
+#else
+  const int W = c->opt_lean >= 2 ? 2 : 1;
+#endif
   const size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
-                            (size_t)lean::NW * (lean::QC * 2 + 64) * sizeof(float4);
+                            (size_t)(W == 1 ? lean::n_warps<1>() : lean::n_warps<2>()) *
+                              ((W == 1 ? lean::qcap<1>() : lean::qcap<2>()) * 2 + 64 * W) * sizeof(float4);
   TensorMap128 tm128;
   const int box[4] = {XYZ ? geo.f(0) : geo.f(1), XYZ ? geo.f(1) : geo.f(2), XYZ ? geo.f(2) : 6, 6};
   PSC_TRY(field_tile_tensor_map(c, 0, XYZ ? 4 : 3, box, &tm128));
   CUtensorMap tm;
   static_assert(sizeof(tm) == sizeof(tm128), "");
   memcpy(&tm, &tm128, sizeof(tm));
-#define PSC_LEAN(CN, SM)                                                                          \
+#define PSC_LEAN_W(CN, SM, WW)                                                                    \
   do {                                                                                            \
-    auto kern = lean::k_push_lean<DIM, DEPOSIT, CN, SM>;                                          \
+    auto kern = lean::k_push_lean<DIM, DEPOSIT, CN, SM, WW>;                                      \
     PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                       (int)smem_bytes));                                          \
-    kern<<<tiles, lean::NW * 32, smem_bytes, c->stream>>>(tm, G, geo, A);                         \
+    kern<<<tiles, lean::n_warps<WW>() * 32, smem_bytes, c->stream>>>(tm, G, geo, A);              \
+  } while (0)
+#define PSC_LEAN(CN, SM)                                                                          \
+  do {                                                                                            \
+    if (W == 1) {                                                                                 \
+      PSC_LEAN_W(CN, SM, 1);                                                                      \
+    } else {                                                                                      \
+      PSC_LEAN_W(CN, SM, 2);                                                                      \
+    }                                                                                             \
   } while (0)
   if (count) {
     // the planes are added to (leavers one by one, stayers once per cell)
@@ -1049,6 +1068,7 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, const Push
       PSC_LEAN(false, false);
     }
   }
+#undef PSC_LEAN_W
 #undef PSC_LEAN
   return 0;
 }

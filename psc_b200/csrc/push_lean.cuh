@@ -32,8 +32,36 @@
 namespace lean
 {
 
-constexpr int NW = 8;   // warps per CTA
-constexpr int QC = 56;  // queue entries per warp
+// warps per CTA: 8 x 3 CTAs per SM at 80 registers (W = 1), 12 x 2 CTAs at 85 (W = 2)
+template <int W>
+__host__ __device__ constexpr int n_warps()
+{
+#ifdef LEAN_NW2
+  return W == 1 ? 8 : LEAN_NW2;
+#else
+  return W == 1 ? 8 : 12;
+#endif
+}
+// queue entries per warp: a chunk (32 W particles) must always fit behind what a walk leaves
+template <int W>
+__host__ __device__ constexpr int qcap()
+{
+  return W == 1 ? 56 : 96;
+}
+
+// E/B tile accessor for two particles per lane
+template <typename GEO>
+struct FldTile2
+{
+  const float* s; // EM tile, component-major; s points at node (n0, n1, n2)
+  const GEO& geo;
+  int n0, n1, n2;
+  __device__ __forceinline__ pm::f2 operator()(int m, pm::i2 i, pm::i2 j, pm::i2 k) const
+  {
+    return pm::mk2(s[(m - pm::EX) * geo.sm() + (k.x - n2) * geo.sz() + (j.x - n1) * geo.sy() + (i.x - n0)],
+                   s[(m - pm::EX) * geo.sm() + (k.y - n2) * geo.sz() + (j.y - n1) * geo.sy() + (i.y - n0)]);
+  }
+};
 
 __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
                                               uint64_t* bar, bool four_d)
@@ -87,10 +115,13 @@ __device__ __forceinline__ float moments_to_leaf(float v, int lane)
   }
 }
 
-template <int DIM, int DEPOSIT, bool COUNT, bool SAME>
-__global__ void __launch_bounds__(NW * 32, 3)
+// W = particles per lane: 1, or 2 with the update on the packed FP32 pipe (pic_math.cuh f2)
+template <int DIM, int DEPOSIT, bool COUNT, bool SAME, int W>
+__global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
   k_push_lean(const __grid_constant__ CUtensorMap tm, GridDev G, GeoStatic<DIM> geo, PushArgs A)
 {
+  constexpr int QC = qcap<W>();
+  constexpr int NW = n_warps<W>();
   constexpr bool XYZ = DIM == pm::DIM_XYZ;
   constexpr int NM = XYZ ? 12 : 8;   // moments per cell = leaf values per cell
   constexpr int NVP = XYZ ? 16 : 8;  // padded to the butterfly width
@@ -102,7 +133,7 @@ __global__ void __launch_bounds__(NW * 32, 3)
   float* sEM = smem;             // [6][f2][f1][f0]
   float* sJ = smem + 6 * NODES;  // [3][f2][f1][f0]
   float4* sQ = reinterpret_cast<float4*>(smem + ((9 * NODES + 3) & ~3)); // [NW][QC][2]
-  float4* sP = sQ + NW * QC * 2;                                         // [NW][2][32] next chunk
+  float4* sP = sQ + NW * QC * 2;                                         // [NW][2][32 W] next chunk
   __shared__ uint64_t bar;
   __shared__ int row_ctr; // rows are handed out dynamically (balances the warps)
 
@@ -143,7 +174,7 @@ __global__ void __launch_bounds__(NW * 32, 3)
 
   FldTile<GeoStatic<DIM>> EM{sEM, geo, n0, n1, n2};
   float4* const myQ = sQ + warp * QC * 2;
-  const uint32_t myP = smem_u32(sP + warp * 64 + lane);
+  const uint32_t myP = smem_u32(sP + warp * 64 * W + lane);
   int qn = 0; // queued trajectories of this warp (warp-uniform)
 
   // what this lane deposits when a cell is flushed: its slot of the leaf, scaled
@@ -153,6 +184,7 @@ __global__ void __launch_bounds__(NW * 32, 3)
   const float my_fnq = DEPOSIT == pm::DEPOSIT_SPLIT ? G.pc.fnqs_split[my_comp % 3] : G.pc.fnq_var1[my_comp % 3];
   const int myJ = my_slot < NM ? leaf_lin<DIM>(my_slot, SY, SZ, NODES) : 0;
   uint32_t* const cnt32 = reinterpret_cast<uint32_t*>(A.cnt);
+  const size_t cen0 = (size_t)CLS_CENTER * A.nct + (size_t)p * G.n_cells; // CENTER plane, this patch
 
   // split + deposit `cnt` queued trajectories (entries [qn - cnt, qn)), one per lane; COUNT:
   // add each one to the plane of its destination class
@@ -255,10 +287,11 @@ __global__ void __launch_bounds__(NW * 32, 3)
     const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, RUN);
     // shared J of the row's first cell, as seen by this lane's leaf slot
     const int jrow = myJ + (rs2 - n2) * SZ + (XYZ ? (rs1 - n1) * SY + (o0 - n0) : (o1 - n1) * SY);
+    if constexpr (W == 1) {
     if (begin < end) {
       int cur = 0;                                           // cell of the row the passes are at
       uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
-      uint32_t n_left = 0;                                   // ... and how many of them left it so far
+      uint32_t n_left = 0;                                   // ... and whether this lane's particles left it (summed at the flush)
       float acc[NM];                                         // this lane's share of the cell's moments
 #pragma unroll
       for (int n = 0; n < NM; n++) {
@@ -358,12 +391,12 @@ __global__ void __launch_bounds__(NW * 32, 3)
         const float h12 = (1.f / 12.f) * dx[0] * dx[1] * dx[2];
         // ---- one pass per cell that has particles in this chunk
         for (;;) {
-          // lanes of this chunk that belong to the cell (warp-uniform mask)
+          // lanes [lo, hi) of this chunk belong to the cell (warp-uniform bounds)
           const uint32_t hi = min(ce - base, 32u), lo = cb > base ? cb - base : 0u;
-          const unsigned mm = (hi >= 32u ? FULL : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-          const float qe = (mm >> lane) & 1u ? q : 0.f;
+          const bool mine = (uint32_t)lane - lo < hi - lo;
+          const float qe = mine ? q : 0.f;
           if (COUNT) {
-            n_left += __popc(cm & mm);
+            n_left += mine && cross;
           }
           {
             const float qh = qe * h12;
@@ -398,10 +431,10 @@ __global__ void __launch_bounds__(NW * 32, 3)
           if (ce > cb) {
             flush_moments(jrow + cur * ROW_STRIDE);
             if (COUNT) {
-              const uint32_t pop = ce - cb;
+              const uint32_t pop = ce - cb, left = __reduce_add_sync(FULL, n_left);
               if (lane == 0) {
-                const size_t e = (size_t)CLS_CENTER * A.nct + (size_t)p * G.n_cells + (size_t)(c0 + cur);
-                atomicAdd(cnt32 + (e >> 1), (pop - n_left) << (16 * (e & 1)));
+                const size_t e = cen0 + (size_t)(c0 + cur);
+                atomicAdd(cnt32 + (e >> 1), (pop - left) << (16 * (e & 1)));
                 if (pop > CNT_MAX) {
                   atomicExch(&A.flags[0], 1u);
                 }
@@ -419,6 +452,200 @@ __global__ void __launch_bounds__(NW * 32, 3)
           }
         }
         base += 32;
+      } while (base < end);
+    }
+    } else if (begin < end) {
+      // ---- two particles per lane: records base + lane (A) and base + 32 + lane (B)
+      using pm::f2;
+      using pm::i2;
+      using pm::mk2;
+      FldTile2<GeoStatic<DIM>> EM2{sEM, geo, n0, n1, n2};
+      int cur = 0;
+      uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
+      uint32_t n_left = 0;
+      f2 acc[NM]; // .x: particle A's share of the cell's moments, .y: particle B's
+#pragma unroll
+      for (int n = 0; n < NM; n++) {
+        acc[n] = mk2(0.f, 0.f);
+      }
+      auto flush_moments = [&](int at) {
+        float v[NVP];
+#pragma unroll
+        for (int n = 0; n < NVP; n++) {
+          v[n] = n < NM ? acc[n].v.x + acc[n].v.y : 0.f;
+        }
+        warp_transpose_reduce<NVP>(v, lane);
+        const float leaf = moments_to_leaf<DIM>(v[0], lane) * my_fnq;
+        if (writer) {
+          atomicAdd(&sJ[at], leaf);
+        }
+#pragma unroll
+        for (int n = 0; n < NM; n++) {
+          acc[n] = mk2(0.f, 0.f);
+        }
+      };
+      // staging: x[0..63], p[0..63]; every lane copies and reads its own four slots
+      auto prefetch = [&](uint32_t ia) {
+        if (ia < end) {
+          cp_async16(myP, A.xi4 + ia);
+          cp_async16(myP + 64 * sizeof(float4), A.pxi4 + ia);
+        }
+        if (ia + 32 < end) {
+          cp_async16(myP + 32 * sizeof(float4), A.xi4 + ia + 32);
+          cp_async16(myP + 96 * sizeof(float4), A.pxi4 + ia + 32);
+        }
+        cp_async_commit();
+      };
+      prefetch(begin + lane);
+      uint32_t base = begin;
+      do {
+        const uint32_t ia = base + lane, ib = ia + 32;
+        const bool act_a = ia < end, act_b = ib < end;
+        while (qn > QC - 64) {
+          flush_moments(jrow + cur * ROW_STRIDE);
+          drain(min(qn, 32));
+        }
+        cp_async_wait_all();
+        const float4 XA = lds128(myP), UA = lds128(myP + 64 * sizeof(float4));
+        float4 XB = lds128(myP + 32 * sizeof(float4)), UB = lds128(myP + 96 * sizeof(float4));
+        prefetch(ia + 64);
+        bool cross_a = false, cross_b = false;
+        f2 dx[3], xa[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          dx[d] = xa[d] = mk2(0.f, 0.f);
+        }
+        f2 q = mk2(0.f, 0.f);
+        pm::TrajectoryT<f2> t;
+        f2 x[3];
+        if (act_a) {
+          if (!act_b) {
+            XB = XA, UB = UA; // (computed, never stored or deposited)
+          }
+          x[0] = mk2(XA.x, XB.x), x[1] = mk2(XA.y, XB.y), x[2] = mk2(XA.z, XB.z);
+          f2 u[3] = {mk2(UA.x, UB.x), mk2(UA.y, UB.y), mk2(UA.z, UB.z)};
+          pm::advance<DIM>(G.pc, EM2, x, u, i2{__float_as_int(XA.w), __float_as_int(XB.w)}, t);
+          A.xi4[ia] = make_float4(x[0].v.x, x[1].v.x, x[2].v.x, XA.w);
+          A.pxi4[ia] = make_float4(u[0].v.x, u[1].v.x, u[2].v.x, UA.w);
+          if (act_b) {
+            A.xi4[ib] = make_float4(x[0].v.y, x[1].v.y, x[2].v.y, XB.w);
+            A.pxi4[ib] = make_float4(u[0].v.y, u[1].v.y, u[2].v.y, UB.w);
+          }
+          cross_a = (XYZ && t.lf[0].x != t.lg[0].x) || t.lf[1].x != t.lg[1].x || t.lf[2].x != t.lg[2].x;
+          cross_b = (XYZ && t.lf[0].y != t.lg[0].y) || t.lf[1].y != t.lg[1].y || t.lf[2].y != t.lg[2].y;
+          if constexpr (!SAME) {
+            const float xoa[3] = {XA.x, XA.y, XA.z}, xob[3] = {XB.x, XB.y, XB.z};
+#pragma unroll
+            for (int d = XYZ ? 0 : 1; d < 3; d++) {
+              cross_a = cross_a || pm::cell_position(G.pc, xoa[d], d) != t.lg[d].x;
+              cross_b = cross_b || pm::cell_position(G.pc, xob[d], d) != t.lg[d].y;
+            }
+          }
+          cross_b = cross_b && act_b;
+          // (J is compared at 1e-5: contraction is welcome from here on)
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            dx[d] = t.xp[d] - t.xm[d];
+            xa[d] = pm::fma2(pm::bc2(.5f), t.xp[d] + t.xm[d], -pm::to_real(t.lg[d]));
+          }
+          if (!XYZ) {
+            dx[0] = f2{__fmul2_rn(t.v[0].v, make_float2(G.pc.dt * G.pc.dxi_idx[0], G.pc.dt * G.pc.dxi_idx[0]))};
+          }
+          q = mk2(cross_a ? 0.f : UA.w, (cross_b || !act_b) ? 0.f : UB.w);
+        }
+        // park cell-crossing particles for the split/deposit walk
+        const unsigned cma = __ballot_sync(FULL, cross_a), cmb = __ballot_sync(FULL, cross_b);
+        if (cma | cmb) {
+          if (cross_a) {
+            const int slot = qn + __popc(cma & lt);
+            const float fi = __int_as_float((int)ia);
+            if constexpr (SAME) {
+              myQ[2 * slot] = make_float4(XYZ ? t.xm[0].v.x : fi, t.xm[1].v.x, t.xm[2].v.x, UA.w);
+              myQ[2 * slot + 1] = make_float4(t.xp[0].v.x, t.xp[1].v.x, t.xp[2].v.x, XYZ ? fi : t.v[0].v.x);
+            } else {
+              myQ[2 * slot] = make_float4(XA.x, XA.y, XA.z, UA.w);
+              myQ[2 * slot + 1] = make_float4(x[0].v.x, x[1].v.x, x[2].v.x, XYZ ? 0.f : t.v[0].v.x);
+            }
+          }
+          if (cross_b) {
+            const int slot = qn + __popc(cma) + __popc(cmb & lt);
+            const float fi = __int_as_float((int)ib);
+            if constexpr (SAME) {
+              myQ[2 * slot] = make_float4(XYZ ? t.xm[0].v.y : fi, t.xm[1].v.y, t.xm[2].v.y, UB.w);
+              myQ[2 * slot + 1] = make_float4(t.xp[0].v.y, t.xp[1].v.y, t.xp[2].v.y, XYZ ? fi : t.v[0].v.y);
+            } else {
+              myQ[2 * slot] = make_float4(XB.x, XB.y, XB.z, UB.w);
+              myQ[2 * slot + 1] = make_float4(x[0].v.y, x[1].v.y, x[2].v.y, XYZ ? 0.f : t.v[0].v.y);
+            }
+          }
+          qn += __popc(cma) + __popc(cmb);
+          __syncwarp();
+        }
+        const f2 h12 = f2{__fmul2_rn(__fmul2_rn(__fmul2_rn(dx[0].v, make_float2(1.f / 12.f, 1.f / 12.f)), dx[1].v), dx[2].v)};
+        // ---- one pass per cell that has particles in this chunk
+        for (;;) {
+          // lanes [lo, hi) of each half belong to the cell (warp-uniform bounds)
+          const uint32_t rb = cb > base ? cb - base : 0u, re = ce - base; // cell range relative to the chunk
+          const uint32_t lo_a = min(rb, 32u), hi_a = min(re, 32u);
+          const uint32_t lo_b = rb > 32u ? min(rb - 32u, 32u) : 0u, hi_b = re > 32u ? min(re - 32u, 32u) : 0u;
+          const bool mine_a = (uint32_t)lane - lo_a < hi_a - lo_a, mine_b = (uint32_t)lane - lo_b < hi_b - lo_b;
+          const f2 qe = mk2(mine_a ? q.v.x : 0.f, mine_b ? q.v.y : 0.f);
+          if (COUNT) {
+            n_left += (mine_a && cross_a) + (mine_b && cross_b);
+          }
+          {
+            const float2 qh = __fmul2_rn(qe.v, h12.v);
+            if (XYZ) {
+#pragma unroll
+              for (int d = 0; d < 3; d++) {
+                const float2 m = __fmul2_rn(qe.v, dx[d].v);
+                const float2 a = xa[(d + 1) % 3].v, b = xa[(d + 2) % 3].v;
+                const float2 ma = __fmul2_rn(m, a);
+                acc[4 * d + 0].v = __fadd2_rn(acc[4 * d + 0].v, m);
+                acc[4 * d + 1].v = __fadd2_rn(acc[4 * d + 1].v, ma);
+                acc[4 * d + 2].v = __ffma2_rn(m, b, acc[4 * d + 2].v);
+                acc[4 * d + 3].v = __ffma2_rn(ma, b, __fadd2_rn(acc[4 * d + 3].v, qh));
+              }
+            } else {
+              const float2 m0 = __fmul2_rn(qe.v, dx[0].v), m1 = __fmul2_rn(qe.v, dx[1].v), m2 = __fmul2_rn(qe.v, dx[2].v);
+              const float2 ma = __fmul2_rn(m0, xa[1].v);
+              acc[0].v = __fadd2_rn(acc[0].v, m0);
+              acc[1].v = __fadd2_rn(acc[1].v, ma);
+              acc[2].v = __ffma2_rn(m0, xa[2].v, acc[2].v);
+              acc[3].v = __ffma2_rn(ma, xa[2].v, __fadd2_rn(acc[3].v, qh));
+              acc[4].v = __fadd2_rn(acc[4].v, m1);
+              acc[5].v = __ffma2_rn(m1, xa[2].v, acc[5].v);
+              acc[6].v = __fadd2_rn(acc[6].v, m2);
+              acc[7].v = __ffma2_rn(m2, xa[1].v, acc[7].v);
+            }
+          }
+          if (ce > base + 64) {
+            break; // the cell continues in the next chunk
+          }
+          if (ce > cb) {
+            flush_moments(jrow + cur * ROW_STRIDE);
+            if (COUNT) {
+              const uint32_t pop = ce - cb, left = __reduce_add_sync(FULL, n_left);
+              if (lane == 0) {
+                const size_t e = cen0 + (size_t)(c0 + cur);
+                atomicAdd(cnt32 + (e >> 1), (pop - left) << (16 * (e & 1)));
+                if (pop > CNT_MAX) {
+                  atomicExch(&A.flags[0], 1u);
+                }
+              }
+              n_left = 0;
+            }
+          }
+          if (++cur == RUN) {
+            break;
+          }
+          cb = ce;
+          ce = __shfl_sync(FULL, myoff, cur + 1);
+          if (cb >= base + 64) {
+            break; // the next cell starts in the next chunk
+          }
+        }
+        base += 64;
       } while (base < end);
     }
     if (lane == 0) {

@@ -179,10 +179,13 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
   // deck's constructors (psc_bubble_yz.cxx:296-320) -- a compile-and-run check that the
   // operator types are source-compatible with it
   {
-    struct PscCheckParams
+    struct PscCheckParams // the fields of CheckParams (include/checks_params.hxx:3-29)
     {
       int check_interval = 1;
       double err_threshold = 1e-4;
+      bool print_max_err_always = false;
+      bool dump_always = false;
+      bool exit_on_failure = false;
     };
     struct PscChecksParams
     {
@@ -205,6 +208,34 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
       balance_(grid_ptr, mprts);
       if (grid_ptr != &grid) {
         return 8;
+      }
+    }
+    {
+      // what Balance does after patches have moved (psc_balance_impl.hxx:893-1016): the host
+      // Grid_t is REPLACED and every container is reset(new_grid).  The device context must
+      // follow the new grid object with its particles and fields, not be re-created empty.
+      Grid new_grid = grid;
+      psc_b200_ctx* ctx_before = mprts.ctx();
+      const int n_before = mprts.size();
+      const auto e_before = mflds.download(PSC_B200_EX, PSC_B200_EX + 1);
+      mprts.reset(new_grid);
+      mflds.reset(new_grid);
+      if (mprts.ctx() != ctx_before || mflds.ctx() != ctx_before || &mprts.grid() != &new_grid ||
+          &mflds.grid() != &new_grid || mprts.size() != n_before ||
+          mflds.download(PSC_B200_EX, PSC_B200_EX + 1) != e_before) {
+        std::fprintf(stderr, "regrid: the containers did not follow the new grid with their data\n");
+        return 9;
+      }
+      // a container constructed on the new grid attaches to the same context
+      typename Config::Mparticles mprts2{new_grid};
+      if (mprts2.ctx() != ctx_before || mprts2.size() != n_before) {
+        return 10;
+      }
+      // ... and back (the rest of the test keeps using `grid`)
+      mprts.reset(grid);
+      mflds.reset(grid);
+      if (mprts.ctx() != ctx_before || &mflds.grid() != &grid) {
+        return 11;
       }
     }
     sort_(mprts);

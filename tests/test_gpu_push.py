@@ -28,6 +28,8 @@ PATHS = {
     "tiled_warp_tma": (dict(tiled=1, tma=1, lean=0), True),  # ... tile staged by TMA bulk copies
     "lean": (dict(tiled=1, tma=1, lean=1), True),          # k_push_lean: tensor-map TMA, moment deposit, counts
     "lean_nocount": (dict(tiled=1, tma=1, lean=1, keep_sorted=0), True),  # ... without the class counts
+    "lean2": (dict(tiled=1, tma=1, lean=2), True),         # ... two particles per lane on the packed FP32 pipe (exact build)
+    "lean2_nocount": (dict(tiled=1, tma=1, lean=2, keep_sorted=0), True),
     "tiled_small": (dict(tiled=1, tma=1, tile=4, threads=128), True),  # run-time tile geometry
 }
 
@@ -83,7 +85,7 @@ def test_push_matches_oracle(name, vth, path, fma):
     assert np.abs(jg - jr).max() <= (1e-5 if fma == 0 else 3e-5) * scale
 
 
-@pytest.mark.parametrize("path", ["general", "tiled_warp", "lean"])
+@pytest.mark.parametrize("path", ["general", "tiled_warp", "lean", "lean2"])
 @pytest.mark.parametrize("dim", ["xyz", "yz"])
 @pytest.mark.parametrize("case", GOLDEN["push_cases"], ids=[c["name"] for c in GOLDEN["push_cases"]])
 def test_golden_single_particle(case, dim, path):
