@@ -622,12 +622,15 @@ int fused_bnd_sort(Ctx* c)
     uint32_t h4[4];
     PSC_CUDA_TRY(cudaMemcpyAsync(h4, flags, sizeof(h4), cudaMemcpyDeviceToHost, c->stream));
     PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    // every rank must reach the exchange below, also when it falls back later
-    const bool bad = h4[0] != 0;
-    const uint32_t n_rem = bad ? 0 : h4[2];
-    if (bad) {
+    // A rank whose precondition broke takes the general path right here.  The ranks stay
+    // in step because BOTH paths issue exactly one comm_exchange_particles per call
+    // (bnd_particles: fixup = false, below: fixup = true) over the same neighbour tables:
+    // the sends / receives pair up whichever path a peer is on.  Keep it that way (an early
+    // return in either that skips the exchange would hang NCCL).
+    if (h4[0] != 0) {
       return fused_fallback(c);
     }
+    const uint32_t n_rem = h4[2];
     if (!c->rf_built) {
       PSC_TRY(build_remote_cells(c));
     }

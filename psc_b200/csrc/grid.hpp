@@ -120,6 +120,14 @@ inline bool grid_setup(const psc_b200_grid_desc& desc, GridHost& g, std::string&
       g.desc.bc_fld_lo[d] = g.desc.bc_fld_hi[d] = PSC_B200_BND_FLD_PERIODIC;
       g.desc.bc_prt_lo[d] = g.desc.bc_prt_hi[d] = PSC_B200_BND_PRT_PERIODIC;
     }
+    for (int bc : {g.desc.bc_fld_lo[d], g.desc.bc_fld_hi[d]}) {
+      if (bc != PSC_B200_BND_FLD_PERIODIC && bc != PSC_B200_BND_FLD_CONDUCTING_WALL) {
+        // psc_bnd_fields_impl.hxx:535-640 (BND_FLD_OPEN) is not built; the reference itself
+        // asserts on BND_FLD_ABSORBING.  Running with untouched ghost cells would be wrong physics.
+        err = "field boundary conditions other than periodic / conducting wall are not implemented";
+        return false;
+      }
+    }
     g.periodic[d] =
       g.desc.bc_fld_lo[d] == PSC_B200_BND_FLD_PERIODIC && desc.gdims[d] > 1;
     g.n_patches_global *= desc.np[d];

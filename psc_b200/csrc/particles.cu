@@ -206,27 +206,50 @@ int prts_reserve(Ctx* c, size_t n)
     return fail("more than 2^32 particles on one rank (PSC indexes particles with uint)");
   }
   // one pair of buffers at a time (the idle pair first), so that the peak is the old
-  // current pair + the new buffers, not twice everything
+  // current pair + the new buffers, not twice everything.  If an allocation fails the store
+  // is left EMPTY and consistent (cap = 0, no particles) and the error is returned: a caller
+  // that carries on gets "no particles", never kernels on null buffers.
   const int cur = c->cur, alt = c->cur ^ 1;
+  auto lost = [&](const char* what, cudaError_t e) {
+    for (int b = 0; b < 2; b++) {
+      cudaFree(c->xi4[b]);
+      cudaFree(c->pxi4[b]);
+      c->xi4[b] = c->pxi4[b] = nullptr;
+    }
+    c->cap = 0;
+    c->n_prts = 0;
+    std::fill(c->h_off.begin(), c->h_off.end(), 0u);
+    c->sorted = c->pushed_from_sorted = c->counts_valid = false;
+    cudaMemsetAsync(c->d_off, 0, c->h_off.size() * sizeof(uint32_t), c->stream);
+    cudaGetLastError();
+    return fail(std::string("prts_reserve: ") + what + ": " + cudaGetErrorString(e) +
+                " (the particle store was released)");
+  };
+  cudaError_t e;
   cudaFree(c->xi4[alt]);
   cudaFree(c->pxi4[alt]);
   c->xi4[alt] = c->pxi4[alt] = nullptr;
-  PSC_CUDA_TRY(cudaMalloc(&c->xi4[alt], ncap * sizeof(float4)));
-  PSC_CUDA_TRY(cudaMalloc(&c->pxi4[alt], ncap * sizeof(float4)));
+  if ((e = cudaMalloc(&c->xi4[alt], ncap * sizeof(float4))) != cudaSuccess ||
+      (e = cudaMalloc(&c->pxi4[alt], ncap * sizeof(float4))) != cudaSuccess) {
+    return lost("growing the idle buffers", e);
+  }
   if (c->n_prts) {
-    PSC_CUDA_TRY(cudaMemcpyAsync(c->xi4[alt], c->xi4[cur], c->n_prts * sizeof(float4),
-                                 cudaMemcpyDeviceToDevice, c->stream));
-    PSC_CUDA_TRY(cudaMemcpyAsync(c->pxi4[alt], c->pxi4[cur], c->n_prts * sizeof(float4),
-                                 cudaMemcpyDeviceToDevice, c->stream));
-    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if ((e = cudaMemcpyAsync(c->xi4[alt], c->xi4[cur], c->n_prts * sizeof(float4), cudaMemcpyDeviceToDevice,
+                             c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(c->pxi4[alt], c->pxi4[cur], c->n_prts * sizeof(float4), cudaMemcpyDeviceToDevice,
+                             c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+      return lost("copying the store", e);
+    }
   }
   cudaFree(c->xi4[cur]);
   cudaFree(c->pxi4[cur]);
   c->xi4[cur] = c->pxi4[cur] = nullptr;
-  c->cap = 0;
   c->cur = alt; // the data live in the pair that was grown first
-  PSC_CUDA_TRY(cudaMalloc(&c->xi4[cur], ncap * sizeof(float4)));
-  PSC_CUDA_TRY(cudaMalloc(&c->pxi4[cur], ncap * sizeof(float4)));
+  if ((e = cudaMalloc(&c->xi4[cur], ncap * sizeof(float4))) != cudaSuccess ||
+      (e = cudaMalloc(&c->pxi4[cur], ncap * sizeof(float4))) != cudaSuccess) {
+    return lost("growing the second pair of buffers", e);
+  }
   c->cap = ncap;
   return 0;
 }

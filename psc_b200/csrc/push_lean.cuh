@@ -32,14 +32,15 @@
 namespace lean
 {
 
-// warps per CTA: 8 x 3 CTAs per SM at 80 registers (W = 1), 12 x 2 CTAs at 85 (W = 2)
+// warps per CTA: 8 x 3 CTAs per SM at 80 registers (W = 1), 8 x 2 CTAs at 128 (W = 2; with 10 warps at 96
+// registers the xyz kernel spills and takes 20.8 ms instead of 18.9, with 12 at 80 it spills 264 bytes)
 template <int W>
 __host__ __device__ constexpr int n_warps()
 {
 #ifdef LEAN_NW2
   return W == 1 ? 8 : LEAN_NW2;
 #else
-  return W == 1 ? 8 : 12;
+  return W == 1 ? 8 : 8;
 #endif
 }
 // queue entries per warp: a chunk (32 W particles) must always fit behind what a walk leaves
@@ -463,16 +464,16 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
       int cur = 0;
       uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1);
       uint32_t n_left = 0;
-      f2 acc[NM]; // .x: particle A's share of the cell's moments, .y: particle B's
+      float acc[NM]; // this lane's share of the cell's moments (both particles)
 #pragma unroll
       for (int n = 0; n < NM; n++) {
-        acc[n] = mk2(0.f, 0.f);
+        acc[n] = 0.f;
       }
       auto flush_moments = [&](int at) {
         float v[NVP];
 #pragma unroll
         for (int n = 0; n < NVP; n++) {
-          v[n] = n < NM ? acc[n].v.x + acc[n].v.y : 0.f;
+          v[n] = n < NM ? acc[n] : 0.f;
         }
         warp_transpose_reduce<NVP>(v, lane);
         const float leaf = moments_to_leaf<DIM>(v[0], lane) * my_fnq;
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         }
 #pragma unroll
         for (int n = 0; n < NM; n++) {
-          acc[n] = mk2(0.f, 0.f);
+          acc[n] = 0.f;
         }
       };
       // staging: x[0..63], p[0..63]; every lane copies and reads its own four slots
@@ -594,29 +595,32 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
             n_left += (mine_a && cross_a) + (mine_b && cross_b);
           }
           {
+            // packed products for both particles, summed into the lane's scalar moments (twelve
+            // packed accumulators would cost twelve more registers, i.e. occupancy)
             const float2 qh = __fmul2_rn(qe.v, h12.v);
+            auto add2 = [](float& a, float2 v) { a += v.x + v.y; };
             if (XYZ) {
 #pragma unroll
               for (int d = 0; d < 3; d++) {
                 const float2 m = __fmul2_rn(qe.v, dx[d].v);
                 const float2 a = xa[(d + 1) % 3].v, b = xa[(d + 2) % 3].v;
                 const float2 ma = __fmul2_rn(m, a);
-                acc[4 * d + 0].v = __fadd2_rn(acc[4 * d + 0].v, m);
-                acc[4 * d + 1].v = __fadd2_rn(acc[4 * d + 1].v, ma);
-                acc[4 * d + 2].v = __ffma2_rn(m, b, acc[4 * d + 2].v);
-                acc[4 * d + 3].v = __ffma2_rn(ma, b, __fadd2_rn(acc[4 * d + 3].v, qh));
+                add2(acc[4 * d + 0], m);
+                add2(acc[4 * d + 1], ma);
+                add2(acc[4 * d + 2], __fmul2_rn(m, b));
+                add2(acc[4 * d + 3], __ffma2_rn(ma, b, qh));
               }
             } else {
               const float2 m0 = __fmul2_rn(qe.v, dx[0].v), m1 = __fmul2_rn(qe.v, dx[1].v), m2 = __fmul2_rn(qe.v, dx[2].v);
               const float2 ma = __fmul2_rn(m0, xa[1].v);
-              acc[0].v = __fadd2_rn(acc[0].v, m0);
-              acc[1].v = __fadd2_rn(acc[1].v, ma);
-              acc[2].v = __ffma2_rn(m0, xa[2].v, acc[2].v);
-              acc[3].v = __ffma2_rn(ma, xa[2].v, __fadd2_rn(acc[3].v, qh));
-              acc[4].v = __fadd2_rn(acc[4].v, m1);
-              acc[5].v = __ffma2_rn(m1, xa[2].v, acc[5].v);
-              acc[6].v = __fadd2_rn(acc[6].v, m2);
-              acc[7].v = __ffma2_rn(m2, xa[1].v, acc[7].v);
+              add2(acc[0], m0);
+              add2(acc[1], ma);
+              add2(acc[2], __fmul2_rn(m0, xa[2].v));
+              add2(acc[3], __ffma2_rn(ma, xa[2].v, qh));
+              add2(acc[4], m1);
+              add2(acc[5], __fmul2_rn(m1, xa[2].v));
+              add2(acc[6], m2);
+              add2(acc[7], __fmul2_rn(m2, xa[1].v));
             }
           }
           if (ce > base + 64) {
