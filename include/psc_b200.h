@@ -206,9 +206,33 @@ typedef struct
   double marder_diffusion;
   int push_fields;      /* 0 = particle part only (push + exchange + sort) */
   int checks;           /* continuity + gauss checks (results via _last_checks) */
+  int energies;         /* DiagEnergies reduced inside the step (field part behind the field
+                           chain, particle part behind the sort); read with _last_energies */
 } psc_b200_step_params;
 int psc_b200_step(psc_b200_ctx* ctx, const psc_b200_step_params* prm);
 int psc_b200_last_checks(psc_b200_ctx* ctx, double* continuity, double* gauss);
+/* out[8] as psc_b200_energies, of the last step that asked for them */
+int psc_b200_last_energies(psc_b200_ctx* ctx, double out[8]);
+
+/* ---- pipelined host I/O: a deck whose field solver / diagnostics live on the host ----
+ * The reference's CUDA backend stages fields through the host synchronously
+ * (psc_fields_cuda.h:78-113 hostMirror/copy).  Here the transfers overlap the particle
+ * re-sort of the same step:
+ *   step_begin            sort (if needed), push + deposit, then side by side: the particle
+ *                         boundary exchange + sort on one stream, J ghosts (+ Yee when
+ *                         push_fields) on the field stream; returns without waiting
+ *   mflds_download_async  / mflds_upload_async: queued on the field stream (PINNED host
+ *                         memory, or they degrade to synchronous copies)
+ *   io_wait               blocks until the field stream's transfers are done (the sort may
+ *                         still be running)
+ *   step_end              waits for the sort, commits it, joins the streams
+ * Any other entry point completes a pending step first, so forgetting step_end is safe. */
+int psc_b200_step_begin(psc_b200_ctx* ctx, const psc_b200_step_params* prm);
+int psc_b200_step_end(psc_b200_ctx* ctx);
+int psc_b200_mflds_download_async(psc_b200_ctx* ctx, int field_id, int mb, int me, float* host);
+int psc_b200_mflds_upload_async(psc_b200_ctx* ctx, int field_id, int mb, int me,
+                                const float* host);
+int psc_b200_io_wait(psc_b200_ctx* ctx);
 
 /* ---- multi-GPU: NCCL over NVLink (replaces every MPI site of SURVEY.md 2.3) ---- */
 int psc_b200_nccl_unique_id(void* id128);

@@ -962,6 +962,7 @@ public:
       sp.marder_diffusion = p_.marder_diffusion;
       sp.push_fields = 1;
       sp.checks = checks_.continuity.should_do_check(t) || checks_.gauss.should_do_check(t);
+      sp.energies = 0;
       PSC_B200_CHECK(psc_b200_step(mprts_.ctx(), &sp));
       if (sp.checks) {
         PSC_B200_CHECK(psc_b200_last_checks(mprts_.ctx(), &checks_.continuity.last_max_err,

@@ -33,7 +33,7 @@ class StepParams(C.Structure):
     """psc_b200_step_params"""
     _fields_ = [
         ("sort", C.c_int), ("marder_loop", C.c_int), ("marder_diffusion", C.c_double),
-        ("push_fields", C.c_int), ("checks", C.c_int),
+        ("push_fields", C.c_int), ("checks", C.c_int), ("energies", C.c_int),
     ]
 
 
@@ -103,7 +103,13 @@ def load():
         "psc_b200_check_continuity_end": [CTX, C.POINTER(C.c_double)],
         "psc_b200_check_gauss": [CTX, C.POINTER(C.c_double)],
         "psc_b200_energies": [CTX, P],
+        "psc_b200_last_energies": [CTX, P],
         "psc_b200_step": [CTX, C.POINTER(StepParams)],
+        "psc_b200_step_begin": [CTX, C.POINTER(StepParams)],
+        "psc_b200_step_end": [CTX],
+        "psc_b200_mflds_download_async": [CTX, C.c_int, C.c_int, C.c_int, P],
+        "psc_b200_mflds_upload_async": [CTX, C.c_int, C.c_int, C.c_int, P],
+        "psc_b200_io_wait": [CTX],
         "psc_b200_last_checks": [CTX, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "psc_b200_nccl_unique_id": [P],
         "psc_b200_nccl_init": [CTX, P],

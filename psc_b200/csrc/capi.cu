@@ -254,6 +254,14 @@ static int ctx_create(const psc_b200_grid_desc* desc, Ctx** out)
     PSC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     PSC_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
   }
+  {
+    // (2-D copies may run as kernels: they must not queue behind the scatter's CTAs)
+    int prio_lo = 0, prio_hi = 0;
+    PSC_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PSC_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_io, cudaStreamNonBlocking, prio_hi));
+  }
+  PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
+  PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_flds_done, cudaEventDisableTiming));
   PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   PSC_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   PSC_CUDA_TRY(cudaEventCreate(&c->ev_start));
@@ -304,6 +312,12 @@ static void ctx_destroy(Ctx* c)
     cudaFree(c->pxi4[b]);
   }
   gap_release(c);
+  if (c->fs_host) {
+    cudaFreeHost(c->fs_host);
+  }
+  if (c->en_host) {
+    cudaFreeHost(c->en_host);
+  }
   cudaFree(c->d_off);
   cudaFree(c->d_cell_off);
   cudaFree(c->d_cell_off_alt);
@@ -326,6 +340,9 @@ static void ctx_destroy(Ctx* c)
   cudaEventDestroy(c->ev_stop);
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
+  cudaEventDestroy(c->ev_j_ready);
+  cudaEventDestroy(c->ev_flds_done);
+  cudaStreamDestroy(c->stream_io);
   cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -371,6 +388,7 @@ static int field_chain(Ctx* c, const psc_b200_step_params* prm)
   PSC_TRY(bndf_add_ghosts_J(c));                       // :417
   PSC_TRY(bnd_add_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :418
   PSC_TRY(bnd_fill_ghosts(c, 0, pm::JXI, pm::JXI + 3)); // :419
+  PSC_CUDA_TRY(cudaEventRecord(c->ev_j_ready, c->stream)); // (a queued download of J need not wait for Yee)
   if (prm->push_fields) {
     PSC_TRY(push_H(c, .5)); // :426
     PSC_TRY(bndf_fill_ghosts_H(c));
@@ -385,8 +403,31 @@ static int field_chain(Ctx* c, const psc_b200_step_params* prm)
   return 0;
 }
 
+static int en_host_ready(Ctx* c)
+{
+  if (!c->en_host) {
+    PSC_CUDA_TRY(cudaMallocHost(&c->en_host, 8 * sizeof(double)));
+  }
+  return 0;
+}
+
+static int step_core(Ctx* c, const psc_b200_step_params* prm);
+
 // Psc::step (src/include/psc.hxx:321-486) without collisions / injection / output
 static int step(Ctx* c, const psc_b200_step_params* prm)
+{
+  PSC_TRY(step_core(c, prm));
+  if (prm->energies) {
+    PSC_TRY(en_host_ready(c));
+    PSC_TRY(store_ready(c));
+    PSC_TRY(field_energies(c, c->en_host));
+    PSC_TRY(prts_energies(c, c->en_host + 6));
+    c->en_valid = true;
+  }
+  return 0;
+}
+
+static int step_core(Ctx* c, const psc_b200_step_params* prm)
 {
   // gapped store (gap.cuh): push + deposit + boundary exchange + sort are one pass over the
   // particles; the store stays gapped from step to step
@@ -469,24 +510,150 @@ static int step(Ctx* c, const psc_b200_step_params* prm)
   return 0;
 }
 
+// ---- pipelined host I/O (psc_b200_step_begin / _step_end)
+//
+// A deck whose field solver or diagnostics live on the host needs J down and E/B up every
+// step.  After the push nothing that touches the particles depends on the fields and vice
+// versa, so step_begin() leaves two streams running side by side:
+//   stream   the fused boundary exchange + sort (12 of the step's 33 ms at S3D)
+//   stream2  J ghosts (+ the Yee half of the step), then whatever the caller queues with
+//            mflds_download_async / mflds_upload_async
+// and returns.  io_wait() blocks on stream2 only (J is on the host while the sort is still
+// running), step_end() waits for the sort, commits it and joins the streams.  Every other
+// entry point completes a pending step first.
+static int step_pending_finish(Ctx* c)
+{
+  if (!c->step_pending) {
+    return 0;
+  }
+  c->step_pending = false;
+  const uint64_t fb0 = c->n_fused_fallback;
+  int rc = fused_bnd_sort_finish(c);
+  if (!rc && c->n_fused_fallback != fb0 && c->en_valid) {
+    // the scatter's result was discarded (general path taken instead): so are its energies
+    rc = prts_energies(c, c->en_host + 6);
+  }
+  cudaError_t e = cudaEventRecord(c->ev_join, c->stream2);
+  if (e == cudaSuccess) {
+    e = cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+  }
+  if (e == cudaSuccess) {
+    e = cudaStreamSynchronize(c->stream2);
+  }
+  if (e == cudaSuccess) {
+    e = cudaStreamSynchronize(c->stream_io); // host buffers of the async transfers are free again
+  }
+  if (rc) {
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    return fail(std::string("step_end: ") + cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+static int step_begin(Ctx* c, const psc_b200_step_params* prm)
+{
+  const bool do_sort = prm->sort || (c->opt_keep_sorted && c->opt_fused_sort && c->opt_tiled);
+  const bool split = do_sort && c->opt_fused_sort && c->opt_tiled && !c->opt_gapped && !prm->checks &&
+                     prm->marder_loop <= 0 && c->n_prts > 0;
+  if (!split) {
+    return step(c, prm); // nothing left pending: the async transfers simply follow it
+  }
+  PSC_TRY(store_ready(c));
+  if (!c->sorted) {
+    PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
+  }
+  c->want_counts = true;
+  PSC_TRY(push_mprts(c)); // :389
+  if (!c->pushed_from_sorted) {
+    // (the tiled push was not applicable: no counts, general exchange)
+    PSC_TRY(bnd_particles(c));
+    PSC_TRY(field_chain(c, prm));
+    if (prm->energies) {
+      PSC_TRY(en_host_ready(c));
+      PSC_TRY(field_energies(c, c->en_host));
+      PSC_TRY(prts_energies(c, c->en_host + 6));
+      c->en_valid = true;
+    }
+    return 0;
+  }
+  // fields on stream2 ...
+  PSC_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+  PSC_CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  if (prm->energies) {
+    PSC_TRY(en_host_ready(c));
+  }
+  std::swap(c->stream, c->stream2);
+  int rc = field_chain(c, prm); // :417-467
+  if (!rc && prm->energies) {
+    rc = field_energies(c, c->en_host, /*sync=*/false); // (before the caller's uploads touch E, B)
+  }
+  if (!rc && cudaEventRecord(c->ev_flds_done, c->stream) != cudaSuccess) {
+    rc = fail("step_begin: cudaEventRecord");
+  }
+  std::swap(c->stream, c->stream2);
+  PSC_TRY(rc);
+  // ... particles on stream (:412 + :356 of the next step); single rank: enqueued only
+  c->step_pending = true;
+  const uint32_t nct = (uint32_t)c->gd.n_cells * c->gd.n_patches;
+  c->want_scatter_energies = prm->energies != 0;
+  c->scatter_energies_done = false;
+  rc = fused_bnd_sort(c, /*defer=*/c->comm == nullptr);
+  c->want_scatter_energies = false;
+  PSC_TRY(rc);
+  if (prm->energies && c->scatter_energies_done) {
+    c->en_valid = true; // (the scatter reduced them on its way)
+  } else if (prm->energies) {
+    if (c->fs_deferred) {
+      // the sorted store is still the "other" buffer and its size is only on the device
+      PSC_TRY(prts_energies(c, c->en_host + 6, false, c->d_cell_off_alt + nct, true));
+    } else {
+      PSC_TRY(prts_energies(c, c->en_host + 6, false));
+    }
+    c->en_valid = true;
+  }
+  return 0;
+}
+
+// the caller's transfers run on their own stream: a download of J components waits for the J
+// ghost sums only (not for the Yee update behind them), anything else for the end of the
+// field chain; without a pending step they are ordered behind everything queued so far
+static int io_stream_ready(Ctx* c, int id, int mb, int me, bool upload)
+{
+  if (c->step_pending) {
+    const bool j_only = !upload && id == 0 && mb >= pm::JXI && me <= pm::JXI + 3;
+    PSC_CUDA_TRY(cudaStreamWaitEvent(c->stream_io, j_only ? c->ev_j_ready : c->ev_flds_done, 0));
+  } else {
+    PSC_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+    PSC_CUDA_TRY(cudaStreamWaitEvent(c->stream_io, c->ev_fork, 0));
+  }
+  return 0;
+}
+
 } // namespace psc_b200
 
 using namespace psc_b200;
 
 #define CTX(ctx) reinterpret_cast<Ctx*>(ctx)
-#define GUARD(body)                                                                      \
+#define GUARD_(finish, body)                                                             \
   try {                                                                                  \
     if (!ctx) {                                                                          \
       return fail("null context");                                                       \
     }                                                                                    \
     Ctx* c = CTX(ctx);                                                                   \
     cudaSetDevice(c->device);                                                            \
+    if (finish) {                                                                        \
+      PSC_TRY(step_pending_finish(c));                                                   \
+    }                                                                                    \
     body                                                                                 \
   } catch (const std::exception& e) {                                                    \
     return fail(std::string("exception: ") + e.what());                                  \
   } catch (...) {                                                                        \
     return fail("unknown exception");                                                    \
   }
+#define GUARD(body) GUARD_(true, body)
+#define GUARD_ASYNC(body) GUARD_(false, body)
 
 extern "C" {
 
@@ -598,6 +765,42 @@ int psc_b200_mflds_upload(psc_b200_ctx* ctx, int id, int mb, int me, const float
 int psc_b200_mflds_download(psc_b200_ctx* ctx, int id, int mb, int me, float* host)
 {
   GUARD(return flds_download(c, id, mb, me, host);)
+}
+
+int psc_b200_mflds_download_async(psc_b200_ctx* ctx, int id, int mb, int me, float* host)
+{
+  GUARD_ASYNC(PSC_TRY(io_stream_ready(c, id, mb, me, false)); std::swap(c->stream, c->stream_io);
+              int rc = flds_download(c, id, mb, me, host, /*sync=*/false);
+              std::swap(c->stream, c->stream_io); return rc;)
+}
+
+int psc_b200_mflds_upload_async(psc_b200_ctx* ctx, int id, int mb, int me, const float* host)
+{
+  GUARD_ASYNC(PSC_TRY(io_stream_ready(c, id, mb, me, true)); std::swap(c->stream, c->stream_io);
+              int rc = flds_upload(c, id, mb, me, host, /*sync=*/false);
+              std::swap(c->stream, c->stream_io); return rc;)
+}
+
+int psc_b200_io_wait(psc_b200_ctx* ctx)
+{
+  GUARD_ASYNC(PSC_CUDA_TRY(cudaStreamSynchronize(c->stream_io)); return check_launch(c, "io_wait");)
+}
+
+int psc_b200_step_begin(psc_b200_ctx* ctx, const psc_b200_step_params* prm)
+{
+  GUARD(if (!prm) { return fail("null step params"); } return step_begin(c, prm);)
+}
+
+int psc_b200_last_energies(psc_b200_ctx* ctx, double out[8])
+{
+  GUARD(if (!c->en_valid) { return fail("no step has reduced the energies yet (step_params.energies)"); }
+        PSC_CUDA_TRY(cudaStreamSynchronize(c->stream)); PSC_CUDA_TRY(cudaStreamSynchronize(c->stream2));
+        memcpy(out, c->en_host, 8 * sizeof(double)); return 0;)
+}
+
+int psc_b200_step_end(psc_b200_ctx* ctx)
+{
+  GUARD(return 0;) // (GUARD completes the pending step)
 }
 
 int psc_b200_mflds_zero(psc_b200_ctx* ctx, int id, int mb, int me)

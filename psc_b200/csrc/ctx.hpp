@@ -90,7 +90,9 @@ struct Ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr; // step(): the field chain runs here next to the particle sort
+  cudaStream_t stream_io = nullptr; // step_begin(): the caller's async host transfers
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_j_ready = nullptr, ev_flds_done = nullptr; // field chain: J final / E, H final
 
   // ---- options (psc_b200_set_option)
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
@@ -129,6 +131,16 @@ struct Ctx
   uint32_t* d_cell_off = nullptr; // n_patches * n_cells + 1
   uint32_t* d_cell_off_alt = nullptr; // written by the fused boundary+sort pass
   uint64_t n_fused_fallback = 0;
+  // step_begin / step_end (pipelined host I/O): the exchange + sort is in flight on `stream`,
+  // the field chain and the host transfers on `stream2`
+  bool step_pending = false;
+  bool fs_deferred = false;      // ... and its flags / new offsets have not been read back yet
+  uint32_t* fs_host = nullptr;   // pinned landing zone of that read-back
+  size_t fs_host_bytes = 0;
+  double* en_host = nullptr;     // pinned: DiagEnergies of the last step that asked for them
+  bool en_valid = false;
+  bool want_scatter_energies = false;  // ask the next fused scatter to reduce the particle energies ...
+  bool scatter_energies_done = false;  // ... and whether it did (single rank, no fallback)
   uint64_t n_dropped = 0;        // absorbed at open/absorbing walls so far
 
   // ---- gapped store (gap.cuh): when `gapped` is set, xi4/pxi4[cur] hold one run per cell,
@@ -211,7 +223,9 @@ int prts_inject(Ctx* c, const void* aos, const uint32_t* n_by_patch);
 int prts_get(Ctx* c, void* aos, uint32_t* off);
 int prts_setup_thermal(Ctx* c, int ppc, const int* ppc_by_patch, const double* vth, uint64_t seed);
 int prts_upload_off(Ctx* c);
-int prts_energies(Ctx* c, double out2[2]);
+// d_n: particle count read on the device (a deferred sort has not told the host yet); alt:
+// the store the fused sort is writing
+int prts_energies(Ctx* c, double out2[2], bool sync = true, const uint32_t* d_n = nullptr, bool alt = false);
 int selftest_math(Ctx* c, uint64_t* n_bad);
 
 // ---- push.cu (two builds of the same source: exact = -fmad=false, fast = FMA)
@@ -222,7 +236,9 @@ int push_mprts_fast(Ctx* c);
 int sort_mprts(Ctx* c);
 int sort_pairs(Ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
                size_t n, int key_bits, bool iota_vals, bool* result_in_alt);
-int fused_bnd_sort(Ctx* c); // boundary exchange + sort of a pushed, previously sorted store
+// boundary exchange + sort of a pushed, previously sorted store; defer: see step_begin (capi.cu)
+int fused_bnd_sort(Ctx* c, bool defer = false);
+int fused_bnd_sort_finish(Ctx* c);
 // gapped store (gap.cuh)
 int gap_prepare(Ctx* c, bool* ok); // allocations, layout, per-step clears; *ok = false: not applicable
 int gap_finish(Ctx* c, bool* redo); // offsets, mover placement, commit; *redo: take the eager path
@@ -243,8 +259,8 @@ int bnd_particles(Ctx* c);
 int flds_create(Ctx* c, int n_comps, int* id);
 int flds_zero(Ctx* c, int id, int mb, int me);
 int flds_fill(Ctx* c, int id, int m, float v);
-int flds_upload(Ctx* c, int id, int mb, int me, const float* host);
-int flds_download(Ctx* c, int id, int mb, int me, float* host);
+int flds_upload(Ctx* c, int id, int mb, int me, const float* host, bool sync = true);
+int flds_download(Ctx* c, int id, int mb, int me, float* host, bool sync = true);
 int bnd_fill_ghosts(Ctx* c, int id, int mb, int me);
 int bnd_add_ghosts(Ctx* c, int id, int mb, int me);
 int bndf_fill_ghosts_E(Ctx* c);
@@ -259,7 +275,7 @@ int marder(Ctx* c, double diffusion, int loop);
 int check_continuity_begin(Ctx* c);
 int check_continuity_end(Ctx* c, double* err);
 int check_gauss(Ctx* c, double* err);
-int field_energies(Ctx* c, double out6[6]);
+int field_energies(Ctx* c, double out6[6], bool sync = true);
 
 // ---- comm.cpp (NCCL through dlopen; nothing here runs unless nccl_init was called)
 int comm_unique_id(void* id128);

@@ -708,25 +708,29 @@ int flds_fill(Ctx* c, int id, int m, float v)
   return check_launch(c, "flds_fill");
 }
 
-int flds_upload(Ctx* c, int id, int mb, int me, const float* host)
+int flds_upload(Ctx* c, int id, int mb, int me, const float* host, bool sync)
 {
   PSC_TRY(check_field(c, id, mb, me));
   size_t w = (size_t)(me - mb) * c->gd.fld_len * sizeof(float);
   PSC_CUDA_TRY(cudaMemcpy2DAsync(c->fld(id) + (size_t)mb * c->gd.fld_len,
                                  (size_t)c->fld_slot_len(id) * sizeof(float), host, w, w,
                                  c->gd.n_patches, cudaMemcpyHostToDevice, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (sync) {
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }
 
-int flds_download(Ctx* c, int id, int mb, int me, float* host)
+int flds_download(Ctx* c, int id, int mb, int me, float* host, bool sync)
 {
   PSC_TRY(check_field(c, id, mb, me));
   size_t w = (size_t)(me - mb) * c->gd.fld_len * sizeof(float);
   PSC_CUDA_TRY(cudaMemcpy2DAsync(host, w, c->fld(id) + (size_t)mb * c->gd.fld_len,
                                  (size_t)c->fld_slot_len(id) * sizeof(float), w, c->gd.n_patches,
                                  cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (sync) {
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }
 
@@ -1219,7 +1223,7 @@ int marder(Ctx* c, double diffusion_, int loop)
   return bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3);
 }
 
-int field_energies(Ctx* c, double out6[6])
+int field_energies(Ctx* c, double out6[6], bool sync)
 {
   PSC_TRY(c->scr[8].reserve(128));
   double* d = c->scr[8].as<double>() + 4;
@@ -1230,7 +1234,9 @@ int field_energies(Ctx* c, double out6[6])
                                              c->g.dx[0] * c->g.dx[1] * c->g.dx[2], d);
   c->n_launches++;
   PSC_CUDA_TRY(cudaMemcpyAsync(out6, d, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (sync) {
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
   return check_launch(c, "field_energies");
 }
 

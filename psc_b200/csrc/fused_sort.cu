@@ -280,12 +280,23 @@ __device__ __forceinline__ void fs_cp_async16(uint32_t dst, const void* src)
 #ifndef SC_DEPTH
 #define SC_DEPTH 3 // stages of the per-warp chunk pipeline
 #endif
+// DiagEnergiesParticle.h:15-40 for the particles the scatter keeps (EN): the pass is
+// DRAM-bound with issue slots to spare, a separate reduction pass costs 5.5 ms at S3D
+struct ScatterEnergies
+{
+  float q[pm::MAX_KINDS], m[pm::MAX_KINDS];
+  double fnqs_fac; // fnqs * dx * dy * dz
+  double* out2;    // [electrons (q < 0), ions (q > 0)]
+};
+
+template <bool EN>
 __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   k_fs_scatter(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ cell_off,
                const uint32_t* __restrict__ new_cell_off, const cnt_t* __restrict__ pre,
                const float4* __restrict__ xi4, const float4* __restrict__ pxi4,
-               float4* __restrict__ xo, float4* __restrict__ po)
+               float4* __restrict__ xo, float4* __restrict__ po, ScatterEnergies E)
 {
+  [[maybe_unused]] double e_neg = 0., e_pos = 0.;
   __shared__ uint32_t pre_s[SC_CELLS][33];
   // SC_DEPTH - 1 chunks per warp are in flight while one is ranked: the pass is bound by
   // memory latency x bytes in flight (profiles/r01_v5_fs_scatter_ncu.txt: long-scoreboard
@@ -378,6 +389,18 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
       if (mine && cls < 27) {
         xo[dst] = X;
         po[dst] = U;
+        if constexpr (EN) {
+          const int kind = __float_as_int(X.w);
+          const float qf = E.q[kind], mf = E.m[kind];
+          const float w = U.w / qf;
+          const double gamma = sqrtf(1.f + U.x * U.x + U.y * U.y + U.z * U.z);
+          const double ekin = (gamma - 1.) * mf * w;
+          if (qf < 0.f) {
+            e_neg += ekin;
+          } else if (qf > 0.f) {
+            e_pos += ekin;
+          }
+        }
       }
       if (ce > base + 32) {
         break; // the cell continues in the next chunk
@@ -398,6 +421,17 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
           }
         }
       }
+    }
+  }
+  if constexpr (EN) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e_neg += __shfl_xor_sync(FULL, e_neg, o);
+      e_pos += __shfl_xor_sync(FULL, e_pos, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&E.out2[0], e_neg * E.fnqs_fac);
+      atomicAdd(&E.out2[1], e_pos * E.fnqs_fac);
     }
   }
 }
@@ -561,7 +595,47 @@ static int fused_fallback(Ctx* c)
   return sort_mprts(c);
 }
 
-int fused_bnd_sort(Ctx* c)
+// second half of fused_bnd_sort: the flags and the new patch offsets are on the host
+static int fused_commit(Ctx* c, const uint32_t* h, uint32_t n_expected, bool multi)
+{
+  const int np = c->gd.n_patches;
+  if (h[0]) {
+    if (multi) {
+      return fail("fused boundary+sort: a received particle lies outside its patch");
+    }
+    return fused_fallback(c);
+  }
+  c->cur ^= 1;
+  std::swap(c->d_cell_off, c->d_cell_off_alt);
+  for (int p = 0; p <= np; p++) {
+    c->h_off[p] = h[4 + p];
+  }
+  c->n_prts = c->h_off[np];
+  if (multi && c->n_prts != n_expected) {
+    return fail("fused boundary+sort: particle count mismatch after the exchange");
+  }
+  c->n_dropped += h[1];
+  c->sorted = true;
+  c->pushed_from_sorted = false;
+  c->n_fused++;
+  return prts_upload_off(c);
+}
+
+// a deferred fused_bnd_sort (step_begin): wait for the scatter, commit its result
+int fused_bnd_sort_finish(Ctx* c)
+{
+  if (!c->fs_deferred) {
+    return 0;
+  }
+  c->fs_deferred = false;
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  PSC_TRY(check_launch(c, "fused_bnd_sort"));
+  return fused_commit(c, c->fs_host, c->n_prts, false);
+}
+
+// defer: single rank only -- enqueue everything, leave the read-back of the flags / new patch
+// offsets (and with it the host's wait for the scatter) to fused_bnd_sort_finish()
+int fused_bnd_sort(Ctx* c, bool defer)
 {
   const GridDev& G = c->gd;
   if (!c->pushed_from_sorted) {
@@ -695,8 +769,25 @@ int fused_bnd_sort(Ctx* c)
   }
   {
     KernelScope ks(c, "fsort_scatter");
-    k_fs_scatter<<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
-      G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt());
+    ScatterEnergies SE{};
+    if (c->want_scatter_energies && !multi) {
+      // step_begin asked for DiagEnergies: the particle part rides on this pass
+      for (int k = 0; k < c->g.desc.n_kinds; k++) {
+        SE.q[k] = (float)c->g.desc.q[k];
+        SE.m[k] = (float)c->g.desc.m[k];
+      }
+      SE.fnqs_fac = c->g.desc.fnqs * c->g.dx[0] * c->g.dx[1] * c->g.dx[2];
+      PSC_TRY(c->scr[0].reserve(2 * sizeof(double)));
+      SE.out2 = c->scr[0].as<double>();
+      PSC_CUDA_TRY(cudaMemsetAsync(SE.out2, 0, 2 * sizeof(double), c->stream));
+      k_fs_scatter<true><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
+        G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
+      PSC_CUDA_TRY(cudaMemcpyAsync(c->en_host + 6, SE.out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      c->scatter_energies_done = true;
+    } else {
+      k_fs_scatter<false><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
+        G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
+    }
     if (n_recv_tot) {
       k_fs_place_remote<<<div_up(n_recv_tot, 256), 256, 0, c->stream>>>(
         n_recv_tot, skey, sidx, c->d_cell_off_alt, xr, pr, c->xi_alt(), c->pxi_alt());
@@ -706,31 +797,26 @@ int fused_bnd_sort(Ctx* c)
                                                                d_new_off);
   }
   c->n_launches += 2;
+  if (defer && !multi) {
+    const size_t need = (size_t)(np + 1 + 4) * sizeof(uint32_t);
+    if (c->fs_host_bytes < need) {
+      if (c->fs_host) {
+        cudaFreeHost(c->fs_host);
+        c->fs_host = nullptr;
+      }
+      PSC_CUDA_TRY(cudaMallocHost(&c->fs_host, need));
+      c->fs_host_bytes = need;
+    }
+    PSC_CUDA_TRY(cudaMemcpyAsync(c->fs_host, flags, need, cudaMemcpyDeviceToHost, c->stream));
+    c->fs_deferred = true;
+    return 0;
+  }
   std::vector<uint32_t> h(np + 1 + 4);
   PSC_CUDA_TRY(cudaMemcpyAsync(h.data(), flags, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                c->stream));
   PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
   PSC_TRY(check_launch(c, "fused_bnd_sort"));
-  if (h[0]) {
-    if (multi) {
-      return fail("fused boundary+sort: a received particle lies outside its patch");
-    }
-    return fused_fallback(c);
-  }
-  c->cur ^= 1;
-  std::swap(c->d_cell_off, c->d_cell_off_alt);
-  for (int p = 0; p <= np; p++) {
-    c->h_off[p] = h[4 + p];
-  }
-  c->n_prts = c->h_off[np];
-  if (multi && c->n_prts != n_expected) {
-    return fail("fused boundary+sort: particle count mismatch after the exchange");
-  }
-  c->n_dropped += h[1];
-  c->sorted = true;
-  c->pushed_from_sorted = false;
-  c->n_fused++;
-  return prts_upload_off(c);
+  return fused_commit(c, h.data(), n_expected, multi);
 }
 
 

@@ -166,8 +166,11 @@ struct KindPrm
 
 // DiagEnergiesParticle.h:15-40
 __global__ void k_prt_energies(const float4* __restrict__ pxi4, const float4* __restrict__ xi4,
-                               uint32_t n, KindPrm K, double* out2)
+                               uint32_t n, const uint32_t* __restrict__ d_n, KindPrm K, double* out2)
 {
+  if (d_n) {
+    n = *d_n;
+  }
   double e_neg = 0., e_pos = 0.;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float4 u = pxi4[i];
@@ -454,7 +457,7 @@ int selftest_math(Ctx* c, uint64_t* n_bad)
   return check_launch(c, "selftest_math");
 }
 
-int prts_energies(Ctx* c, double out2[2])
+int prts_energies(Ctx* c, double out2[2], bool sync, const uint32_t* d_n, bool alt)
 {
   const GridHost& g = c->g;
   KindPrm K{};
@@ -468,12 +471,16 @@ int prts_energies(Ctx* c, double out2[2])
   double* d = c->scr[0].as<double>();
   PSC_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), c->stream));
   if (c->n_prts) {
+    KernelScope ks(c, "prt_energies");
     unsigned nb = std::min<unsigned>(div_up(c->n_prts, 256), 148 * 8);
-    k_prt_energies<<<nb, 256, 0, c->stream>>>(c->pxi(), c->xi(), c->n_prts, K, d);
+    k_prt_energies<<<nb, 256, 0, c->stream>>>(alt ? c->pxi_alt() : c->pxi(), alt ? c->xi_alt() : c->xi(), c->n_prts,
+                                             d_n, K, d);
     c->n_launches++;
   }
   PSC_CUDA_TRY(cudaMemcpyAsync(out2, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (sync) {
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
   return check_launch(c, "prt_energies");
 }
 
