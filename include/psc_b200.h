@@ -198,6 +198,23 @@ int psc_b200_check_gauss(psc_b200_ctx* ctx, double* max_err);
  * out[0..5] = EX2 EY2 EZ2 HX2 HY2 HZ2 ; out[6] = E_electron (q<0), out[7] = E_ion ---- */
 int psc_b200_energies(psc_b200_ctx* ctx, double out[8]);
 
+/* ---- Collision (src/libpsc/psc_collision/psc_collision_impl.hxx:56-252 around
+ * src/include/binary_collision.hxx:57-295): per cell a random permutation, then binary
+ * Coulomb collisions of the pairs (a triangle at half rate when the population is odd).
+ * Psc::step calls it every `interval` steps right after the sort (psc.hxx:363-371). ---- */
+typedef struct
+{
+  int interval;  /* steps between calls (enters the collision frequency) */
+  double nu;     /* collision frequency scale */
+  double cori;   /* grid.norm.cori = 1 / nicell (grid.hxx:288) */
+  int rng;       /* 0: RngFake -- uniform() = .5, identity permutation (binary_collision.hxx:36-41,
+                    the reference's known-answer setting); 1: counter-based streams keyed by
+                    (seed, step, global cell, pair) */
+  uint64_t seed;
+  uint64_t step; /* time step (keys the streams) */
+} psc_b200_collision_params;
+int psc_b200_collide(psc_b200_ctx* ctx, const psc_b200_collision_params* prm, uint64_t* n_collisions);
+
 /* ---- Psc::step (src/include/psc.hxx:321-486): the whole sequence on the stream ---- */
 typedef struct
 {

@@ -19,8 +19,8 @@
 //   Marder         MarderB200           ~ MarderCommon      (marder_impl.hxx:197-264)
 //   Checks         ChecksB200           ~ Checks_           (checks_impl.hxx:33-215)
 //   Balance        BalanceB200          ~ Balance_          (psc_balance_impl.hxx:770-1026)
-//   Collision      CollisionB200        (type only: collisions are out of scope; CollisionViaHostB200
-//                                        = PSC's CollisionCudaHost round trip for a host operator)
+//   Collision      CollisionB200        ~ Collision_ / CollisionHost (psc_collision_impl.hxx:20-274) on the
+//                                        device; CollisionViaHostB200 = PSC's CollisionCudaHost round trip
 //   moments        Moment_n_1st_B200 ...~ ItemMoment<moment_*> (fields_item_moments_1st.hxx:9-37)
 //
 // Every method is one call into libpsc_b200.so (include/psc_b200.h); nothing is computed
@@ -660,31 +660,43 @@ using Moments_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_ALL>;
 template <typename GridT>
 using Moment_rho_1st_nc_B200 = MomentB200<GridT, PSC_B200_MOMENT_RHO_NC>;
 
-// Collision (psc.hxx:111,363-366; decks: `Collision collision{grid, interval, nu}`, e.g.
-// psc_bubble_yz.cxx:303-306).  Binary collisions are not part of this backend; the
-// type exists so that Psc<PscConfig> instantiates.  A deck that leaves collisions off (interval <= 0, the
-// default of the parity runs) is unaffected; asking this type to collide stops the run with a message
-// instead of silently skipping physics.  To keep PSC's host collision operator, use
-// CollisionViaHostB200 below -- the round trip PSC's own CUDA build makes in CollisionCudaHost
-// (libpsc/cuda/collision_cuda_host_impl.hxx:16-33).
+// Collision (psc.hxx:111,363-371; decks: `Collision collision{grid, interval, nu}`, e.g.
+// psc_bubble_yz.cxx:303-306): binary Coulomb collisions inside every cell on the device
+// (psc_b200_collide: CollisionHost's pairing, psc_collision_impl.hxx:56-252, around
+// BinaryCollision, binary_collision.hxx:57-295).  Like the reference's CUDA operator it brings
+// its own random streams (counter-based, keyed by seed / time step / cell / pair); Psc::step
+// calls it right after the sort, which is the order it needs (the pairing walks cell runs; an
+// unordered store is sorted first).  CollisionViaHostB200 below remains for a deck that wants
+// PSC's host operator verbatim (the CollisionCudaHost round trip).
 template <typename GridT>
 struct CollisionB200
 {
   using Mparticles = MparticlesB200<GridT>;
-  CollisionB200(const GridT&, int interval, double nu) : interval_(interval), nu_(nu) {}
+  CollisionB200(const GridT& grid, int interval, double nu, uint64_t seed = 0)
+    : interval_(interval), nu_(nu), cori_(grid.norm.cori), seed_(seed)
+  {}
   int interval() const { return interval_; }
   double nu() const { return nu_; }
-  void operator()(Mparticles&)
+  void operator()(Mparticles& mprts)
   {
-    std::fprintf(stderr,
-                 "psc_b200: binary collisions are not implemented on the device; set the collision interval "
-                 "to 0 or plug a host operator in through CollisionViaHostB200\n");
-    std::abort();
+    psc_b200_collision_params prm;
+    prm.interval = interval_;
+    prm.nu = nu_;
+    prm.cori = cori_;
+    prm.rng = rng_;
+    prm.seed = seed_;
+    prm.step = n_calls_++; // (a fresh stream per call; Psc::step does not hand the time step down)
+    PSC_B200_CHECK(psc_b200_collide(mprts.ctx(), &prm, nullptr));
   }
+  // 0 = RngFake (uniform() = .5, identity permutation): the reference's known-answer setting
+  void set_rng(int rng) { rng_ = rng; }
 
 private:
   int interval_;
-  double nu_;
+  double nu_, cori_;
+  uint64_t seed_;
+  uint64_t n_calls_ = 0;
+  int rng_ = 1;
 };
 
 // Host round trip: the particles come back as PSC's 32-byte records (patch by patch, off[p]..off[p+1]),
@@ -904,7 +916,7 @@ struct PscConfig
   using Balance = BalanceB200<GridT>;
   using Checks = ChecksB200<GridT>;
   using Marder = MarderB200<GridT>;
-  using Collision = CollisionB200<GridT>; // psc.hxx:111 (see CollisionViaHostB200 for PSC's host operator)
+  using Collision = CollisionB200<GridT>; // psc.hxx:111
 #ifdef PSC_B200_WITH_PSC_GRID
   // PSC's own particle output works through accessor() (psc_config.hxx:94)
   using OutputParticles = OutputParticlesDefault<Mparticles>;

@@ -1592,3 +1592,5 @@ const char* po_describe(void)
   return "plain-C restatement of psc-code/psc 1vb hot path (oracle/psc_oracle.c), "
          "gcc -O3 -ffp-contract=off, no -march";
 }
+
+#include "psc_oracle_collision.inc"

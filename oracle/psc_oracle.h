@@ -1,3 +1,4 @@
+#include <stdint.h>
 /* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of psc-code/psc's
  * per-timestep PIC hot path.  Never linked into, imported by or called from the
  * product path (psc_b200/): only tests/, __graft_entry__.smoke() and bench.py's
@@ -199,6 +200,16 @@ void po_energies(const po_grid* g, const float* flds, const po_prt* prts,
 /* Balance: best_mapping / best_mapping_recursive (psc_balance_impl.hxx:99-160): 1-D
  * recursive bisection of the patch list by load, at least one patch per rank;
  * get_loads (psc_balance_impl.hxx:223-269): load = n_prts + factor_fields * n_cells */
+/* ---- binary Coulomb collisions (psc_oracle_collision.inc) ---- */
+#define PO_RNG_FAKE 0 /* RngFake: uniform() = .5, identity permutation (binary_collision.hxx:36-41) */
+#define PO_RNG_HASH 1 /* the counter-based streams shared with the device kernel */
+float po_binary_collision_f(float u1[3], float u2[3], float q1, float m1, float q2, float m2, float nudt1,
+                            float ran1, float ran2);
+double po_binary_collision_d(double u1[3], double u2[3], double q1, double m1, double q2, double m2,
+                             double nudt1, double ran1, double ran2);
+long po_collide(const po_grid* g, po_prt* prts, const unsigned* off, int interval, double nu, double cori,
+                int rng, uint64_t seed, uint64_t step, int patch_begin);
+
 void po_best_mapping(int n_ranks, const double* capability, int n_patches,
                      const double* loads, int* n_patches_by_rank);
 void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,

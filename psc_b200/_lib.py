@@ -37,6 +37,14 @@ class StepParams(C.Structure):
     ]
 
 
+class CollisionParams(C.Structure):
+    """psc_b200_collision_params"""
+    _fields_ = [
+        ("interval", C.c_int), ("nu", C.c_double), ("cori", C.c_double), ("rng", C.c_int),
+        ("seed", C.c_uint64), ("step", C.c_uint64),
+    ]
+
+
 class PscB200Error(RuntimeError):
     pass
 
@@ -102,6 +110,7 @@ def load():
         "psc_b200_check_continuity_begin": [CTX],
         "psc_b200_check_continuity_end": [CTX, C.POINTER(C.c_double)],
         "psc_b200_check_gauss": [CTX, C.POINTER(C.c_double)],
+        "psc_b200_collide": [CTX, C.POINTER(CollisionParams), P],
         "psc_b200_energies": [CTX, P],
         "psc_b200_last_energies": [CTX, P],
         "psc_b200_step": [CTX, C.POINTER(StepParams)],

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GridDesc, StepParams, PscB200Error, load, check, i3, d3, MAX_KINDS
+from ._lib import GridDesc, StepParams, CollisionParams, PscB200Error, load, check, i3, d3, MAX_KINDS
 
 JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS = range(10)
 BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING = range(4)
@@ -45,6 +45,7 @@ class Grid:
             # Grid_t::Normalization, dimensionless (grid.hxx:205-220,265-293): 1/nicell
             fnqs = 1.0 / nicell if nicell else 1.0
         d.fnqs, d.eta = fnqs, eta
+        self.cori = 1.0 / nicell if nicell else 1.0  # grid.norm.cori (grid.hxx:288)
         assert len(kinds) <= MAX_KINDS
         d.n_kinds = len(kinds)
         for k, (q, m) in enumerate(kinds):
@@ -263,6 +264,30 @@ class Sort:
         check(g.lib.psc_b200_sort(g.ctx))
 
 
+class Collision:
+    """CollisionB200: Collision_<Mparticles, ...> (psc_collision_impl.hxx:20-274): binary Coulomb
+    collisions inside every cell, called every `interval` steps right after the sort
+    (psc.hxx:363-371).  rng = 1: counter-based streams keyed by (seed, step, cell, pair);
+    rng = 0: RngFake (the reference's known-answer setting)."""
+
+    def __init__(self, grid, interval, nu, rng=1, seed=0):
+        assert nu > 0.  # psc_collision_impl.hxx:51
+        self.grid_, self.interval_, self.nu, self.rng, self.seed = grid, interval, nu, rng, seed
+        self.n_collisions = 0
+
+    def interval(self):
+        return self.interval_
+
+    def __call__(self, mprts, step=None):
+        g = mprts.grid()
+        prm = CollisionParams(interval=self.interval_, nu=self.nu, cori=g.cori, rng=self.rng, seed=self.seed,
+                              step=g.timestep if step is None else step)
+        n = C.c_uint64()
+        check(g.lib.psc_b200_collide(g.ctx, C.byref(prm), C.byref(n)))
+        self.n_collisions = n.value
+        return n.value
+
+
 class BndParticles:
     """BndParticlesB200 (bnd_particles_impl.hxx:234-247)"""
 
@@ -410,7 +435,8 @@ class Psc:
     sequence through the single C-ABI call psc_b200_step (host C++ driver)."""
 
     def __init__(self, grid, mflds, mprts, sort_interval=1, marder_interval=0,
-                 marder_diffusion=0.9, marder_loop=3, checks=None, fused=False):
+                 marder_diffusion=0.9, marder_loop=3, checks=None, fused=False, collision=None):
+        self.collision = collision
         self.grid_, self.mflds_, self.mprts_ = grid, mflds, mprts
         self.sort_interval, self.marder_interval = sort_interval, marder_interval
         self.marder = Marder(grid, marder_diffusion, marder_loop)
@@ -433,6 +459,10 @@ class Psc:
         t = g.timestep
         do_sort = self.sort_interval > 0 and t % self.sort_interval == 0
         do_marder = self.marder_interval > 0 and t % self.marder_interval == 0
+        if self.collision is not None and self.collision.interval() > 0 and t % self.collision.interval() == 0:
+            # psc.hxx:356-371: sort, then collide (the pairing walks cell runs)
+            self.sort_(mprts)
+            self.collision(mprts, step=t)
         if self.fused:
             prm = StepParams(sort=int(do_sort), marder_loop=self.marder.loop if do_marder else 0,
                              marder_diffusion=self.marder.diffusion, push_fields=1,

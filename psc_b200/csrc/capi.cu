@@ -828,6 +828,11 @@ int psc_b200_bnd_particles(psc_b200_ctx* ctx)
   GUARD(PSC_TRY(store_ready(c)); return op_bnd_particles(c);)
 }
 
+int psc_b200_collide(psc_b200_ctx* ctx, const psc_b200_collision_params* prm, uint64_t* n_collisions)
+{
+  GUARD(PSC_TRY(store_ready(c)); return collide(c, prm, n_collisions);)
+}
+
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
 {
   GUARD(return bnd_add_ghosts(c, id, mb, me);)

@@ -255,6 +255,9 @@ inline int store_ready(Ctx* c)
 // ---- bndp.cu
 int bnd_particles(Ctx* c);
 
+// ---- collision.cu
+int collide(Ctx* c, const psc_b200_collision_params* prm, uint64_t* n_collisions);
+
 // ---- fields.cu
 int flds_create(Ctx* c, int n_comps, int* id);
 int flds_zero(Ctx* c, int id, int mb, int me);

@@ -36,7 +36,7 @@ struct Kind
 // grid.hxx:265-293: dimensionless normalisation, fnqs = 1 / nicell
 struct Normalization
 {
-  double fnqs = 1., eta = 1.;
+  double fnqs = 1., eta = 1., cori = 1.;
 };
 
 // grid.hxx:35-61
@@ -63,6 +63,7 @@ struct Grid
     }
     ldims = domain.ldims;
     norm.fnqs = 1. / nicell;
+    norm.cori = 1. / nicell; // grid.hxx:288
     // "bydim" patch order (libmrc/src/mrc_domain_lib.c:21-35)
     for (int pz = 0; pz < np[2]; pz++) {
       for (int py = 0; py < np[1]; py++) {

@@ -193,7 +193,7 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
     } checks_params;
     checks_params.gauss.err_threshold = 1e30; // the random start is not Gauss-consistent
     typename Config::Checks checks_{grid, 0 /* MPI_Comm */, checks_params};
-    typename Config::Collision collision_{grid, 0, 0.1};
+    typename Config::Collision collision_{grid, 1, 0.1}; // device binary collisions, every step
     typename Config::Sort sort_;
     typename Config::PushParticles pushp_;
     typename Config::BndParticles bndp_{grid};

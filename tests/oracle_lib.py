@@ -60,7 +60,7 @@ def lib():
     if _lib is None:
         path = os.path.join(ORACLE_DIR, "libpsc_oracle.so")
         src = [os.path.join(ORACLE_DIR, f) for f in
-               ("psc_oracle.c", "psc_oracle.h", "psc_oracle_deposit.inc")]
+               ("psc_oracle.c", "psc_oracle.h", "psc_oracle_deposit.inc", "psc_oracle_collision.inc")]
         if (not os.path.exists(path)
                 or os.path.getmtime(path) < max(os.path.getmtime(s) for s in src)):
             build_oracle()
@@ -104,6 +104,12 @@ def lib():
         L.po_energies.argtypes = [G, P, P, P, P]
         L.po_best_mapping.argtypes = [C.c_int, P, C.c_int, P, P]
         L.po_get_loads.argtypes = [G, P, C.c_double, P]
+        L.po_binary_collision_f.restype = C.c_float
+        L.po_binary_collision_f.argtypes = [P, P] + [C.c_float] * 7
+        L.po_binary_collision_d.restype = C.c_double
+        L.po_binary_collision_d.argtypes = [P, P] + [C.c_double] * 7
+        L.po_collide.restype = C.c_long
+        L.po_collide.argtypes = [G, P, P, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
         L.po_describe.restype = C.c_char_p
         _lib = L
     return _lib
@@ -331,6 +337,16 @@ def gauss(grid, rho, flds):
 
 def marder(grid, flds, prts, off, diffusion, loop):
     lib().po_marder_correct(grid.byref(), ptr(flds), ptr(prts), ptr(off), diffusion, loop)
+
+
+RNG_FAKE, RNG_HASH = 0, 1
+
+
+def collide(grid, prts, off, interval, nu, cori, rng=RNG_HASH, seed=0, step=0, patch_begin=0):
+    """CollisionHost::operator() on a cell-sorted store (in place); returns the number of binary collisions"""
+    n = lib().po_collide(grid.byref(), ptr(prts), ptr(off), interval, nu, cori, rng, seed, step, patch_begin)
+    assert n >= 0, "the store is not ordered by cell"
+    return n
 
 
 def energies(grid, flds, prts, off):
