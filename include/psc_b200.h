@@ -215,6 +215,22 @@ typedef struct
 } psc_b200_collision_params;
 int psc_b200_collide(psc_b200_ctx* ctx, const psc_b200_collision_params* prm, uint64_t* n_collisions);
 
+/* ---- Heating (libpsc/psc_heating/psc_heating_impl.hxx:27-76) with the HeatingSpotFoil
+ * profile (include/heating_spot_foil.hxx:6-89): particles inside the spot get a Gaussian
+ * momentum kick of variance H(x, kind) * interval * dt per component.  psc_flatfoil_yz
+ * heats every 20 steps (psc_flatfoil_yz.cxx:464-467, 649-656). ---- */
+typedef struct
+{
+  double zl, zh, xc, yc, rH; /* HeatingSpotFoilParams, internal units */
+  double T[PSC_B200_MAX_KINDS];
+  double Mi;
+  int n_kinds;
+  int interval;              /* heating_dt = interval * dt */
+  uint64_t seed, step;       /* counter-based streams keyed by (seed, step, patch, index) */
+} psc_b200_heating_params;
+int psc_b200_heating_spot_foil(psc_b200_ctx* ctx, const psc_b200_heating_params* prm,
+                               uint64_t* n_kicked);
+
 /* ---- Psc::step (src/include/psc.hxx:321-486): the whole sequence on the stream ---- */
 typedef struct
 {

@@ -699,6 +699,38 @@ private:
   int rng_ = 1;
 };
 
+// Heating (decks: `HeatingSelector<Mparticles>::Heating heating{grid, interval, HeatingSpotFoil<Dim>{grid, params}}`,
+// psc_flatfoil_yz.cxx:556-570; called from the deck's inject/heat lambda, :649-656): the
+// HeatingSpotFoil profile and kick_particle on the device (psc_b200_heating_spot_foil).
+// `Spot` is anything with HeatingSpotFoilParams' members (heating_spot_foil.hxx:6-16).
+template <typename GridT>
+struct HeatingB200
+{
+  using Mparticles = MparticlesB200<GridT>;
+  template <typename Spot>
+  HeatingB200(const GridT&, int interval, const Spot& spot, uint64_t seed = 0)
+  {
+    std::memset(&prm_, 0, sizeof(prm_));
+    prm_.zl = spot.zl, prm_.zh = spot.zh, prm_.xc = spot.xc, prm_.yc = spot.yc, prm_.rH = spot.rH;
+    prm_.Mi = spot.Mi;
+    prm_.n_kinds = spot.n_kinds;
+    for (int k = 0; k < spot.n_kinds && k < PSC_B200_MAX_KINDS; k++) {
+      prm_.T[k] = spot.T[k];
+    }
+    prm_.interval = interval;
+    prm_.seed = seed;
+  }
+  void operator()(Mparticles& mprts)
+  {
+    prm_.step = n_calls_++;
+    PSC_B200_CHECK(psc_b200_heating_spot_foil(mprts.ctx(), &prm_, nullptr));
+  }
+
+private:
+  psc_b200_heating_params prm_;
+  uint64_t n_calls_ = 0;
+};
+
 // Host round trip: the particles come back as PSC's 32-byte records (patch by patch, off[p]..off[p+1]),
 // `collide(prts, off)` changes momenta in place (a lambda around Collision_<MparticlesSingle, ...>), the
 // records go back.  Counts per patch must not change.

@@ -210,6 +210,19 @@ double po_binary_collision_d(double u1[3], double u2[3], double q1, double m1, d
 long po_collide(const po_grid* g, po_prt* prts, const unsigned* off, int interval, double nu, double cori,
                 int rng, uint64_t seed, uint64_t step, int patch_begin);
 
+/* ---- heating (psc_oracle_collision.inc): HeatingSpotFoilParams (heating_spot_foil.hxx:6-16) + cadence/streams */
+typedef struct
+{
+  double zl, zh, xc, yc, rH;
+  double T[PO_MAX_KINDS];
+  double Mi;
+  int n_kinds;
+  int interval;
+  uint64_t seed, step;
+} po_heating_prm;
+double po_heating_spot_foil_H(const po_grid* g, const po_heating_prm* hp, const double crd[3], int kind);
+long po_heating(const po_grid* g, const po_heating_prm* hp, po_prt* prts, const unsigned* off, int patch_begin);
+
 void po_best_mapping(int n_ranks, const double* capability, int n_patches,
                      const double* loads, int* n_patches_by_rank);
 void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,

@@ -45,6 +45,15 @@ class CollisionParams(C.Structure):
     ]
 
 
+class HeatingParams(C.Structure):
+    """psc_b200_heating_params"""
+    _fields_ = [
+        ("zl", C.c_double), ("zh", C.c_double), ("xc", C.c_double), ("yc", C.c_double), ("rH", C.c_double),
+        ("T", C.c_double * MAX_KINDS), ("Mi", C.c_double), ("n_kinds", C.c_int), ("interval", C.c_int),
+        ("seed", C.c_uint64), ("step", C.c_uint64),
+    ]
+
+
 class PscB200Error(RuntimeError):
     pass
 
@@ -111,6 +120,7 @@ def load():
         "psc_b200_check_continuity_end": [CTX, C.POINTER(C.c_double)],
         "psc_b200_check_gauss": [CTX, C.POINTER(C.c_double)],
         "psc_b200_collide": [CTX, C.POINTER(CollisionParams), P],
+        "psc_b200_heating_spot_foil": [CTX, C.POINTER(HeatingParams), P],
         "psc_b200_energies": [CTX, P],
         "psc_b200_last_energies": [CTX, P],
         "psc_b200_step": [CTX, C.POINTER(StepParams)],

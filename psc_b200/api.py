@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GridDesc, StepParams, CollisionParams, PscB200Error, load, check, i3, d3, MAX_KINDS
+from ._lib import GridDesc, StepParams, CollisionParams, HeatingParams, PscB200Error, load, check, i3, d3, MAX_KINDS
 
 JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS = range(10)
 BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING = range(4)
@@ -285,6 +285,28 @@ class Collision:
         n = C.c_uint64()
         check(g.lib.psc_b200_collide(g.ctx, C.byref(prm), C.byref(n)))
         self.n_collisions = n.value
+        return n.value
+
+
+class Heating:
+    """HeatingB200: Heating__ with the HeatingSpotFoil profile (psc_heating_impl.hxx:27-76,
+    heating_spot_foil.hxx:6-89); `spot` = dict(zl, zh, xc, yc, rH, T=[per kind], Mi)"""
+
+    def __init__(self, grid, interval, spot, seed=0):
+        self.grid_, self.interval_, self.spot, self.seed = grid, interval, dict(spot), seed
+        self.n_kicked = 0
+
+    def __call__(self, mprts, step=None):
+        g = mprts.grid()
+        sp = self.spot
+        prm = HeatingParams(zl=sp["zl"], zh=sp["zh"], xc=sp["xc"], yc=sp["yc"], rH=sp["rH"], Mi=sp["Mi"],
+                            n_kinds=len(sp["T"]), interval=self.interval_, seed=self.seed,
+                            step=g.timestep if step is None else step)
+        for k, t in enumerate(sp["T"]):
+            prm.T[k] = t
+        n = C.c_uint64()
+        check(g.lib.psc_b200_heating_spot_foil(g.ctx, C.byref(prm), C.byref(n)))
+        self.n_kicked = n.value
         return n.value
 
 

@@ -833,6 +833,11 @@ int psc_b200_collide(psc_b200_ctx* ctx, const psc_b200_collision_params* prm, ui
   GUARD(PSC_TRY(store_ready(c)); return collide(c, prm, n_collisions);)
 }
 
+int psc_b200_heating_spot_foil(psc_b200_ctx* ctx, const psc_b200_heating_params* prm, uint64_t* n_kicked)
+{
+  GUARD(PSC_TRY(store_ready(c)); return heating_spot_foil(c, prm, n_kicked);)
+}
+
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
 {
   GUARD(return bnd_add_ghosts(c, id, mb, me);)

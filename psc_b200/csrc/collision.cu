@@ -345,3 +345,147 @@ int collide(Ctx* c, const psc_b200_collision_params* prm, uint64_t* n_collisions
 }
 
 } // namespace psc_b200
+
+// ====================================================================== heating
+//
+// Heating__::operator() / kick_particle (libpsc/psc_heating/psc_heating_impl.hxx:27-76) with the
+// HeatingSpotFoil profile (include/heating_spot_foil.hxx:22-89): a particle inside the spot
+// gets a Gaussian momentum kick of variance H(x, kind) * interval * dt per component.  One
+// thread per particle; the six uniforms are counter-based (the reference draws from libc
+// random()) and shared with the oracle.
+
+namespace psc_b200
+{
+
+namespace
+{
+
+struct HeatPrm
+{
+  double zl, zh, xc, yc, rH, Lx, Ly;
+  double fac[pm::MAX_KINDS];
+  double xb_dx[3], corner[3]; // patch origin = off * dx + corner
+  float heating_dt;
+  int np[3], ldims[3];
+  int patch_begin;
+  int xyz;
+  uint64_t seed, step;
+};
+
+__device__ __forceinline__ double sqr_d(double a) { return a * a; }
+
+__device__ double heating_H(const HeatPrm& P, const double crd[3], int kind)
+{
+  const double fac = P.fac[kind];
+  if (fac == 0.0) {
+    return 0.;
+  }
+  if (crd[2] <= P.zl || crd[2] >= P.zh) {
+    return 0.;
+  }
+  if (P.rH == 0) {
+    return fac; // uniform heating, not a spot
+  }
+  const double x = crd[0], y = crd[1], xc = P.xc, yc = P.yc, r2 = P.rH * P.rH, Lx = P.Lx, Ly = P.Ly;
+  if (P.xyz) {
+    return fac * (exp(-(sqr_d(x - (xc)) + sqr_d(y - (yc))) / r2) + exp(-(sqr_d(x - (xc)) + sqr_d(y - (yc + Ly))) / r2) +
+                  exp(-(sqr_d(x - (xc)) + sqr_d(y - (yc - Ly))) / r2) + exp(-(sqr_d(x - (xc + Lx)) + sqr_d(y - (yc))) / r2) +
+                  exp(-(sqr_d(x - (xc + Lx)) + sqr_d(y - (yc + Ly))) / r2) +
+                  exp(-(sqr_d(x - (xc + Lx)) + sqr_d(y - (yc - Ly))) / r2) + exp(-(sqr_d(x - (xc - Lx)) + sqr_d(y - (yc))) / r2) +
+                  exp(-(sqr_d(x - (xc - Lx)) + sqr_d(y - (yc + Ly))) / r2) +
+                  exp(-(sqr_d(x - (xc - Lx)) + sqr_d(y - (yc - Ly))) / r2));
+  }
+  return fac * (exp(-(sqr_d(y - (yc))) / r2) + exp(-(sqr_d(y - (yc + Ly))) / r2) + exp(-(sqr_d(y - (yc - Ly))) / r2));
+}
+
+__global__ void k_heating(HeatPrm P, int n_patches, uint32_t n, const uint32_t* __restrict__ off,
+                          const float4* __restrict__ xi4, float4* __restrict__ pxi4,
+                          unsigned long long* __restrict__ n_kicked)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool kicked = false;
+  if (i < n) {
+    const int p = patch_of(off, n_patches, i);
+    const int gp = P.patch_begin + p;
+    const int idx3[3] = {gp % P.np[0], (gp / P.np[0]) % P.np[1], gp / (P.np[0] * P.np[1])};
+    const float4 X = xi4[i];
+    const float xf[3] = {X.x, X.y, X.z};
+    double xx[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      xx[d] = xf[d] + ((idx3[d] * P.ldims[d]) * P.xb_dx[d] + P.corner[d]);
+    }
+    const int kind = __float_as_int(X.w);
+    const double Hd = heating_H(P, xx, kind);
+    if (Hd > 0.f) {
+      const float H = (float)Hd;
+      float ran[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const uint64_t h = mix64(P.seed ^ mix64(P.step ^ mix64((uint64_t)gp ^ mix64(((uint64_t)(i - off[p]) << 3) | (uint64_t)k))));
+        ran[k] = (float)(h >> 40) * (1.f / 16777216.f);
+      }
+      const float ranx = sqrtf(-2.f * logf((float)(1.0 - ran[0]))) * cosf((float)(2.f * M_PI * ran[1]));
+      const float rany = sqrtf(-2.f * logf((float)(1.0 - ran[2]))) * cosf((float)(2.f * M_PI * ran[3]));
+      const float ranz = sqrtf(-2.f * logf((float)(1.0 - ran[4]))) * cosf((float)(2.f * M_PI * ran[5]));
+      const float Dp = sqrtf(H * P.heating_dt);
+      float4 U = pxi4[i];
+      U.x += Dp * ranx;
+      U.y += Dp * rany;
+      U.z += Dp * ranz;
+      pxi4[i] = U;
+      kicked = true;
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, kicked);
+  if (m && (threadIdx.x & 31) == 0 && n_kicked) {
+    atomicAdd(n_kicked, (unsigned long long)__popc(m));
+  }
+}
+
+} // namespace
+
+int heating_spot_foil(Ctx* c, const psc_b200_heating_params* prm, uint64_t* n_kicked)
+{
+  if (!prm) {
+    return fail("null heating params");
+  }
+  const GridHost& g = c->g;
+  if (prm->n_kinds > g.desc.n_kinds || prm->n_kinds >= PSC_B200_MAX_KINDS) {
+    return fail("heating: n_kinds out of range (heating_spot_foil.hxx:36)");
+  }
+  HeatPrm P{};
+  P.zl = prm->zl, P.zh = prm->zh, P.xc = prm->xc, P.yc = prm->yc, P.rH = prm->rH;
+  P.Lx = g.desc.length[0], P.Ly = g.desc.length[1];
+  const double width = prm->zh - prm->zl;
+  for (int k = 0; k < prm->n_kinds; k++) {
+    P.fac[k] = (8.f * pow(prm->T[k], 1.5)) / (sqrt(prm->Mi) * width);
+  }
+  for (int d = 0; d < 3; d++) {
+    P.xb_dx[d] = g.dx[d];
+    P.corner[d] = g.desc.corner[d];
+    P.np[d] = g.desc.np[d];
+    P.ldims[d] = g.ldims[d];
+  }
+  P.heating_dt = (float)(prm->interval * g.desc.dt);
+  P.patch_begin = g.patch_begin;
+  P.xyz = g.dim == pm::DIM_XYZ;
+  P.seed = prm->seed, P.step = prm->step;
+  PSC_TRY(c->scr[0].reserve(sizeof(unsigned long long)));
+  unsigned long long* d_n = c->scr[0].as<unsigned long long>();
+  PSC_CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), c->stream));
+  if (c->n_prts) {
+    KernelScope ks(c, "heating");
+    k_heating<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(P, g.n_patches, c->n_prts, c->d_off, c->xi(), c->pxi(), d_n);
+    c->n_launches++;
+  }
+  if (n_kicked) {
+    unsigned long long h = 0;
+    PSC_CUDA_TRY(cudaMemcpyAsync(&h, d_n, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_kicked = h;
+  }
+  return check_launch(c, "heating");
+}
+
+} // namespace psc_b200

@@ -257,6 +257,7 @@ int bnd_particles(Ctx* c);
 
 // ---- collision.cu
 int collide(Ctx* c, const psc_b200_collision_params* prm, uint64_t* n_collisions);
+int heating_spot_foil(Ctx* c, const psc_b200_heating_params* prm, uint64_t* n_kicked);
 
 // ---- fields.cu
 int flds_create(Ctx* c, int n_comps, int* id);

@@ -339,6 +339,25 @@ def marder(grid, flds, prts, off, diffusion, loop):
     lib().po_marder_correct(grid.byref(), ptr(flds), ptr(prts), ptr(off), diffusion, loop)
 
 
+class PoHeating(C.Structure):
+    """po_heating_prm"""
+    _fields_ = [("zl", C.c_double), ("zh", C.c_double), ("xc", C.c_double), ("yc", C.c_double), ("rH", C.c_double),
+                ("T", C.c_double * 10), ("Mi", C.c_double), ("n_kinds", C.c_int), ("interval", C.c_int),
+                ("seed", C.c_uint64), ("step", C.c_uint64)]
+
+
+def heating(grid, prts, off, interval, spot, seed=0, step=0, patch_begin=0):
+    """Heating__::operator() with HeatingSpotFoil (in place); returns the number of particles kicked"""
+    hp = PoHeating(zl=spot["zl"], zh=spot["zh"], xc=spot["xc"], yc=spot["yc"], rH=spot["rH"], Mi=spot["Mi"],
+                   n_kinds=len(spot["T"]), interval=interval, seed=seed, step=step)
+    for k, t in enumerate(spot["T"]):
+        hp.T[k] = t
+    L = lib()
+    L.po_heating.restype = C.c_long
+    L.po_heating.argtypes = [C.POINTER(PoGrid), C.POINTER(PoHeating), C.c_void_p, C.c_void_p, C.c_int]
+    return L.po_heating(grid.byref(), C.byref(hp), ptr(prts), ptr(off), patch_begin)
+
+
 RNG_FAKE, RNG_HASH = 0, 1
 
 

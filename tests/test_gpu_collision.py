@@ -97,3 +97,34 @@ def test_psc_steps_with_collisions_conserve():
     assert abs(e_after.sum() - e_before.sum()) < 1e-5 * e_before.sum()
     assert abs(e_after[0] - e_before[0]) > 0  # electrons and ions did exchange energy
     grid.close()
+
+
+SPOT = dict(zl=2., zh=6., xc=4., yc=5., rH=3., T=[0.04, 0., 0.01], Mi=25.)
+
+
+@pytest.mark.parametrize("case", [dict(gdims=(8, 8, 8), length=(8., 8., 8.), np_=(2, 1, 2)),
+                                  dict(gdims=(1, 16, 16), length=(1., 10., 8.), np_=(1, 2, 2), corner=(0., -1., 0.))],
+                         ids=["xyz", "yz"])
+@pytest.mark.parametrize("rH", [3., 0.])
+def test_heating_matches_oracle(case, rH):
+    """Heating__ + HeatingSpotFoil (psc_heating_impl.hxx:27-76, heating_spot_foil.hxx:22-89): same
+    particles kicked, same kicks (shared counter-based streams; libm differs by an ulp or two)"""
+    import psc_b200 as pb
+    kinds = ((-1., 1.), (-1., 1.), (1., 25.))  # flatfoil's three kinds; the second is not heated (T = 0)
+    og = ol.Grid(dt=0.5, kinds=kinds, nicell=10, **case)
+    prts, off = thermal_plasma(og, ppc=5, seed=3, vth=(0.1, 0.1, 0.02))
+    spot = dict(SPOT, rH=rH)
+    grid, mprts, _ = gpu_state(og, None, prts, off)
+    heat = pb.Heating(grid, 20, spot, seed=7)
+    n_gpu = heat(mprts, step=40)
+    got, got_off = mprts.get()
+    ref = prts.copy()
+    n_ref = ol.heating(og, ref, off, 20, spot, seed=7, step=40)
+    assert n_gpu == n_ref and 0 < n_ref < len(prts)
+    changed_ref = np.any(ref["u"] != prts["u"], axis=1)
+    changed_gpu = np.any(got["u"] != prts["u"], axis=1)
+    assert np.array_equal(changed_ref, changed_gpu)
+    assert not changed_ref[prts["kind"] == 1].any()
+    assert got["x"].tobytes() == prts["x"].tobytes()
+    assert np.abs(got["u"].astype(np.float64) - ref["u"]).max() < 2e-5 * np.abs(ref["u"]).max()
+    grid.close()
