@@ -498,12 +498,13 @@ def run_b200(args, rank, world, local_rank):
                     "step_frac": (value / world) * B_STEP / 1e9 / peak,
                     "step_algorithmic_bytes_per_particle": B_STEP}
     # DRAM bytes of one launch of the dominant kernel from the last `ncu --set full`
-    # capture of this workload (profiles/push_traffic.json, written by tools/summarize_ncu.py)
+    # capture of this workload (profiles/push_traffic.json, from tools/ncu_summary.py's dram__bytes lines)
     if roofline:
         try:
             with open(os.path.join(ROOT, "profiles", "push_traffic.json")) as f:
                 tr = json.load(f)
-            if tr.get("particles") == n_prts:
+            # (only if the capture is of THIS kernel and THIS workload: a stale file reads as null)
+            if tr.get("particles") == n_prts and tr.get("kernel_key") == push_key:
                 roofline["traffic"] = tr["dram_bytes_per_launch"]
                 roofline["traffic_source"] = tr.get("source")
         except Exception:
