@@ -490,6 +490,10 @@ class Psc:
                              marder_diffusion=self.marder.diffusion, push_fields=1,
                              checks=int(self.checks.continuity.should_do_check(t)))
             check(g.lib.psc_b200_step(g.ctx, C.byref(prm)))
+            if prm.checks:
+                cont, gauss = C.c_double(), C.c_double()
+                check(g.lib.psc_b200_last_checks(g.ctx, C.byref(cont), C.byref(gauss)))
+                self.checks.continuity.last_max_err, self.checks.gauss.last_max_err = cont.value, gauss.value
             return
         if do_sort:
             self.sort_(mprts)                                    # psc.hxx:356-361

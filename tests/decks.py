@@ -99,15 +99,15 @@ def _grid(dt=None, **kw):
     return ol.Grid(dt=courant_dt(g0), **kw)
 
 
-def bubble_yz(nicell=64, seed=1):
+def bubble_yz(nicell=64, seed=1, gdims=(1, 64, 96), np_=(1, 2, 3)):
     """psc_bubble_yz (src/psc_bubble_yz.cxx:79-105 parameters, :117-146 grid, :155-204
     particles, :209-268 fields), 1 x 64 x 96 cells instead of 1 x 1024 x 1536"""
     BB, nnb, nn0, MMach, TTe, TTi, MMi = .07, .1, 1., 3., .02, .02, 100.
     LLn = 12.5
     LLB = LLn / 6.
     LLy, LLz = 2. * LLn, 3. * LLn
-    og = _grid(gdims=(1, 64, 96), length=(LLn, LLy, LLz), corner=(0., -.5 * LLy, -.5 * LLz),
-               np_=(1, 2, 3), kinds=((-1., 1.), (1., MMi)), nicell=nicell)
+    og = _grid(gdims=gdims, length=(LLn, LLy, LLz), corner=(0., -.5 * LLy, -.5 * LLz),
+               np_=np_, kinds=((-1., 1.), (1., MMi)), nicell=nicell)
     V0 = MMach * np.sqrt(TTe / MMi)
 
     def npt(kind, x, y, z):
@@ -148,7 +148,7 @@ def bubble_yz(nicell=64, seed=1):
     return dict(og=og, flds=flds, prts=prts, off=off, sort_interval=10, marder_interval=0)
 
 
-def harris_yz(nicell=32, seed=2):
+def harris_yz(nicell=32, seed=2, gdims=(1, 64, 128), np_=(1, 2, 4)):
     """psc_harris_yz (src/psc_harris_yz.cxx:209-245 grid / kinds / boundary conditions,
     :262-330 Harris sheet + background, :337-360 fields, :370,395 cadence), 1 x 64 x 128
     cells: B_z = B0 tanh(y / L) with a perturbation, conducting walls in y, periodic z"""
@@ -159,7 +159,7 @@ def harris_yz(nicell=32, seed=2):
     Ly, Lz = 12.8 * L_di * di, 25.6 * L_di * di
     Te = b0 ** 2 / (2. * (1. + Ti_Te))
     Ti = Te * Ti_Te
-    og = _grid(gdims=(1, 64, 128), length=(1., Ly, Lz), corner=(0., -.5 * Ly, 0.), np_=(1, 2, 4),
+    og = _grid(gdims=gdims, length=(1., Ly, Lz), corner=(0., -.5 * Ly, 0.), np_=np_,
                kinds=((1., mass_ratio), (-1., 1.)), nicell=nicell,
                bc_fld_lo=[1, 2, 1], bc_fld_hi=[1, 2, 1], bc_prt_lo=[1, 0, 1], bc_prt_hi=[1, 0, 1])
     # drift speeds that carry the sheet current, split by temperature (Harris equilibrium)
@@ -186,13 +186,13 @@ def harris_yz(nicell=32, seed=2):
     return dict(og=og, flds=flds, prts=prts, off=off, sort_interval=10, marder_interval=100)
 
 
-def kh_xyz(nicell=8, seed=3):
+def kh_xyz(nicell=8, seed=3, gdims=(16, 16, 16), np_=(2, 2, 2), length=(8., 8., 8.)):
     """psc_kelvin_helmholtz (src/psc_kelvin_helmholtz.cxx:66-170: four kinds -- two electron
     and two ion populations --, conducting walls in y, periodic x / z, a sheared E x B flow
     across y), 3D 16 x 16 x 16 cells in 2 x 2 x 2 patches"""
     mi, Te, Ti, B0, v0, delta = 25., .02, .02, .5, .1, 1.2
-    Lx, Ly, Lz = 8., 8., 8.
-    og = _grid(gdims=(16, 16, 16), length=(Lx, Ly, Lz), corner=(0., -.5 * Ly, 0.), np_=(2, 2, 2),
+    Lx, Ly, Lz = length
+    og = _grid(gdims=gdims, length=(Lx, Ly, Lz), corner=(0., -.5 * Ly, 0.), np_=np_,
                kinds=((-1., 1.), (1., mi), (-1., 1.), (1., mi)), nicell=nicell,
                bc_fld_lo=[1, 2, 1], bc_fld_hi=[1, 2, 1], bc_prt_lo=[1, 0, 1], bc_prt_hi=[1, 0, 1])
 
@@ -218,7 +218,7 @@ def kh_xyz(nicell=8, seed=3):
     return dict(og=og, flds=flds, prts=prts, off=off, sort_interval=10, marder_interval=0)
 
 
-def flatfoil_yz(nicell=25, seed=4):
+def flatfoil_yz(nicell=25, seed=4, gdims=(1, 32, 96), np_=(1, 2, 6), length=(1., 32., 96.)):
     """psc_flatfoil_yz (src/psc_flatfoil_yz.cxx:258-279 parameters, :289-343 grid: periodic
     yz, three kinds he_e / e / i with the ions neutralizing, :352-386 background + foil
     target, :110-161 InjectFoil, :461,501 cadence), 1 x 32 x 96 cells instead of the deck's
@@ -228,8 +228,8 @@ def flatfoil_yz(nicell=25, seed=4):
     T_target, bg_n, bg_T = .001, .002, .001
     d_i = np.sqrt(mass_ratio)
     zw = 1. * d_i
-    Ly, Lz = 32., 96.
-    og = _grid(gdims=(1, 32, 96), length=(1., Ly, Lz), corner=(-.5, -.5 * Ly, -.5 * Lz), np_=(1, 2, 6),
+    _, Ly, Lz = length
+    og = _grid(gdims=gdims, length=(1., Ly, Lz), corner=(-.5, -.5 * Ly, -.5 * Lz), np_=np_,
                kinds=((-1., 1.), (-1., 1.), (1., mass_ratio)), nicell=nicell)
 
     def npt(kind, x, y, z):
