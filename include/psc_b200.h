@@ -267,6 +267,14 @@ int psc_b200_mflds_upload_async(psc_b200_ctx* ctx, int field_id, int mb, int me,
                                 const float* host);
 int psc_b200_io_wait(psc_b200_ctx* ctx);
 
+/* ---- checkpoint / restart (src/include/checkpoint.hxx:14-82: write_checkpoint puts "grid",
+ * "mprts", "mflds"; read_checkpoint restores them).  One flat binary per rank, <path>.<rank>,
+ * with PSC's variable decomposition (size_by_patch + one array per particle component,
+ * particles_simple.inl:113-131; ib / im + component-major field patches, fields3d.inl:18-57).
+ * The context that reads must have been created for the same grid and decomposition. ---- */
+int psc_b200_checkpoint_write(psc_b200_ctx* ctx, const char* path, int64_t timestep);
+int psc_b200_checkpoint_read(psc_b200_ctx* ctx, const char* path, int64_t* timestep);
+
 /* ---- multi-GPU: NCCL over NVLink (replaces every MPI site of SURVEY.md 2.3) ---- */
 int psc_b200_nccl_unique_id(void* id128);
 int psc_b200_nccl_init(psc_b200_ctx* ctx, const void* id128);

@@ -919,6 +919,58 @@ struct BalanceB200
   Regrid regrid_;
 };
 
+// write_checkpoint / read_checkpoint / Checkpointing (src/include/checkpoint.hxx:14-133): same
+// names, arguments and cadence rules; the file set is "checkpoint_<timestep>.b200.<rank>"
+// (psc_b200_checkpoint_write: PSC's variable decomposition in a flat binary, no ADIOS2).
+template <typename GridT>
+inline void write_checkpoint(const GridT& grid, MparticlesB200<GridT>& mprts, MfieldsStateB200<GridT>&)
+{
+  const std::string filename = "checkpoint_" + std::to_string(grid.timestep()) + ".b200";
+  PSC_B200_CHECK(psc_b200_checkpoint_write(mprts.ctx(), filename.c_str(), grid.timestep()));
+}
+// (the containers must have been constructed on `grid`, which must describe the run that wrote
+// the checkpoint; returns the time step the checkpoint was written at)
+template <typename GridT>
+inline long read_checkpoint(const std::string& filename, GridT&, MparticlesB200<GridT>& mprts,
+                            MfieldsStateB200<GridT>&)
+{
+  int64_t timestep = 0;
+  PSC_B200_CHECK(psc_b200_checkpoint_read(mprts.ctx(), filename.c_str(), &timestep));
+  return (long)timestep;
+}
+class CheckpointingB200
+{
+public:
+  explicit CheckpointingB200(int interval) : interval_{interval} {}
+  // called every step (checkpoint.hxx:96-113): not right after start-up / restart
+  template <typename GridT>
+  void operator()(const GridT& grid, MparticlesB200<GridT>& mprts, MfieldsStateB200<GridT>& mflds)
+  {
+    if (interval_ <= 0) {
+      return;
+    }
+    if (first_time_) {
+      first_time_ = false;
+      return;
+    }
+    if (grid.timestep() % interval_ == 0) {
+      write_checkpoint(grid, mprts, mflds);
+    }
+  }
+  // after the time loop (checkpoint.hxx:117-126)
+  template <typename GridT>
+  void final(const GridT& grid, MparticlesB200<GridT>& mprts, MfieldsStateB200<GridT>& mflds)
+  {
+    if (interval_ > 0) {
+      write_checkpoint(grid, mprts, mflds);
+    }
+  }
+
+private:
+  int interval_;
+  bool first_time_ = true;
+};
+
 // DiagEnergies (DiagEnergiesField.h:19-42, DiagEnergiesParticle.h:15-40)
 template <typename GridT>
 inline std::array<double, 8> energies(MparticlesB200<GridT>& mprts)

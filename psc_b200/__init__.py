@@ -6,7 +6,7 @@ include/psc_b200.h) plus the C++ wrapper types in include/psc_b200/.  This Pytho
 package is the host-side mirror of the same interface for tests and benchmarks."""
 from ._lib import GridDesc, StepParams, CollisionParams, HeatingParams, PscB200Error, load, check  # noqa: F401
 from .api import (Moment, MOMENT_N, MOMENT_V, MOMENT_P, MOMENT_T, MOMENT_ALL, MOMENT_RHO_NC,  # noqa: F401
-                  Grid, Mparticles, Mfields, MfieldsState, energies, PushParticles, Sort, BndParticles,  # noqa: F401
+                  Grid, Mparticles, Mfields, MfieldsState, energies, write_checkpoint, read_checkpoint, PushParticles, Sort, BndParticles,  # noqa: F401
                   Bnd, BndFields, PushFields, Marder, Checks, Psc, Collision, Heating, PRT_DTYPE,
                   JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS,
                   BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING,

@@ -121,6 +121,8 @@ def load():
         "psc_b200_check_gauss": [CTX, C.POINTER(C.c_double)],
         "psc_b200_collide": [CTX, C.POINTER(CollisionParams), P],
         "psc_b200_heating_spot_foil": [CTX, C.POINTER(HeatingParams), P],
+        "psc_b200_checkpoint_write": [CTX, C.c_char_p, C.c_int64],
+        "psc_b200_checkpoint_read": [CTX, C.c_char_p, C.POINTER(C.c_int64)],
         "psc_b200_energies": [CTX, P],
         "psc_b200_last_energies": [CTX, P],
         "psc_b200_step": [CTX, C.POINTER(StepParams)],

@@ -443,6 +443,23 @@ class Checks:
         self.gauss = _Gauss(grid, gauss_interval)
 
 
+def write_checkpoint(grid, path=None):
+    """write_checkpoint (checkpoint.hxx:14-46): grid + mprts + mflds of this rank -> <path>.<rank>;
+    default name as the reference's, "checkpoint_<timestep>.b200" """
+    path = path or "checkpoint_%d.b200" % grid.timestep
+    check(grid.lib.psc_b200_checkpoint_write(grid.ctx, path.encode(), grid.timestep))
+    return path
+
+
+def read_checkpoint(path, grid):
+    """read_checkpoint (checkpoint.hxx:52-82) into a context created for the same grid; restores
+    the time step too"""
+    t = C.c_int64()
+    check(grid.lib.psc_b200_checkpoint_read(grid.ctx, path.encode(), C.byref(t)))
+    grid.timestep = t.value
+    return t.value
+
+
 def energies(grid):
     """DiagEnergies: [EX2 EY2 EZ2 HX2 HY2 HZ2 E_electron E_ion]"""
     out = np.zeros(8, dtype=np.float64)

@@ -838,6 +838,16 @@ int psc_b200_heating_spot_foil(psc_b200_ctx* ctx, const psc_b200_heating_params*
   GUARD(PSC_TRY(store_ready(c)); return heating_spot_foil(c, prm, n_kicked);)
 }
 
+int psc_b200_checkpoint_write(psc_b200_ctx* ctx, const char* path, int64_t timestep)
+{
+  GUARD(PSC_TRY(store_ready(c)); return checkpoint_write(c, path, timestep);)
+}
+
+int psc_b200_checkpoint_read(psc_b200_ctx* ctx, const char* path, int64_t* timestep)
+{
+  GUARD(return checkpoint_read(c, path, timestep);)
+}
+
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
 {
   GUARD(return bnd_add_ghosts(c, id, mb, me);)

@@ -296,6 +296,10 @@ int comm_exchange_particles(Ctx* c, const float4* xi_src, const float4* pxi_src,
 int comm_allreduce_max(Ctx* c, double* v, int n);
 int comm_allreduce_sum(Ctx* c, double* v, int n);
 
+// ---- checkpoint.cu
+int checkpoint_write(Ctx* c, const char* path, int64_t timestep);
+int checkpoint_read(Ctx* c, const char* path, int64_t* timestep);
+
 // ---- tables
 int build_patch_tables(Ctx* c);
 
