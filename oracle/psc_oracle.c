@@ -969,23 +969,147 @@ static void cw_J(const po_grid* g, float* F, int d, int hi)
   }
 }
 
+/* ---- BND_FLD_OPEN (psc_bnd_fields_impl.hxx:210-300 set_lower/upper_ghosts with
+ * include_edge = false, :535-640 radiative_H_lo/hi; no incoming pulse, background_e = background_h = 0
+ * as the decks leave them).  E: every ghost of the three E components behind the wall is set to the
+ * background.  H: first-order absorbing condition for the two tangential components in the first
+ * ghost plane.  The reference's loop also evaluates H0(edge - 1) one index below the array at the
+ * outermost transverse ghost line (an out-of-bounds read there); the restatement takes the
+ * difference as zero on that line -- nothing reads those corner values. */
+static void open_E(const po_grid* g, float* F, int d, int hi)
+{
+  int lo3[3], hi3[3];
+  for (int a = 0; a < 3; a++) {
+    lo3[a] = g->ib[a];
+    hi3[a] = g->ib[a] + g->im[a];
+  }
+  if (g->invar[d]) {
+    return;
+  }
+  if (!hi) {
+    hi3[d] = 0; /* stop[d] = 0 (:223) */
+  } else {
+    lo3[d] = g->ldims[d] + 1; /* start[d] = ldims + 1 (:270) */
+  }
+  for (int m = PO_EX; m < PO_EX + 3; m++) {
+    for (int k = lo3[2]; k < hi3[2]; k++) {
+      for (int j = lo3[1]; j < hi3[1]; j++) {
+        for (int i = lo3[0]; i < hi3[0]; i++) {
+          FLD(F, g, m, i, j, k) = 0.f;
+        }
+      }
+    }
+  }
+  if (hi) {
+    /* upper edge plane (:281-296): the component normal to the wall is not on the edge */
+    lo3[d] = g->ldims[d];
+    hi3[d] = g->ldims[d] + 1;
+    const int m = PO_EX + d;
+    for (int k = lo3[2]; k < hi3[2]; k++) {
+      for (int j = lo3[1]; j < hi3[1]; j++) {
+        for (int i = lo3[0]; i < hi3[0]; i++) {
+          FLD(F, g, m, i, j, k) = 0.f;
+        }
+      }
+    }
+  }
+}
+
+static void open_H(const po_grid* g, float* F, int d, int hi)
+{
+  if (g->invar[d]) {
+    return;
+  }
+  const float dt = (float)g->dt;
+  float dtdx[3];
+  for (int a = 0; a < 3; a++) {
+    dtdx[a] = dt * (float)g->dx_inv[a];
+  }
+  const int d0 = d, d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+  const int H0 = PO_HX + d0, H1 = PO_HX + d1, H2 = PO_HX + d2;
+  const int E1 = PO_EX + d1, E2 = PO_EX + d2;
+  const int J1 = PO_JXI + d1, J2 = PO_JXI + d2;
+  int lo3[3], hi3[3];
+  for (int a = 0; a < 3; a++) {
+    lo3[a] = g->ib[a];
+    hi3[a] = g->ib[a] + g->im[a];
+  }
+  lo3[d0] = hi ? g->ldims[d0] : -1;
+  hi3[d0] = lo3[d0] + 1;
+#define AT(m, q) FLD(F, g, m, (q)[0], (q)[1], (q)[2])
+  for (int k = lo3[2]; k < hi3[2]; k++) {
+    for (int j = lo3[1]; j < hi3[1]; j++) {
+      for (int i = lo3[0]; i < hi3[0]; i++) {
+        int i3[3] = {i, j, k}, e[3] = {i, j, k}, e_m2[3], e_m1[3];
+        e[d0] += hi ? -1 : 1; /* edge_idx */
+        /* the point the H0 differences are taken at: edge_idx (lo) / i3 (hi) */
+        int* at = hi ? i3 : e;
+        for (int a = 0; a < 3; a++) {
+          e_m2[a] = e_m1[a] = at[a];
+        }
+        float dH0_2 = 0.f, dH0_1 = 0.f;
+        if (!g->invar[d2] && at[d2] - 1 >= g->ib[d2]) {
+          e_m2[d2] -= 1;
+          dH0_2 = AT(H0, at) - AT(H0, e_m2);
+        }
+        if (!g->invar[d1] && at[d1] - 1 >= g->ib[d1]) {
+          e_m1[d1] -= 1;
+          dH0_1 = AT(H0, at) - AT(H0, e_m1);
+        }
+        if (!hi) {
+          AT(H2, i3) = (4.f * 0.f - 2.f * (AT(E1, e) - 0.f) - dtdx[d2] * dH0_2 - (1.f - dtdx[d0]) * (AT(H2, e) - 0.f) +
+                        dt * AT(J1, e)) /
+                         (1.f + dtdx[d0]) +
+                       0.f;
+          AT(H1, i3) = (-4.f * 0.f + 2.f * (AT(E2, e) - 0.f) - dtdx[d1] * dH0_1 - (1.f - dtdx[d0]) * (AT(H1, e) - 0.f) +
+                        dt * AT(J2, e)) /
+                         (1.f + dtdx[d0]) +
+                       0.f;
+        } else {
+          AT(H2, i3) = (-4.f * 0.f + 2.f * (AT(E1, i3) - 0.f) + dtdx[d2] * dH0_2 - (1.f - dtdx[d0]) * (AT(H2, e) - 0.f) -
+                        dt * AT(J1, i3)) /
+                         (1.f + dtdx[d0]) +
+                       0.f;
+          AT(H1, i3) = (4.f * 0.f - 2.f * (AT(E2, i3) - 0.f) + dtdx[d1] * dH0_1 - (1.f - dtdx[d0]) * (AT(H1, e) - 0.f) -
+                        dt * AT(J2, i3)) /
+                         (1.f + dtdx[d0]) +
+                       0.f;
+        }
+      }
+    }
+  }
+#undef AT
+}
+
+static void open_J(const po_grid* g, float* F, int d, int hi)
+{ /* add_ghosts_J: BND_FLD_OPEN does nothing (:169-171) */
+  (void)g, (void)F, (void)d, (void)hi;
+}
+
 /* psc_bnd_fields_impl.hxx:27-188: per patch, lo for d=0..2 then hi for d=0..2 */
 static void bndf_apply(const po_grid* g, float* flds,
-                       void (*cw)(const po_grid*, float*, int, int))
+                       void (*cw)(const po_grid*, float*, int, int),
+                       void (*open)(const po_grid*, float*, int, int))
 {
   long plen = po_fld_patch_len(g) * PO_NR_FIELDS;
   for (int p = 0; p < g->n_patches; p++) {
     float* F = flds + p * plen;
     for (int d = 0; d < 3; d++) {
-      if (at_boundary_lo(g, p, d) &&
-          g->bc_fld_lo[d] == PO_BND_FLD_CONDUCTING_WALL) {
-        cw(g, F, d, 0);
+      if (at_boundary_lo(g, p, d)) {
+        if (g->bc_fld_lo[d] == PO_BND_FLD_CONDUCTING_WALL) {
+          cw(g, F, d, 0);
+        } else if (g->bc_fld_lo[d] == PO_BND_FLD_OPEN) {
+          open(g, F, d, 0);
+        }
       }
     }
     for (int d = 0; d < 3; d++) {
-      if (at_boundary_hi(g, p, d) &&
-          g->bc_fld_hi[d] == PO_BND_FLD_CONDUCTING_WALL) {
-        cw(g, F, d, 1);
+      if (at_boundary_hi(g, p, d)) {
+        if (g->bc_fld_hi[d] == PO_BND_FLD_CONDUCTING_WALL) {
+          cw(g, F, d, 1);
+        } else if (g->bc_fld_hi[d] == PO_BND_FLD_OPEN) {
+          open(g, F, d, 1);
+        }
       }
     }
   }
@@ -993,15 +1117,15 @@ static void bndf_apply(const po_grid* g, float* flds,
 
 void po_bndf_fill_ghosts_E(const po_grid* g, float* flds)
 {
-  bndf_apply(g, flds, cw_E);
+  bndf_apply(g, flds, cw_E, open_E);
 }
 void po_bndf_fill_ghosts_H(const po_grid* g, float* flds)
 {
-  bndf_apply(g, flds, cw_H);
+  bndf_apply(g, flds, cw_H, open_H);
 }
 void po_bndf_add_ghosts_J(const po_grid* g, float* flds)
 {
-  bndf_apply(g, flds, cw_J);
+  bndf_apply(g, flds, cw_J, open_J);
 }
 
 /* ====================================================================== */
@@ -1329,6 +1453,15 @@ double po_continuity(const po_grid* g, const float* rho_m, const float* rho_p,
                         SC(rho_m + p * plen1, g, i, j, k);
           double v =
             (double)d_rho + g->dt * (double)SC(divj + p * plen1, g, i, j, k);
+          /* checks_impl.hxx:78-90: div j := -d rho / dt in the first cell layer at a lower open boundary */
+          {
+            int idx3[3] = {i, j, k};
+            for (int d = 0; d < 3; d++) {
+              if (at_boundary_lo(g, p, d) && idx3[d] == 0 && g->bc_fld_lo[d] == PO_BND_FLD_OPEN) {
+                v = 0.;
+              }
+            }
+          }
           if (fabs(v) > err) {
             err = fabs(v);
           }

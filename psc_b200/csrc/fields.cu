@@ -491,9 +491,15 @@ __global__ void k_div_nc(GridDev G, DxDev D, const float* __restrict__ F, long s
 }
 
 // checks_impl.hxx:60-97: max | rho_p - rho_m + dt * div J |
-__global__ void k_continuity(GridDev G, DxDev D, double dt, const float* __restrict__ F,
+struct OpenLoDev
+{
+  int lo[3]; // BND_FLD_OPEN at the lower domain boundary in dim d
+};
+
+__global__ void k_continuity(GridDev G, DxDev D, OpenLoDev O, double dt, const float* __restrict__ F,
                              long slot_len, const float* __restrict__ rho_m,
-                             const float* __restrict__ rho_p, double* __restrict__ err)
+                             const float* __restrict__ rho_p, const pm::PatchBnd* __restrict__ pbs,
+                             double* __restrict__ err)
 {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.;
@@ -504,6 +510,16 @@ __global__ void k_continuity(GridDev G, DxDev D, double dt, const float* __restr
     float d_rho = rho_p[o] - rho_m[o];
     float divj = div_nc_at(G, D, F + p * slot_len, pm::JXI, i, j, k);
     v = fabs((double)d_rho + dt * (double)divj);
+    // checks_impl.hxx:78-90: particles enter / leave through a lower open boundary: div j is
+    // DEFINED as -d rho / dt in the first cell layer there
+    const int c3[3] = {i, j, k};
+    const int at_lo = pbs[p].at_lo;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (O.lo[d] && ((at_lo >> d) & 1) && c3[d] == 0) {
+        v = 0.;
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -781,6 +797,129 @@ int bnd_add_ghosts(Ctx* c, int id, int mb, int me)
 
 // ---------------------------------------------------------------- BndFields
 
+// ---- BND_FLD_OPEN (psc_bnd_fields_impl.hxx:210-300 set_lower/upper_ghosts with include_edge =
+// false; :535-640 radiative_H_lo/hi without an incoming pulse; background_e = background_h = 0).
+// One thread per point of the patch array; `d` is the wall's direction.
+struct OpenDev
+{
+  float dt, dtdx[3];
+};
+
+// E: every ghost of the three E components behind the wall := background (0); at the upper wall
+// the normal component is a ghost already in the edge plane
+__global__ void k_open_E(GridDev G, float* __restrict__ F, long slot_len, int d, int hi,
+                         const pm::PatchBnd* __restrict__ pbs)
+{
+  const size_t per = (size_t)G.fld_len;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * G.n_patches) {
+    return;
+  }
+  const int p = (int)(idx / per);
+  size_t r = idx - (size_t)p * per;
+  const int c3[3] = {(int)(r % G.im[0]) - G.ibn[0], (int)((r / G.im[0]) % G.im[1]) - G.ibn[1],
+                     (int)(r / ((size_t)G.im[0] * G.im[1])) - G.ibn[2]};
+  const pm::PatchBnd pb = pbs[p];
+  if (!(((hi ? pb.at_hi : pb.at_lo) >> d) & 1)) {
+    return;
+  }
+  float* Fp = F + p * slot_len;
+  const bool ghost = hi ? c3[d] >= G.ldims[d] + 1 : c3[d] < 0;
+  const bool edge = hi && c3[d] == G.ldims[d];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    if (ghost || (edge && m == d)) {
+      Fp[fld_off(G, pm::EX + m, c3[0], c3[1], c3[2])] = 0.f;
+    }
+  }
+}
+
+// H: first-order absorbing condition for the two tangential components in the first ghost plane
+__global__ void k_open_H(GridDev G, OpenDev O, float* __restrict__ F, long slot_len, int d, int hi,
+                         const pm::PatchBnd* __restrict__ pbs)
+{
+  const int d0 = d, d1 = (d + 1) % 3, d2 = (d + 2) % 3;
+  const size_t plane = (size_t)G.im[d1] * G.im[d2];
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= plane * G.n_patches) {
+    return;
+  }
+  const int p = (int)(idx / plane);
+  size_t r = idx - (size_t)p * plane;
+  const pm::PatchBnd pb = pbs[p];
+  if (!(((hi ? pb.at_hi : pb.at_lo) >> d) & 1)) {
+    return;
+  }
+  int i3[3], e[3];
+  i3[d0] = hi ? G.ldims[d0] : -1;
+  i3[d1] = (int)(r % G.im[d1]) - G.ibn[d1];
+  i3[d2] = (int)(r / G.im[d1]) - G.ibn[d2];
+  e[0] = i3[0], e[1] = i3[1], e[2] = i3[2];
+  e[d0] += hi ? -1 : 1; // edge_idx
+  float* Fp = F + p * slot_len;
+  auto at = [&](int m, const int* q) -> float& { return Fp[fld_off(G, m, q[0], q[1], q[2])]; };
+  const int H0 = pm::HX + d0, H1 = pm::HX + d1, H2 = pm::HX + d2;
+  const int E1 = pm::EX + d1, E2 = pm::EX + d2, J1 = pm::JXI + d1, J2 = pm::JXI + d2;
+  // the H0 differences are taken at edge_idx (lo) / i3 (hi); one index below the array (the
+  // reference reads out of bounds there) the difference is taken as zero
+  const int* q = hi ? i3 : e;
+  int qm[3] = {q[0], q[1], q[2]};
+  float dH0_2 = 0.f, dH0_1 = 0.f;
+  if (G.im[d2] > 1 && q[d2] - 1 >= -G.ibn[d2]) {
+    qm[d2] -= 1;
+    dH0_2 = at(H0, q) - at(H0, qm);
+    qm[d2] += 1;
+  }
+  if (G.im[d1] > 1 && q[d1] - 1 >= -G.ibn[d1]) {
+    qm[d1] -= 1;
+    dH0_1 = at(H0, q) - at(H0, qm);
+  }
+  const float dt = O.dt;
+  if (!hi) {
+    at(H2, i3) = (4.f * 0.f - 2.f * (at(E1, e) - 0.f) - O.dtdx[d2] * dH0_2 - (1.f - O.dtdx[d0]) * (at(H2, e) - 0.f) +
+                  dt * at(J1, e)) /
+                   (1.f + O.dtdx[d0]) +
+                 0.f;
+    at(H1, i3) = (-4.f * 0.f + 2.f * (at(E2, e) - 0.f) - O.dtdx[d1] * dH0_1 - (1.f - O.dtdx[d0]) * (at(H1, e) - 0.f) +
+                  dt * at(J2, e)) /
+                   (1.f + O.dtdx[d0]) +
+                 0.f;
+  } else {
+    at(H2, i3) = (-4.f * 0.f + 2.f * (at(E1, i3) - 0.f) + O.dtdx[d2] * dH0_2 - (1.f - O.dtdx[d0]) * (at(H2, e) - 0.f) -
+                  dt * at(J1, i3)) /
+                   (1.f + O.dtdx[d0]) +
+                 0.f;
+    at(H1, i3) = (4.f * 0.f - 2.f * (at(E2, i3) - 0.f) + O.dtdx[d1] * dH0_1 - (1.f - O.dtdx[d0]) * (at(H1, e) - 0.f) -
+                  dt * at(J2, i3)) /
+                   (1.f + O.dtdx[d0]) +
+                 0.f;
+  }
+}
+
+template <int OP>
+static int bndf_open(Ctx* c, int d, int hi, const char* name)
+{
+  const GridHost& g = c->g;
+  if (g.invar[d] || OP == CW_J) {
+    return 0; // (add_ghosts_J: BND_FLD_OPEN does nothing, psc_bnd_fields_impl.hxx:169-171)
+  }
+  KernelScope ks(c, name);
+  if (OP == CW_E) {
+    const size_t n = (size_t)c->gd.fld_len * c->gd.n_patches;
+    k_open_E<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(0), c->fld_slot_len(0), d, hi, c->d_patch_bnd);
+  } else {
+    OpenDev O;
+    O.dt = (float)g.desc.dt;
+    for (int a = 0; a < 3; a++) {
+      O.dtdx[a] = O.dt * (float)g.dx_inv[a];
+    }
+    const size_t n = (size_t)c->gd.im[(d + 1) % 3] * c->gd.im[(d + 2) % 3] * c->gd.n_patches;
+    k_open_H<<<div_up(n, 128), 128, 0, c->stream>>>(c->gd, O, c->fld(0), c->fld_slot_len(0), d, hi, c->d_patch_bnd);
+  }
+  c->n_launches++;
+  return 0;
+}
+
 template <int OP>
 static int bndf_apply(Ctx* c, const char* name)
 {
@@ -789,6 +928,10 @@ static int bndf_apply(Ctx* c, const char* name)
   for (int hi = 0; hi < 2; hi++) {
     for (int d = 0; d < 3; d++) {
       int bc = hi ? g.desc.bc_fld_hi[d] : g.desc.bc_fld_lo[d];
+      if (bc == PSC_B200_BND_FLD_OPEN) {
+        PSC_TRY(bndf_open<OP>(c, d, hi, name));
+        continue;
+      }
       if (bc != PSC_B200_BND_FLD_CONDUCTING_WALL) {
         continue;
       }
@@ -1146,9 +1289,13 @@ int check_continuity_end(Ctx* c, double* err)
   double* d_err = c->scr[8].as<double>() + 2;
   PSC_CUDA_TRY(cudaMemsetAsync(d_err, 0, sizeof(double), c->stream));
   size_t n = (size_t)c->gd.n_patches * c->gd.n_cells;
-  k_continuity<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, make_dx(c), c->g.desc.dt, c->fld(0),
+  OpenLoDev O;
+  for (int d = 0; d < 3; d++) {
+    O.lo[d] = c->g.desc.bc_fld_lo[d] == PSC_B200_BND_FLD_OPEN;
+  }
+  k_continuity<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, make_dx(c), O, c->g.desc.dt, c->fld(0),
                                                      c->fld_slot_len(0), c->fld(c->rho_m_id),
-                                                     c->fld(c->rho_p_id), d_err);
+                                                     c->fld(c->rho_p_id), c->d_patch_bnd, d_err);
   c->n_launches++;
   PSC_TRY(check_launch(c, "continuity"));
   PSC_TRY(read_max(c, d_err, err));

@@ -121,10 +121,11 @@ inline bool grid_setup(const psc_b200_grid_desc& desc, GridHost& g, std::string&
       g.desc.bc_prt_lo[d] = g.desc.bc_prt_hi[d] = PSC_B200_BND_PRT_PERIODIC;
     }
     for (int bc : {g.desc.bc_fld_lo[d], g.desc.bc_fld_hi[d]}) {
-      if (bc != PSC_B200_BND_FLD_PERIODIC && bc != PSC_B200_BND_FLD_CONDUCTING_WALL) {
-        // psc_bnd_fields_impl.hxx:535-640 (BND_FLD_OPEN) is not built; the reference itself
-        // asserts on BND_FLD_ABSORBING.  Running with untouched ghost cells would be wrong physics.
-        err = "field boundary conditions other than periodic / conducting wall are not implemented";
+      if (bc != PSC_B200_BND_FLD_PERIODIC && bc != PSC_B200_BND_FLD_CONDUCTING_WALL &&
+          bc != PSC_B200_BND_FLD_OPEN) {
+        // the reference itself asserts on BND_FLD_ABSORBING (psc_bnd_fields_impl.hxx:48-50);
+        // running with untouched ghost cells would be wrong physics
+        err = "field boundary condition BND_FLD_ABSORBING is not implemented (nor is it in PSC)";
         return false;
       }
     }

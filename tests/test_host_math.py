@@ -131,3 +131,27 @@ def test_best_mapping_known_answer():
     start = np.concatenate([[0], np.cumsum(out)])
     r = np.searchsorted(start, 3, side="right") - 1
     assert out[r] <= 2
+
+
+def test_grid_setup_accepts_open_and_rejects_absorbing_field_bc():
+    """BND_FLD_OPEN is implemented (psc_bnd_fields_impl.hxx:210-300,535-640); BND_FLD_ABSORBING is not --
+    the reference asserts on it -- and must be refused instead of running with untouched ghost cells"""
+    import ctypes as C
+    import psc_b200
+    from b200_helpers import desc_from_grid
+    import oracle_lib as ol
+    lib = psc_b200.load()
+    for bc, ok_expected in ((0, True), (3, False)):
+        og = ol.Grid(gdims=(8, 8, 8), length=(8., 8., 8.), np_=(1, 1, 1), dt=0.1, kinds=((-1., 1.),), nicell=1,
+                     bc_fld_lo=[1, 1, bc], bc_fld_hi=[1, 1, bc], bc_prt_lo=[1, 1, 2], bc_prt_hi=[1, 1, 2])
+        d = desc_from_grid(og)
+        ctx = C.c_void_p()
+        rc = lib.psc_b200_create(C.byref(d), C.byref(ctx))
+        msg = lib.psc_b200_last_error().decode()
+        if rc == 0:
+            lib.psc_b200_destroy(ctx)
+        if ok_expected:
+            # (no GPU here: creation fails later, on the missing device, not on the grid)
+            assert rc == 0 or "ABSORBING" not in msg
+        else:
+            assert rc != 0 and "ABSORBING" in msg
