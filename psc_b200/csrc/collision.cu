@@ -61,7 +61,7 @@ __device__ __forceinline__ float coll_u01(uint64_t h)
 
 // BinaryCollision::operator() (binary_collision.hxx:57-295), real_t = float.  ran1, ran2 are
 // the two rng.uniform() draws.  Returns nudt.
-__device__ float binary_collision(float u1[3], float u2[3], float q1, float m1, float q2, float m2, float nudt1,
+__device__ __noinline__ float binary_collision(float u1[3], float u2[3], float q1, float m1, float q2, float m2, float nudt1,
                                   float ran1, float ran2)
 {
   float px1 = u1[0], py1 = u1[1], pz1 = u1[2];
@@ -186,6 +186,15 @@ __device__ float binary_collision(float u1[3], float u2[3], float q1, float m1, 
   return nudt;
 }
 
+// One warp takes 32 consecutive cells.  Cells with more than COLL_SMALL particles are walked
+// one after the other by the whole warp (permutation by a bitonic sort in shared memory, then
+// one pair per lane); the small ones -- a deck's background plasma has 2-3 particles in most
+// cells -- are taken one cell per LANE (insertion sort of its few keys, its pairs in sequence),
+// so that a warp of 32 two-particle cells issues one collision with 32 lanes instead of 32
+// collisions with one lane each.  Which lane does what never changes the result: keys, pairs
+// and random numbers are functions of (seed, step, cell, index) only.
+constexpr int COLL_SMALL = 8;
+
 __global__ void __launch_bounds__(COLL_WARPS * 32)
   k_collide(GridDev G, CollPrm P, uint32_t nct, const uint32_t* __restrict__ cell_off,
             const float4* __restrict__ xi4, float4* __restrict__ pxi4, unsigned long long* __restrict__ n_coll)
@@ -193,20 +202,17 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
   __shared__ uint64_t sk_all[COLL_WARPS][COLL_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* const sk = sk_all[warp];
-  const uint32_t g = blockIdx.x * COLL_WARPS + warp;
-  if (g >= nct) {
+  const uint32_t g0 = (blockIdx.x * COLL_WARPS + warp) * 32u;
+  if (g0 >= nct) {
     return;
   }
-  const uint32_t cb = __ldg(&cell_off[g]), ce = __ldg(&cell_off[g + 1]);
-  const int nn = (int)(ce - cb);
-  if (nn < 2) {
-    return; // can't collide only one (or zero) particles (:223-225)
-  }
-  const uint64_t gcell = P.cell0 + g;
+  const uint32_t my_g = min(g0 + (uint32_t)lane, nct - 1);
+  const uint32_t my_cb = __ldg(&cell_off[my_g]);
+  const int my_nn = g0 + lane < nct ? (int)(__ldg(&cell_off[my_g + 1]) - my_cb) : 0;
   unsigned long long my_coll = 0;
 
-  // one binary collision between records a and b (indices into the store)
-  auto do_bc = [&](uint32_t a, uint32_t b, float nudt1, uint64_t s0, uint64_t j) {
+  // one binary collision between records a and b (indices into the store) of global cell gcell
+  auto do_bc = [&](uint32_t a, uint32_t b, float nudt1, uint64_t gcell, uint64_t s0, uint64_t j) {
     float4 ua = pxi4[a], ub = pxi4[b];
     const int ka = __float_as_int(xi4[a].w), kb = __float_as_int(xi4[b].w);
     float u1[3] = {ua.x, ua.y, ua.z}, u2[3] = {ub.x, ub.y, ub.z};
@@ -217,73 +223,116 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
     pxi4[b] = make_float4(u2[0], u2[1], u2[2], ub.w);
     my_coll++;
   };
+  // all particles need to have same weight (:227-229): nudt1 from the first of the permutation
+  auto nudt1_of = [&](uint32_t f, int nn) {
+    const int kf = __float_as_int(xi4[f].w);
+    const float wni = pxi4[f].w / P.q[kf];
+    return (float)((double)wni * P.cori * nn * P.interval * P.dt * P.nu);
+  };
 
-  for (int s0 = 0; s0 < nn; s0 += COLL_CAP) {
-    const int m = min(COLL_CAP, nn - s0);
-    if (m < 2) {
-      break;
-    }
-    // ---- randomize_in_cell (:160-166): sort composite keys (random 40 bits, index)
-    int m2 = 2;
-    while (m2 < m) {
-      m2 <<= 1;
-    }
-    for (int i = lane; i < m2; i += 32) {
-      uint64_t key = ~0ull; // padding sorts to the end
-      if (i < m) {
-        key = P.rng ? (((coll_hash(P.seed, P.step, gcell, (uint64_t)(s0 + i), 0) >> 24) << 24) | (uint64_t)i)
-                    : (uint64_t)i;
+  // ---- small cells: one cell per lane
+  if (my_nn >= 2 && my_nn <= COLL_SMALL) {
+    const uint64_t gcell = P.cell0 + my_g;
+    uint64_t* const k8 = sk + lane * COLL_SMALL; // this lane's keys
+    for (int i = 0; i < my_nn; i++) {
+      // insertion sort of the composite keys (random 40 bits, index)
+      const uint64_t key = P.rng ? (((coll_hash(P.seed, P.step, gcell, (uint64_t)i, 0) >> 24) << 24) | (uint64_t)i)
+                                 : (uint64_t)i;
+      int j = i;
+      while (j > 0 && k8[j - 1] > key) {
+        k8[j] = k8[j - 1];
+        j--;
       }
-      sk[i] = key;
+      k8[j] = key;
     }
-    __syncwarp();
-    if (P.rng) {
-      for (int k = 2; k <= m2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int t = lane; t < (m2 >> 1); t += 32) {
-            // t-th compare-exchange of this stage
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const int l = i | j;
-            const bool up = (i & k) == 0;
-            const uint64_t a = sk[i], b = sk[l];
-            if ((a > b) == up) {
-              sk[i] = b;
-              sk[l] = a;
+    const float nudt1 = nudt1_of(my_cb + (uint32_t)(k8[0] & 0xffffffu), my_nn);
+    int n = 0, jp = 0;
+    if (my_nn & 1) { // odd # of particles: do 3-collision (:235-240)
+      const uint32_t p0 = my_cb + (uint32_t)(k8[0] & 0xffffffu), p1 = my_cb + (uint32_t)(k8[1] & 0xffffffu),
+                     p2 = my_cb + (uint32_t)(k8[2] & 0xffffffu);
+      const float half = (float)(.5 * (double)nudt1);
+      // (one call site in a loop: the collision is a large function)
+      for (int t = 0; t < 3; t++) {
+        do_bc(t == 2 ? p1 : p0, t == 0 ? p1 : p2, half, gcell, 0, (uint64_t)t);
+      }
+      n = 3, jp = 3;
+    }
+    for (; n < my_nn; n += 2, jp++) {
+      do_bc(my_cb + (uint32_t)(k8[n] & 0xffffffu), my_cb + (uint32_t)(k8[n + 1] & 0xffffffu), nudt1, gcell, 0,
+            (uint64_t)jp);
+    }
+  }
+  __syncwarp();
+
+  // ---- the other cells, one after the other, by the whole warp
+  unsigned big = __ballot_sync(FULL, my_nn > COLL_SMALL);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t cb = __shfl_sync(FULL, my_cb, src);
+    const int nn = __shfl_sync(FULL, my_nn, src);
+    const uint64_t gcell = P.cell0 + g0 + (uint32_t)src;
+    for (int s0 = 0; s0 < nn; s0 += COLL_CAP) {
+      const int m = min(COLL_CAP, nn - s0);
+      if (m < 2) {
+        break;
+      }
+      // ---- randomize_in_cell (:160-166): sort composite keys (random 40 bits, index)
+      int m2 = 2;
+      while (m2 < m) {
+        m2 <<= 1;
+      }
+      for (int i = lane; i < m2; i += 32) {
+        uint64_t key = ~0ull; // padding sorts to the end
+        if (i < m) {
+          key = P.rng ? (((coll_hash(P.seed, P.step, gcell, (uint64_t)(s0 + i), 0) >> 24) << 24) | (uint64_t)i)
+                      : (uint64_t)i;
+        }
+        sk[i] = key;
+      }
+      __syncwarp();
+      if (P.rng) {
+        for (int k = 2; k <= m2; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (m2 >> 1); t += 32) {
+              // t-th compare-exchange of this stage
+              const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+              const int l = i | j;
+              const bool up = (i & k) == 0;
+              const uint64_t a = sk[i], b = sk[l];
+              if ((a > b) == up) {
+                sk[i] = b;
+                sk[l] = a;
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
-    }
-    const uint32_t base = cb + (uint32_t)s0;
-    // all particles need to have same weight (:227-229): nudt1 from the first of the permutation
-    float nudt1;
-    {
-      const uint32_t f = base + (uint32_t)(sk[0] & 0xffffffu);
-      const int kf = __float_as_int(xi4[f].w);
-      const float wni = pxi4[f].w / P.q[kf];
-      nudt1 = (float)((double)wni * P.cori * nn * P.interval * P.dt * P.nu);
-    }
-    int first = 0;
-    if (m & 1) { // odd # of particles: do 3-collision (:235-240)
-      if (lane == 0) {
-        const uint32_t p0 = base + (uint32_t)(sk[0] & 0xffffffu), p1 = base + (uint32_t)(sk[1] & 0xffffffu),
-                       p2 = base + (uint32_t)(sk[2] & 0xffffffu);
-        const float half = (float)(.5 * (double)nudt1);
-        do_bc(p0, p1, half, (uint64_t)s0, 0);
-        do_bc(p0, p2, half, (uint64_t)s0, 1);
-        do_bc(p1, p2, half, (uint64_t)s0, 2);
+      const uint32_t base = cb + (uint32_t)s0;
+      const float nudt1 = nudt1_of(base + (uint32_t)(sk[0] & 0xffffffu), nn);
+      // the triangle of an odd population runs on lane 0 while the others start on the pairs:
+      // work item t of lane 0 is the triangle, the pairs follow
+      const int first = (m & 1) ? 3 : 0;
+      const int n_pairs = (m - first) >> 1;
+      const int n_items = n_pairs + (first ? 1 : 0);
+      for (int t = lane; t < n_items; t += 32) {
+        if (first && t == 0) {
+          const uint32_t p0 = base + (uint32_t)(sk[0] & 0xffffffu), p1 = base + (uint32_t)(sk[1] & 0xffffffu),
+                         p2 = base + (uint32_t)(sk[2] & 0xffffffu);
+          const float half = (float)(.5 * (double)nudt1);
+          for (int q = 0; q < 3; q++) {
+            do_bc(q == 2 ? p1 : p0, q == 0 ? p1 : p2, half, gcell, (uint64_t)s0, (uint64_t)q);
+          }
+        } else {
+          const int tp = first ? t - 1 : t;
+          const int n = first + 2 * tp;
+          do_bc(base + (uint32_t)(sk[n] & 0xffffffu), base + (uint32_t)(sk[n + 1] & 0xffffffu), nudt1, gcell,
+                (uint64_t)s0, (uint64_t)(first + tp));
+        }
       }
-      first = 3;
+      __syncwarp();
     }
-    // remaining particles as pairs: disjoint, one pair per lane
-    const int n_pairs = (m - first) >> 1;
-    for (int t = lane; t < n_pairs; t += 32) {
-      const int n = first + 2 * t;
-      do_bc(base + (uint32_t)(sk[n] & 0xffffffu), base + (uint32_t)(sk[n + 1] & 0xffffffu), nudt1, (uint64_t)s0,
-            (uint64_t)(first + t));
-    }
-    __syncwarp();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -329,7 +378,7 @@ int collide(Ctx* c, const psc_b200_collision_params* prm, uint64_t* n_collisions
   const uint32_t nct = (uint32_t)g.n_cells * g.n_patches;
   if (c->n_prts) {
     KernelScope ks(c, "collide");
-    k_collide<<<div_up(nct, COLL_WARPS), COLL_WARPS * 32, 0, c->stream>>>(c->gd, P, nct, c->d_cell_off, c->xi(),
+    k_collide<<<div_up(nct, COLL_WARPS * 32), COLL_WARPS * 32, 0, c->stream>>>(c->gd, P, nct, c->d_cell_off, c->xi(),
                                                                         c->pxi(), d_n);
     c->n_launches++;
   }

@@ -103,6 +103,8 @@ def main():
         return t.cpu().numpy()
 
     e0 = pb.energies(grid)  # (already summed over the ranks by the library)
+    grid.set_option("profile", 1)
+    grid.profile_reset()
     grid.sync()
     if dist:
         dist.barrier()
@@ -117,6 +119,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     e1 = pb.energies(grid)
+    prof = {k: round(v[0] / args.steps, 3) for k, v in grid.profile().items()}
+    grid.set_option("profile", 0)
     n_after = int(allsum([mprts.size()])[0])
     # one checked step: continuity residual (psc.hxx:379-384,471-476)
     chk = pb.Psc(grid, mflds, mprts, sort_interval=1, fused=True,
@@ -133,7 +137,7 @@ def main():
             "energy_drift": float(e1.sum() / e0.sum() - 1.), "field_energy_start": float(e0[:6].sum()),
             "field_energy_end": float(e1[:6].sum()), "continuity_max_err": cont,
             "fused_steps": grid.get_stat("fused_steps"), "fused_fallbacks": grid.get_stat("fused_fallbacks"),
-            "host_build_s": round(t_build, 1)}), flush=True)
+            "kernels_ms_per_step": prof, "host_build_s": round(t_build, 1)}), flush=True)
     grid.close()
     if dist:
         dist.destroy_process_group()
