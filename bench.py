@@ -302,7 +302,31 @@ def balance_phase(args, rank, world, local_rank, dist, torch):
 
 # ---------------------------------------------------------------------------- GPU arm
 
+def bind_to_gpu_numa_node(local_rank):
+    """pin this process (and with it the pinned host buffers it allocates) to the NUMA node the GPU
+    hangs off: at 8 ranks the host<->device copies of the e2e loop otherwise cross the sockets"""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, rank, world, local_rank):
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     import torch
     import psc_b200 as pb
     if not torch.cuda.is_available():
@@ -459,7 +483,7 @@ def run_b200(args, rank, world, local_rank):
         names = ("first_upload", "push..J_on_host", "upload+sort_end", "energies")
         e2e = {"value": n_total * k_e2e / dt_e2e, "unit": "particle-steps/s",
                "h2d_bytes_per_step": int(h_eb.nbytes) * world, "d2h_bytes_per_step": (int(h_j.nbytes) + 64) * world,
-               "steps": k_e2e,
+               "steps": k_e2e, "numa_node_of_rank0": numa_node,
                "ms_per_step": {k: round(float(v) / k_e2e * 1e3, 2) for k, v in zip(names, parts)},
                "what": "per step through the C ABI with pinned HOST buffers: psc_b200_step_begin (push + deposit, then "
                        "sort || J ghosts + Yee), J (3 comps, all patches) down as soon as it is final, the next "

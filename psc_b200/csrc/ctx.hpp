@@ -99,6 +99,7 @@ struct Ctx
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with TMA (tensor map / cp.async.bulk) instead of LDG/STS
   int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time
+  int opt_vec_fields = 1;  // Yee update with 128-bit accesses where the rows allow it (3D, im0 % 4 == 0)
   int opt_threads = 256;   // CTA size of the tiled push
   int opt_min_blocks = 3;  // resident CTAs per SM the tiled push is compiled for
   int opt_tile[3] = {0, 0, 0}; // cells per tile edge, 0 = default

@@ -263,6 +263,88 @@ __global__ void k_push_fields(GridDev G, YeeDev Y, float* __restrict__ F, long s
 }
 #undef FX
 
+// The same update, four x-neighbours per thread with 128-bit loads / stores (3D, rows a multiple
+// of four floats: every row of PSC's layout then starts 16-byte aligned).  Per element the
+// arithmetic is the expression above, so the result is bit-identical; the scalar kernel issues
+// 16 loads per point and runs at 42 % of the HBM peak, this one 15 per four points.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <bool IS_E>
+__global__ void __launch_bounds__(256) k_push_fields_v4(GridDev G, YeeDev Y, float* __restrict__ F, long slot_len)
+{
+  const int l = IS_E ? 1 : 2, r = IS_E ? 2 : 1;
+  const int nv = G.im[0] >> 2;
+  const int e1 = G.ldims[1] + l + r, e2 = G.ldims[2] + l + r;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)G.n_patches * nv * e1 * e2) {
+    return;
+  }
+  const int v = (int)(idx % nv);
+  idx /= nv;
+  const int j = (int)(idx % e1) - l;
+  idx /= e1;
+  const int k = (int)(idx % e2) - l;
+  const int p = (int)(idx / e2);
+  float* Fp = F + p * slot_len;
+  const int i0 = 4 * v - G.ibn[0]; // x index of the vector's first element
+  const long sy = G.im[0], sz = (long)G.im[0] * G.im[1];
+  auto at = [&](int m) { return Fp + fld_off(G, m, i0, j, k); };
+  // element a of the row is updated for a in [1, im0) (E) / [0, im0 - 1) (H)  (grid.hxx:124-139)
+  const int a0 = 4 * v;
+  float4 o0, o1, o2;
+  if (IS_E) {
+    float* ex = at(pm::EX);
+    float* ey = at(pm::EY);
+    float* ez = at(pm::EZ);
+    const float *hx = at(pm::HX), *hy = at(pm::HY), *hz = at(pm::HZ);
+    const float4 HZc = ld4(hz), HZj = ld4(hz - sy), HYc = ld4(hy), HYk = ld4(hy - sz);
+    const float4 HXc = ld4(hx), HXk = ld4(hx - sz), HXj = ld4(hx - sy);
+    const float4 JX = ld4(at(pm::JXI)), JY = ld4(at(pm::JYI)), JZ = ld4(at(pm::JZI));
+    const float hz_m = a0 > 0 ? hz[-1] : 0.f, hy_m = a0 > 0 ? hy[-1] : 0.f; // (a = 0 is not updated)
+    const float4 HZi = make_float4(hz_m, HZc.x, HZc.y, HZc.z), HYi = make_float4(hy_m, HYc.x, HYc.y, HYc.z);
+    o0 = ld4(ex), o1 = ld4(ey), o2 = ld4(ez);
+#define UPD_E(c)                                                                                   \
+  o0.c += (Y.cny * (HZc.c - HZj.c) - Y.cnz * (HYc.c - HYk.c) - Y.dth * JX.c);                       \
+  o1.c += (Y.cnz * (HXc.c - HXk.c) - Y.cnx * (HZc.c - HZi.c) - Y.dth * JY.c);                       \
+  o2.c += (Y.cnx * (HYc.c - HYi.c) - Y.cny * (HXc.c - HXj.c) - Y.dth * JZ.c);
+    if (a0 > 0) {
+      UPD_E(x)
+    }
+    UPD_E(y)
+    UPD_E(z)
+    UPD_E(w)
+#undef UPD_E
+    *reinterpret_cast<float4*>(ex) = o0;
+    *reinterpret_cast<float4*>(ey) = o1;
+    *reinterpret_cast<float4*>(ez) = o2;
+  } else {
+    float* hx = at(pm::HX);
+    float* hy = at(pm::HY);
+    float* hz = at(pm::HZ);
+    const float *ex = at(pm::EX), *ey = at(pm::EY), *ez = at(pm::EZ);
+    const float4 EZc = ld4(ez), EZj = ld4(ez + sy), EYc = ld4(ey), EYk = ld4(ey + sz);
+    const float4 EXc = ld4(ex), EXk = ld4(ex + sz), EXj = ld4(ex + sy);
+    const bool last = a0 + 4 >= G.im[0];
+    const float ez_p = last ? 0.f : ez[4], ey_p = last ? 0.f : ey[4]; // (a = im0 - 1 is not updated)
+    const float4 EZi = make_float4(EZc.y, EZc.z, EZc.w, ez_p), EYi = make_float4(EYc.y, EYc.z, EYc.w, ey_p);
+    o0 = ld4(hx), o1 = ld4(hy), o2 = ld4(hz);
+#define UPD_H(c)                                                                                   \
+  o0.c -= (Y.cny * (EZj.c - EZc.c) - Y.cnz * (EYk.c - EYc.c));                                      \
+  o1.c -= (Y.cnz * (EXk.c - EXc.c) - Y.cnx * (EZi.c - EZc.c));                                      \
+  o2.c -= (Y.cnx * (EYi.c - EYc.c) - Y.cny * (EXj.c - EXc.c));
+    UPD_H(x)
+    UPD_H(y)
+    UPD_H(z)
+    if (!last) {
+      UPD_H(w)
+    }
+#undef UPD_H
+    *reinterpret_cast<float4*>(hx) = o0;
+    *reinterpret_cast<float4*>(hy) = o1;
+    *reinterpret_cast<float4*>(hz) = o2;
+  }
+}
+
 // ---------------------------------------------------------------- conducting wall
 
 enum
@@ -974,6 +1056,16 @@ static int push_fields(Ctx* c, double dt_fac, bool is_E)
   size_t n = (size_t)G.n_patches * (G.ibn[0] ? G.ldims[0] + 3 : 1) * (G.ldims[1] + 3) *
              (G.ldims[2] + 3);
   KernelScope ks(c, is_E ? "push_E" : "push_H");
+  if (G.dim == pm::DIM_XYZ && G.im[0] % 4 == 0 && G.ibn[0] == 2 && c->fld_slot_len(0) % 4 == 0 && c->opt_vec_fields) {
+    const size_t nv = (size_t)G.n_patches * (G.im[0] / 4) * (G.ldims[1] + 3) * (G.ldims[2] + 3);
+    if (is_E) {
+      k_push_fields_v4<true><<<div_up(nv, 256), 256, 0, c->stream>>>(G, Y, c->fld(0), c->fld_slot_len(0));
+    } else {
+      k_push_fields_v4<false><<<div_up(nv, 256), 256, 0, c->stream>>>(G, Y, c->fld(0), c->fld_slot_len(0));
+    }
+    c->n_launches++;
+    return check_launch(c, "push_fields");
+  }
   if (is_E) {
     k_push_fields<true><<<div_up(n, 256), 256, 0, c->stream>>>(G, Y, c->fld(0), c->fld_slot_len(0));
   } else {
