@@ -534,7 +534,7 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # (the contract: rank 0 at N = 1 only; `--impl reference` times it at any N)
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         v, _, sample, used, kind = cpu_arm(32, 64, max(4, 2 * cores), 2, 1, cores)
         cpu = {"value": v, "unit": "particle-steps/s", "cores": used, "kind": kind, "sample": sample}
