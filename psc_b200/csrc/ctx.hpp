@@ -98,6 +98,7 @@ struct Ctx
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with TMA (tensor map / cp.async.bulk) instead of LDG/STS
+  int opt_push_collect = 1; // multi-rank: k_push_lean lists the remote leavers (else a pass over the boundary cells)
   int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time
   int opt_vec_fields = 1;  // Yee update with 128-bit accesses where the rows allow it (3D, im0 % 4 == 0)
   int opt_threads = 256;   // CTA size of the tiled push
@@ -198,6 +199,10 @@ struct Ctx
   DevBuf rf_cells;      // cells from which particles can leave for another rank
   uint32_t n_rf_cells = 0;
   bool rf_built = false;
+  // the lean push lists the remote leavers itself (push.cu launch_lean): capacity of the
+  // list in scr[7] for the step in flight (0 = none), and last step's count to size it by
+  uint32_t rem_cap = 0;
+  uint32_t last_n_rem = 0;
 
   float4* xi() { return xi4[cur]; }
   float4* pxi() { return pxi4[cur]; }

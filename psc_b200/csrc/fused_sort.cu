@@ -638,6 +638,8 @@ int fused_bnd_sort_finish(Ctx* c)
 int fused_bnd_sort(Ctx* c, bool defer)
 {
   const GridDev& G = c->gd;
+  const uint32_t rem_cap = c->rem_cap; // remote leavers listed by the push of this step (0: not)
+  c->rem_cap = 0;
   if (!c->pushed_from_sorted) {
     c->counts_valid = false;
     PSC_TRY(bnd_particles(c));
@@ -654,7 +656,8 @@ int fused_bnd_sort(Ctx* c, bool defer)
   uint32_t* flags = c->scr[11].as<uint32_t>(); // [bad, dropped, remote, counter, new patch offsets...]
   uint32_t* d_new_off = flags + 4;
   FsTables T{c->d_patch_bnd, c->d_nei_patch};
-  if (!c->counts_valid) { // else: the push kernel already filled cnt and flags
+  const bool counted_by_push = c->counts_valid;
+  if (!counted_by_push) { // else: the push kernel already filled cnt and flags
     PSC_CUDA_TRY(cudaMemsetAsync(flags, 0, 4 * sizeof(uint32_t), c->stream));
     KernelScope ks(c, "fsort_count");
     k_fs_count<<<div_up(nct, FS_CELLS), FS_WARPS * 32, 0, c->stream>>>(G, T, nct, c->d_cell_off,
@@ -709,16 +712,23 @@ int fused_bnd_sort(Ctx* c, bool defer)
       PSC_TRY(build_remote_cells(c));
     }
     uint32_t *gk = nullptr, *gi = nullptr;
+    c->last_n_rem = n_rem;
     if (n_rem) {
       KernelScope ks(c, "fsort_remote_collect");
-      PSC_TRY(c->scr[7].reserve(4 * (size_t)n_rem * sizeof(uint32_t)));
-      uint32_t* a = c->scr[7].as<uint32_t>();
-      uint32_t *k0 = a, *v0 = a + n_rem, *k1 = a + 2 * (size_t)n_rem, *v1 = a + 3 * (size_t)n_rem;
+      uint32_t *k0, *v0, *k1, *v1;
       // pass 1 sorts by index (keys = index, values = group), pass 2 by group
-      k_fs_collect_remote<<<div_up(c->n_rf_cells, FS_WARPS), FS_WARPS * 32, 0, c->stream>>>(
-        G, T, c->n_rf_cells, c->rf_cells.as<uint32_t>(), c->d_cell_off, c->xi(), v0, k0, flags + 3,
-        n_rem);
-      c->n_launches++;
+      if (counted_by_push && n_rem <= rem_cap) { // the push listed them (push.cu launch_lean) ...
+        uint32_t* a = c->scr[7].as<uint32_t>();
+        k0 = a, v0 = a + rem_cap, k1 = a + 2 * (size_t)rem_cap, v1 = a + 3 * (size_t)rem_cap;
+      } else { // ... or it did not, or its list overflowed: pass over the boundary cells
+        PSC_TRY(c->scr[7].reserve(4 * (size_t)n_rem * sizeof(uint32_t)));
+        uint32_t* a = c->scr[7].as<uint32_t>();
+        k0 = a, v0 = a + n_rem, k1 = a + 2 * (size_t)n_rem, v1 = a + 3 * (size_t)n_rem;
+        k_fs_collect_remote<<<div_up(c->n_rf_cells, FS_WARPS), FS_WARPS * 32, 0, c->stream>>>(
+          G, T, c->n_rf_cells, c->rf_cells.as<uint32_t>(), c->d_cell_off, c->xi(), v0, k0, flags + 3,
+          n_rem);
+        c->n_launches++;
+      }
       bool in_alt = false;
       PSC_TRY(sort_pairs(c, k0, v0, k1, v1, n_rem, 32, false, &in_alt));
       uint32_t *ik = in_alt ? k1 : k0, *iv = in_alt ? v1 : v0; // (index, group) by index

@@ -395,6 +395,12 @@ struct PushArgs
   uint32_t nct;
   int same_dxi; // 1/float(dx) == float(dx_inv) bitwise: the pusher's cell = the indexer's cell
   FsTables tab;
+  // lean kernel, SAME, multi-rank: the drain lists the particles that leave for another rank
+  // (group key, index) while it classifies them; flags[2] is the list's fill count.  rem_cap
+  // = 0: no list (fused_sort.cu collects them from the boundary cells instead).
+  uint32_t* rem_key;
+  uint32_t* rem_idx;
+  uint32_t rem_cap;
   GapPush gap; // GAP variant only (gap.cuh)
 };
 
@@ -1014,10 +1020,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
 
 // k_push_lean: compile-time geometry, tensor-map TMA, no gapped store
 template <int DIM, int DEPOSIT>
-static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, const PushArgs& A)
+static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, PushArgs A)
 {
   const GridDev& G = c->gd;
   constexpr bool XYZ = DIM == pm::DIM_XYZ;
+  if (count && c->comm && A.same_dxi && c->opt_push_collect) {
+    // room for half as many again as left last step; a step that overflows it falls back to
+    // the boundary-cell collection
+    const size_t cap = std::max<size_t>(1u << 16, (size_t)c->last_n_rem + c->last_n_rem / 2);
+    PSC_TRY(c->scr[7].reserve(4 * cap * sizeof(uint32_t)));
+    A.rem_idx = c->scr[7].as<uint32_t>();
+    A.rem_key = A.rem_idx + cap;
+    A.rem_cap = (uint32_t)cap;
+    c->rem_cap = A.rem_cap;
+  }
   const int tiles = geo.nt(0) * geo.nt(1) * geo.nt(2) * G.n_patches;
   // particles per lane.  2 = the update on the packed FP32 pipe (FADD2 / FFMA2): 18 % fewer
   // warp instructions, but 128 registers => 16 warps per SM instead of 24, and the kernel
@@ -1183,6 +1199,7 @@ static int push_dim(Ctx* c, bool gap)
       A.same_dxi = A.same_dxi && G.pc.dxi[d] == G.pc.dxi_idx[d];
     }
     bool count = c->want_counts || gap;
+    c->rem_cap = 0;
     if (count) {
       // the kernel writes every cnt[class][cell] entry exactly once: no memset
       PSC_TRY(c->scr[9].reserve((size_t)A.nct * FS_PLANES * sizeof(cnt_t)));

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         const bool ok = (unsigned)dc[0] < (unsigned)G.ldims[0] && (unsigned)dc[1] < (unsigned)G.ldims[1] &&
                         (unsigned)dc[2] < (unsigned)G.ldims[2] && (unsigned)(d0 + 1) <= 2u &&
                         (unsigned)(d1 + 1) <= 2u && (unsigned)(d2 + 1) <= 2u;
-        int cls;
+        int cls, rq = 0, rc = 0; // (rq, rc): fs_classify's target rank / direction of a remote leaver
         if (ok) {
           cls = ((d2 + 1) * 3 + d1 + 1) * 3 + d0 + 1;
         } else {
@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
             xn[0] = Xr.x, xn[1] = Xr.y, xn[2] = Xr.z;
           }
           float uu[3] = {0.f, 0.f, 0.f};
-          int q, c;
-          cls = fs_classify(G, A.tab, p, sc[0], sc[1], sc[2], xn, uu, q, c);
+          cls = fs_classify(G, A.tab, p, sc[0], sc[1], sc[2], xn, uu, rq, rc);
         }
         if (cls < FS_PLANES) {
           const size_t e = (size_t)cls * A.nct + (size_t)p * G.n_cells +
@@ -253,7 +252,13 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         } else if (cls == CLS_DROP) {
           atomicAdd(&A.flags[1], 1u);
         } else if (cls == CLS_REMOTE) {
-          atomicAdd(&A.flags[2], 1u);
+          const uint32_t slot = atomicAdd(&A.flags[2], 1u);
+          if constexpr (SAME) {
+            if (slot < A.rem_cap) {
+              A.rem_key[slot] = ((uint32_t)(-2 - rq) * G.n_patches + p) * 32u + (uint32_t)rc;
+              A.rem_idx[slot] = (uint32_t)__float_as_int(XYZ ? A1.w : A0.x);
+            }
+          }
         }
       }
       more = w.first(G.pc, t, qw, ci, val);
