@@ -231,6 +231,27 @@ typedef struct
 int psc_b200_heating_spot_foil(psc_b200_ctx* ctx, const psc_b200_heating_params* prm,
                                uint64_t* n_kicked);
 
+/* ---- BoundaryInjector (src/include/boundary_injector.hxx:93-160; Psc::step calls the
+ * injectors between the push and the particle exchange, psc.hxx:391-399).  The generator,
+ * the one-step advance and the "did it enter the patch" test are host code there and stay
+ * host code here (psc_config_b200.hxx BoundaryInjectorB200, psc_b200.api.BoundaryInjector);
+ * the device takes the two halves that touch its data: the accepted particles go in through
+ * psc_b200_mprts_inject, and the current of their way in is deposited by this call =
+ * Current::calc_j(J, xm, xp, lf, lg, qni_wni, v) (boundary_injector.hxx:146-147;
+ * inc_curr_1vb_split.cxx / inc_curr_1vb_var1.cxx as the grid's deposit selects) for every
+ * trajectory, added to JXI..JZI of the state fields.
+ * xm / xp: start and end, patch-local and normalised (x * dx_inv formed in float as the
+ * reference does, :140-141); lg: the cell the trajectory starts in (the ghost cell the
+ * particle was generated in; lf = fint(xp) is formed on the device); v: calc_v(u). ---- */
+typedef struct
+{
+  int patch; /* local patch */
+  int lg[3];
+  float xm[3], xp[3], v[3];
+  float qni_wni;
+} psc_b200_jpath;
+int psc_b200_deposit_j(psc_b200_ctx* ctx, const psc_b200_jpath* paths, uint64_t n);
+
 /* ---- Psc::step (src/include/psc.hxx:321-486): the whole sequence on the stream ---- */
 typedef struct
 {

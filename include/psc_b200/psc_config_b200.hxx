@@ -40,12 +40,14 @@
 
 #include <array>
 #include <cassert>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
 #include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -981,6 +983,133 @@ inline std::array<double, 8> energies(MparticlesB200<GridT>& mprts)
 }
 
 // ----------------------------------------------------------------------
+// BoundaryInjectorB200: BoundaryInjector<PARTICLE_GENERATOR, PUSH_PARTICLES>
+// (src/include/boundary_injector.hxx:66-167), same constructor and inject(mprts, mflds)
+// (InjectorBase, injector_base.hxx:5-11), so Psc::add_injector takes it.  Every step, for
+// every ghost cell just below the lower y wall, particles of an imaginary unit-density
+// population are drawn from the generator, advanced one step in y, and those that enter the
+// patch are injected with the current of their way in.  The generator, the cell loop and the
+// advance are host code there and stay host code here; the device takes the accepted
+// particles (injector(), one H2D append) and the deposit (psc_b200_deposit_j =
+// Current::calc_j for each trajectory).  The reference instantiates its template for double
+// configurations only (push_x binds Vec3<real_t>& to the generator's Double3); here the same
+// statements run in this configuration's real_t = float.
+//
+// ParticleGenerator: get(min_pos, pos_range) -> record with x[3], u[3], w, kind
+// (psc::particle::Inject; positions patch-local).  ParticleGeneratorMaxwellian of
+// boundary_injector.hxx:16-57 is host code over PSC's rng.hxx and works unchanged.
+
+template <typename PARTICLE_GENERATOR, typename GridT>
+class BoundaryInjectorB200
+{
+  static const int INJECT_DIM_IDX_ = 1;
+
+public:
+  using ParticleGenerator = PARTICLE_GENERATOR;
+  using Mparticles = MparticlesB200<GridT>;
+  using MfieldsState = MfieldsStateB200<GridT>;
+  using real_t = float;
+
+  BoundaryInjectorB200(ParticleGenerator particle_generator, const GridT& grid)
+    : particle_generator_(particle_generator),
+      dt_(real_t(grid.dt)),
+      prts_per_unit_density_(real_t(grid.norm.prts_per_unit_density))
+  {}
+  virtual ~BoundaryInjectorB200() {}
+
+  // get_n_in_cell(1.0, prts_per_unit_density, true) (setup_particles.hxx:110-122): the density
+  // plus a uniform draw, truncated.  A deck inside PSC passes ::get_n_in_cell's own generator
+  // through this hook; the default draws from <random>.
+  std::function<int()> n_in_cell;
+
+  int n_injected() const { return n_injected_; }
+
+  virtual void inject(Mparticles& mprts, MfieldsState& mflds)
+  {
+    const GridT& grid = mprts.grid();
+    std::vector<psc_b200_jpath> paths;
+    n_injected_ = 0;
+    {
+      auto injectors_by_patch = mprts.injector();
+      real_t dxi[3];
+      for (int d = 0; d < 3; d++) {
+        dxi[d] = real_t(double(grid.domain.gdims[d]) / grid.domain.length[d]); // Real3 dxi = dx_inv
+      }
+      for (int p = 0; p < grid.n_patches(); p++) {
+        if (grid.patches[p].off[INJECT_DIM_IDX_] != 0) { // !grid.atBoundaryLo(p, 1)
+          continue;
+        }
+        int ilo[3] = {0, 0, 0}, ihi[3] = {grid.ldims[0], grid.ldims[1], grid.ldims[2]};
+        ilo[INJECT_DIM_IDX_] = -1;
+        ihi[INJECT_DIM_IDX_] = 0;
+        auto injector = injectors_by_patch[p];
+        // VecRange(ilo, ihi): row-major, the last index runs fastest (kg/VecRange.hxx:5-24)
+        for (int i0 = ilo[0]; i0 < ihi[0]; i0++) {
+          for (int i1 = ilo[1]; i1 < ihi[1]; i1++) {
+            for (int i2 = ilo[2]; i2 < ihi[2]; i2++) {
+              const int initial_idx[3] = {i0, i1, i2};
+              auto cell_corner = grid.domain.dx; // (same vector type as dx; narrowed like Real3)
+              for (int d = 0; d < 3; d++) {
+                cell_corner[d] = real_t(double(initial_idx[d]) * grid.domain.dx[d]);
+              }
+              const int n_prts_to_try_inject = n_in_cell ? n_in_cell() : default_n_in_cell();
+              for (int cnt = 0; cnt < n_prts_to_try_inject; cnt++) {
+                auto prt = particle_generator_.get(cell_corner, grid.domain.dx);
+                // calc_v (pushp.hxx:68-72)
+                const real_t u[3] = {real_t(prt.u[0]), real_t(prt.u[1]), real_t(prt.u[2])};
+                const real_t root = real_t(1.) / std::sqrt(real_t(1.) + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+                const real_t v[3] = {u[0] * root, u[1] * root, u[2] * root};
+                const real_t initial_x[3] = {real_t(prt.x[0]), real_t(prt.x[1]), real_t(prt.x[2])};
+                real_t x[3] = {initial_x[0], initial_x[1], initial_x[2]};
+                // push_x of AdvanceParticle<real_t, dim_y> (pushp.hxx:17-29): y only ("can't
+                // move along x or z, or else might leave patch")
+                x[INJECT_DIM_IDX_] += real_t(1.) * dt_ * v[INJECT_DIM_IDX_];
+                if (x[INJECT_DIM_IDX_] < real_t(0.)) {
+                  continue; // don't inject a particle that fails to enter the patch
+                }
+                // injectors expect global positions, the deposit patch-local ones (:131-135)
+                auto prt_with_global_x = prt;
+                for (int d = 0; d < 3; d++) {
+                  prt_with_global_x.x[d] = double(x[d]) + grid.patches[p].xb[d];
+                }
+                injector(prt_with_global_x);
+                n_injected_++;
+
+                psc_b200_jpath path;
+                path.patch = p;
+                for (int d = 0; d < 3; d++) {
+                  path.lg[d] = initial_idx[d];
+                  path.xm[d] = initial_x[d] * dxi[d];
+                  path.xp[d] = x[d] * dxi[d];
+                  path.v[d] = v[d];
+                }
+                path.qni_wni = real_t(grid.kinds[prt.kind].q * prt.w);
+                paths.push_back(path);
+              }
+            }
+          }
+        }
+      }
+    } // (the buffered injector appends on destruction)
+    (void)mflds;
+    PSC_B200_CHECK(psc_b200_deposit_j(mprts.ctx(), paths.data(), paths.size()));
+  }
+
+private:
+  int default_n_in_cell()
+  {
+    static std::mt19937 gen(0);
+    static std::uniform_real_distribution<float> dist(0.f, 1.f);
+    return int(real_t(1.) * prts_per_unit_density_ + dist(gen));
+  }
+
+  ParticleGenerator particle_generator_;
+  real_t dt_;
+  real_t prts_per_unit_density_;
+  int n_injected_ = 0;
+};
+
+// ----------------------------------------------------------------------
 // the config bundle (src/psc_config.hxx:99-146)
 
 template <typename _Dim, typename GridT>
@@ -1046,12 +1175,26 @@ public:
     bnd_.fill_ghosts(mflds_, PSC_B200_EX, PSC_B200_EX + 3);
   }
 
+  // Psc::add_injector (psc.hxx:172-176): anything with inject(mprts, mflds).  The injectors
+  // act between the push and the particle exchange (psc.hxx:391-399), so a step with
+  // injectors is issued operator by operator instead of as the single fused call.
+  void add_injector(std::function<void(Mparticles&, MfieldsState&)> injector)
+  {
+    injectors_.push_back(std::move(injector));
+  }
+  template <typename Injector>
+  void add_injector(Injector* injector)
+  {
+    assert(injector);
+    injectors_.push_back([injector](Mparticles& mprts, MfieldsState& mflds) { injector->inject(mprts, mflds); });
+  }
+
   void operator()()
   {
     const int t = ++timestep_;
     const bool do_sort = p_.sort_interval > 0 && t % p_.sort_interval == 0;
     const bool do_marder = p_.marder_interval > 0 && t % p_.marder_interval == 0;
-    if (p_.fused) {
+    if (p_.fused && injectors_.empty()) {
       psc_b200_step_params sp;
       sp.sort = do_sort;
       sp.marder_loop = do_marder ? p_.marder_loop : 0;
@@ -1072,6 +1215,9 @@ public:
     }
     checks_.continuity.before_particle_push(mprts_, t); // :379-384
     pushp_.push_mprts(mprts_, mflds_);                  // :389
+    for (auto& injector : injectors_) {                 // :391-399
+      injector(mprts_, mflds_);
+    }
     bndp_(mprts_);                                      // :412
     bndf_.add_ghosts_J(mflds_);                         // :417
     bnd_.add_ghosts(mflds_, PSC_B200_JXI, PSC_B200_JXI + 3);  // :418
@@ -1107,6 +1253,7 @@ private:
   typename Config::BndParticles bndp_;
   typename Config::Marder marder_;
   typename Config::Checks checks_;
+  std::vector<std::function<void(Mparticles&, MfieldsState&)>> injectors_;
   int timestep_ = 0;
 };
 

@@ -1720,6 +1720,70 @@ void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,
   }
 }
 
+/* ---- BoundaryInjector::inject (src/include/boundary_injector.hxx:93-160) ----
+ * The particle generator and get_n_in_cell draw from the host's sequential generators;
+ * their output is handed in (cand: what generator.get(cell_corner, dx) returned for ghost
+ * cell idx of patch `patch`, positions patch-local), and this restates what inject() does
+ * with each draw, statement by statement, in the configuration's real_t (float; the
+ * reference itself instantiates the template for its double configurations only, because
+ * push_x binds a Vec3<real_t>& to the generator's Double3):
+ *   :122     v = calc_v(u)                       (pushp.hxx:68-72)
+ *   :123-124 initial_x = x; push_x(x, v)         (AdvanceParticle<real_t, dim_y>: y only, pushp.hxx:17-29)
+ *   :126-129 a particle that does not enter the patch (x_y < 0) is not injected
+ *   :133-135 x + xb goes to the injector, which stores real_t(x_glob) - real_t(xb) and
+ *            qni_wni = real_t(w * q)             (injector_simple.hxx:27-34)
+ *   :140-147 calc_j(J, initial_x * dxi, x * dxi, fint(..), initial_idx, q * w, v) with
+ *            dxi = real_t(grid.domain.dx_inv)
+ * out / out_patch (room for n) receive the accepted records in candidate order.
+ * Returns the number accepted. */
+long po_boundary_inject(const po_grid* g, float* flds, const po_inject_cand* cand, long n, po_prt* out,
+                        int* out_patch)
+{
+  const int DIM_INJ = 1; /* INJECT_DIM_IDX_ */
+  long plen = po_fld_patch_len(g) * PO_NR_FIELDS;
+  float dt = (float)g->dt; /* AdvanceParticle(grid.dt) */
+  float dxi[3];
+  for (int d = 0; d < 3; d++) {
+    dxi[d] = (float)g->dx_inv[d];
+  }
+  long n_out = 0;
+  for (long i = 0; i < n; i++) {
+    const po_inject_cand* c = &cand[i];
+    float u[3] = {(float)c->u[0], (float)c->u[1], (float)c->u[2]};
+    float root = rsqrt_host(1.f + sqrf(u[0]) + sqrf(u[1]) + sqrf(u[2]));
+    float v[3] = {u[0] * root, u[1] * root, u[2] * root};
+    float x0[3] = {(float)c->x[0], (float)c->x[1], (float)c->x[2]};
+    float x[3] = {x0[0], x0[1], x0[2]};
+    x[DIM_INJ] += 1.f * dt * v[DIM_INJ];
+    if (x[DIM_INJ] < 0.f) {
+      continue;
+    }
+    int poff[3];
+    po_patch_off(g, c->patch, poff);
+    po_prt* o = &out[n_out];
+    for (int d = 0; d < 3; d++) {
+      double xb = (double)poff[d] * g->dx[d] + g->corner[d]; /* grid.hxx:82-86 */
+      o->x[d] = (float)((double)x[d] + xb) - (float)xb;
+      o->u[d] = (float)c->u[d];
+    }
+    o->kind = c->kind;
+    o->qni_wni = (float)(c->w * g->q[c->kind]);
+    out_patch[n_out++] = c->patch;
+
+    float xm[3], xp[3];
+    int lf[3], lg[3] = {c->idx[0], c->idx[1], c->idx[2]};
+    for (int d = 0; d < 3; d++) {
+      xm[d] = x0[d] * dxi[d];
+      xp[d] = x[d] * dxi[d];
+      lf[d] = (int)floorf(xp[d]);
+    }
+    po_curr_f cur;
+    po_curr_setup_f(&cur, g, flds + c->patch * plen);
+    po_calc_j_impl_f(&cur, g->deposit, xm, xp, lf, lg, (float)(g->q[c->kind] * c->w), v);
+  }
+  return n_out;
+}
+
 const char* po_describe(void)
 {
   return "plain-C restatement of psc-code/psc 1vb hot path (oracle/psc_oracle.c), "

@@ -223,6 +223,19 @@ typedef struct
 double po_heating_spot_foil_H(const po_grid* g, const po_heating_prm* hp, const double crd[3], int kind);
 long po_heating(const po_grid* g, const po_heating_prm* hp, po_prt* prts, const unsigned* off, int patch_begin);
 
+/* BoundaryInjector::inject (boundary_injector.hxx:93-160) on the generator's draws */
+typedef struct
+{
+  int patch;
+  int idx[3];  /* the ghost cell the particle was generated in (initial_idx) */
+  double x[3]; /* patch-local (generator.get(cell_corner, dx)) */
+  double u[3];
+  double w;
+  int kind;
+} po_inject_cand;
+long po_boundary_inject(const po_grid* g, float* flds, const po_inject_cand* cand, long n, po_prt* out,
+                        int* out_patch);
+
 void po_best_mapping(int n_ranks, const double* capability, int n_patches,
                      const double* loads, int* n_patches_by_rank);
 void po_get_loads(const po_grid* g, const unsigned* off, double factor_fields,

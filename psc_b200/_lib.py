@@ -54,6 +54,14 @@ class HeatingParams(C.Structure):
     ]
 
 
+class JPath(C.Structure):
+    """psc_b200_jpath"""
+    _fields_ = [
+        ("patch", C.c_int), ("lg", C.c_int * 3), ("xm", C.c_float * 3), ("xp", C.c_float * 3),
+        ("v", C.c_float * 3), ("qni_wni", C.c_float),
+    ]
+
+
 class PscB200Error(RuntimeError):
     pass
 
@@ -121,6 +129,7 @@ def load():
         "psc_b200_check_gauss": [CTX, C.POINTER(C.c_double)],
         "psc_b200_collide": [CTX, C.POINTER(CollisionParams), P],
         "psc_b200_heating_spot_foil": [CTX, C.POINTER(HeatingParams), P],
+        "psc_b200_deposit_j": [CTX, P, C.c_uint64],
         "psc_b200_checkpoint_write": [CTX, C.c_char_p, C.c_int64],
         "psc_b200_checkpoint_read": [CTX, C.c_char_p, C.POINTER(C.c_int64)],
         "psc_b200_energies": [CTX, P],

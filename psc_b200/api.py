@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GridDesc, StepParams, CollisionParams, HeatingParams, PscB200Error, load, check, i3, d3, MAX_KINDS
+from ._lib import GridDesc, StepParams, CollisionParams, HeatingParams, JPath, PscB200Error, load, check, i3, d3, MAX_KINDS
 
 JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS = range(10)
 BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING = range(4)
@@ -46,6 +46,8 @@ class Grid:
             fnqs = 1.0 / nicell if nicell else 1.0
         d.fnqs, d.eta = fnqs, eta
         self.cori = 1.0 / nicell if nicell else 1.0  # grid.norm.cori (grid.hxx:288)
+        self.prts_per_unit_density = float(nicell) if nicell else 1.0  # grid.norm (grid.hxx:291)
+        self.corner, self.length = tuple(float(v) for v in corner), tuple(float(v) for v in length)
         assert len(kinds) <= MAX_KINDS
         d.n_kinds = len(kinds)
         for k, (q, m) in enumerate(kinds):
@@ -82,6 +84,20 @@ class Grid:
 
     def patch_begin(self):
         return self.lib.psc_b200_patch_begin(self.ctx)
+
+    def patch_off(self, p):
+        """cell offset of local patch p ("bydim" order, mrc_domain_lib.c:21-35)"""
+        g = self.patch_begin() + p
+        idx3 = (g % self.np3[0], (g // self.np3[0]) % self.np3[1], g // (self.np3[0] * self.np3[1]))
+        return tuple(i * l for i, l in zip(idx3, self.ldims))
+
+    def patch_xb(self, p):
+        """Grid_t::Patch::xb (grid.hxx:82-86)"""
+        return tuple(o * dx + c for o, dx, c in zip(self.patch_off(p), self.dx, self.corner))
+
+    def at_boundary_lo(self, p, d):
+        """Grid_t::atBoundaryLo (grid.hxx:142-145)"""
+        return self.patch_off(p)[d] == 0
 
     def sync(self):
         check(self.lib.psc_b200_sync(self.ctx))
@@ -310,6 +326,114 @@ class Heating:
         return n.value
 
 
+class ParticleGeneratorMaxwellian:
+    """ParticleGeneratorMaxwellian (src/include/boundary_injector.hxx:16-57): uniform position
+    inside the cell, each momentum component normal(mean_u, sqrt(T / m)); `kind` = (q, m).
+    Host code in the reference (rng::Uniform / rng::Normal), host code here (numpy)."""
+
+    def __init__(self, kind_idx, kind, mean_u, temperature, correct_gamma=False, rng=None):
+        self.kind_idx, self.correct_gamma = kind_idx, correct_gamma
+        self.mean_u = [float(v) for v in mean_u]
+        self.stdev_u = [float(np.sqrt(t / kind[1])) for t in temperature]
+        self.rng = rng or np.random.default_rng(0)
+
+    def get(self, min_pos, pos_range):
+        x = [m + self.rng.random() * r for m, r in zip(min_pos, pos_range)]
+        u = [m + s * self.rng.standard_normal() for m, s in zip(self.mean_u, self.stdev_u)]
+        if self.correct_gamma:  # vel_to_4vel (setup_particles.hxx:39-43)
+            gamma = 1.0 / np.sqrt(1.0 - sum(c * c for c in u))
+            u = [c * gamma for c in u]
+        return x, u, 1.0, self.kind_idx
+
+
+class BoundaryInjector:
+    """BoundaryInjectorB200: BoundaryInjector<ParticleGenerator, PushParticles>
+    (src/include/boundary_injector.hxx:66-167).  Every step, for every ghost cell just below
+    the lower y wall of the patches that touch it, `n_in_cell()` particles of an imaginary
+    unit-density population are drawn from `generator.get(min_pos, pos_range)` -- returning
+    (x[3], u[3], w, kind), positions patch-local -- advanced one step in y, and those that
+    enter the patch are injected, with the current of their way in deposited into J.
+
+    The generator and the cell loop are host code, exactly as in the reference; the device
+    takes the accepted particles (Mparticles.inject) and the deposit (psc_b200_deposit_j).
+    The arithmetic between the draw and the hand-over runs in the configuration's real_t
+    (float32).  `n_in_cell` defaults to get_n_in_cell(1, prts_per_unit_density, true)
+    (setup_particles.hxx:110-122): nicell + a uniform draw, truncated."""
+
+    INJECT_DIM = 1
+
+    def __init__(self, generator, grid, n_in_cell=None, rng=None):
+        self.generator, self.grid_ = generator, grid
+        self.rng = rng or np.random.default_rng(0)
+        self.n_in_cell = n_in_cell or (lambda: int(np.float32(grid.prts_per_unit_density) +
+                                                   np.float32(self.rng.random())))
+        self.n_injected = 0
+
+    def candidates(self):
+        """the draws of one inject() call: list of (patch, idx, x, u, w, kind)"""
+        g = self.grid_
+        out = []
+        D = self.INJECT_DIM
+        for p in range(g.n_patches()):
+            if not g.at_boundary_lo(p, D):
+                continue
+            ilo, ihi = [0, 0, 0], list(g.ldims)
+            ilo[D], ihi[D] = -1, 0
+            # VecRange(ilo, ihi) (kg/VecRange.hxx): the last index runs fastest
+            for i in range(ilo[0], ihi[0]):
+                for j in range(ilo[1], ihi[1]):
+                    for k in range(ilo[2], ihi[2]):
+                        idx = (i, j, k)
+                        # Real3 cell_corner = Double3(idx) * dx: narrowed to real_t
+                        corner = [float(np.float32(ii * dx)) for ii, dx in zip(idx, g.dx)]
+                        for _ in range(self.n_in_cell()):
+                            x, u, w, kind = self.generator.get(corner, g.dx)
+                            out.append((p, idx, tuple(x), tuple(u), float(w), int(kind)))
+        return out
+
+    def inject(self, mprts, mflds, cand=None):
+        g = self.grid_
+        D = self.INJECT_DIM
+        cand = self.candidates() if cand is None else cand
+        f32 = np.float32
+        dt = f32(g.dt)
+        dxi = [f32(n / L) for n, L in zip(g.gdims, g.length)]  # Real3 dxi = grid.domain.dx_inv (domain.hxx:44)
+        n_by_patch = np.zeros(g.n_patches(), dtype=np.uint32)
+        recs, paths = [], []
+        for (p, idx, x, u, w, kind) in sorted(cand, key=lambda c: c[0]):  # (stable: patch order)
+            uf = [f32(c) for c in u]
+            root = f32(1.) / np.sqrt(f32(1.) + uf[0] * uf[0] + uf[1] * uf[1] + uf[2] * uf[2])
+            v = [c * root for c in uf]
+            x0 = [f32(c) for c in x]
+            x1 = list(x0)
+            x1[D] = x1[D] + f32(1.) * dt * v[D]
+            if x1[D] < 0:
+                continue  # did not enter the patch
+            xb = g.patch_xb(p)
+            rec = np.zeros((), dtype=PRT_DTYPE)
+            rec["x"] = [f32(float(a) + b) - f32(b) for a, b in zip(x1, xb)]
+            rec["u"] = uf
+            rec["kind"] = kind
+            rec["qni_wni"] = f32(w * g.kinds[kind][0])
+            recs.append(rec)
+            n_by_patch[p] += 1
+            jp = JPath()
+            jp.patch = p
+            for d in range(3):
+                jp.lg[d] = idx[d]
+                jp.xm[d] = x0[d] * dxi[d]
+                jp.xp[d] = x1[d] * dxi[d]
+                jp.v[d] = v[d]
+            jp.qni_wni = f32(g.kinds[kind][0] * w)
+            paths.append(jp)
+        if recs:
+            mprts.inject(np.array(recs, dtype=PRT_DTYPE), n_by_patch)
+            arr = (JPath * len(paths))(*paths)
+            check(g.lib.psc_b200_deposit_j(g.ctx, arr, len(paths)))
+        self.n_injected = len(recs)
+        return len(recs)
+
+
 class BndParticles:
     """BndParticlesB200 (bnd_particles_impl.hxx:234-247)"""
 
@@ -476,6 +600,7 @@ class Psc:
     def __init__(self, grid, mflds, mprts, sort_interval=1, marder_interval=0,
                  marder_diffusion=0.9, marder_loop=3, checks=None, fused=False, collision=None):
         self.collision = collision
+        self.injectors_ = []
         self.grid_, self.mflds_, self.mprts_ = grid, mflds, mprts
         self.sort_interval, self.marder_interval = sort_interval, marder_interval
         self.marder = Marder(grid, marder_diffusion, marder_loop)
@@ -483,6 +608,13 @@ class Psc:
         self.fused = fused
         self.sort_, self.pushp_, self.pushf_ = Sort(), PushParticles(), PushFields()
         self.bnd_, self.bndf, self.bndp_ = Bnd(), BndFields(), BndParticles(grid)
+
+    def add_injector(self, injector):
+        """Psc::add_injector (psc.hxx:172-176): anything with inject(mprts, mflds).  Injectors
+        act between the push and the particle exchange (psc.hxx:391-399), so a step with
+        injectors is issued operator by operator rather than as the single fused call."""
+        assert injector is not None
+        self.injectors_.append(injector)
 
     def initialize(self):
         """psc.hxx:220-238 pre_first_step: fill H, J, E ghosts"""
@@ -502,7 +634,7 @@ class Psc:
             # psc.hxx:356-371: sort, then collide (the pairing walks cell runs)
             self.sort_(mprts)
             self.collision(mprts, step=t)
-        if self.fused:
+        if self.fused and not self.injectors_:
             prm = StepParams(sort=int(do_sort), marder_loop=self.marder.loop if do_marder else 0,
                              marder_diffusion=self.marder.diffusion, push_fields=1,
                              checks=int(self.checks.continuity.should_do_check(t)))
@@ -516,6 +648,8 @@ class Psc:
             self.sort_(mprts)                                    # psc.hxx:356-361
         self.checks.continuity.before_particle_push(mprts)       # :379-384
         self.pushp_.push_mprts(mprts, mflds)                     # :389
+        for injector in self.injectors_:                         # :391-399
+            injector.inject(mprts, mflds)
         self.bndp_(mprts)                                        # :412
         self.bndf.add_ghosts_J(mflds)                            # :417
         self.bnd_.add_ghosts(mflds, JXI, JXI + 3)                # :418

@@ -838,6 +838,24 @@ int psc_b200_heating_spot_foil(psc_b200_ctx* ctx, const psc_b200_heating_params*
   GUARD(PSC_TRY(store_ready(c)); return heating_spot_foil(c, prm, n_kicked);)
 }
 
+int psc_b200_deposit_j(psc_b200_ctx* ctx, const psc_b200_jpath* paths, uint64_t n)
+{
+  GUARD(
+    if (n == 0) { return 0; }
+    if (!paths || n > 0xffffffffu) { return fail("deposit_j: bad trajectory list"); }
+    for (uint64_t i = 0; i < n; i++) {
+      if (paths[i].patch < 0 || paths[i].patch >= c->g.n_patches) {
+        return fail("deposit_j: trajectory " + std::to_string(i) + " names patch " +
+                    std::to_string(paths[i].patch) + " of " + std::to_string(c->g.n_patches));
+      }
+    }
+    PSC_TRY(c->scr[0].reserve(n * sizeof(psc_b200_jpath)));
+    psc_b200_jpath* d = c->scr[0].as<psc_b200_jpath>();
+    // (pageable source: the copy is staged and the call returns with `paths` free again)
+    PSC_CUDA_TRY(cudaMemcpyAsync(d, paths, n * sizeof(psc_b200_jpath), cudaMemcpyHostToDevice, c->stream));
+    return c->opt_fma ? deposit_paths_fast(c, d, (uint32_t)n) : deposit_paths_exact(c, d, (uint32_t)n);)
+}
+
 int psc_b200_checkpoint_write(psc_b200_ctx* ctx, const char* path, int64_t timestep)
 {
   GUARD(PSC_TRY(store_ready(c)); return checkpoint_write(c, path, timestep);)

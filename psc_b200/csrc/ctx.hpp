@@ -237,6 +237,8 @@ int selftest_math(Ctx* c, uint64_t* n_bad);
 // ---- push.cu (two builds of the same source: exact = -fmad=false, fast = FMA)
 int push_mprts_exact(Ctx* c);
 int push_mprts_fast(Ctx* c);
+int deposit_paths_exact(Ctx* c, const psc_b200_jpath* d_paths, uint32_t n);
+int deposit_paths_fast(Ctx* c, const psc_b200_jpath* d_paths, uint32_t n);
 
 // ---- sort.cu
 int sort_mprts(Ctx* c);

@@ -263,6 +263,44 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Current of trajectories handed over by the host (BoundaryInjector::inject,
+// boundary_injector.hxx:136-147: current.calc_j(J, xm, xp, lf, lg, qni_wni, v) for every
+// particle that entered through the wall): one thread per trajectory, the same walk and
+// the same leaf values as the pusher's, added to J with global atomics.
+template <int DIM, int DEPOSIT>
+__global__ void __launch_bounds__(128)
+  k_deposit_paths(GridDev G, uint32_t n, const psc_b200_jpath* __restrict__ paths, float* __restrict__ flds,
+                  long slot_len)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) {
+    return;
+  }
+  const psc_b200_jpath P = paths[i];
+  if ((unsigned)P.patch >= (unsigned)G.n_patches) {
+    return; // (the host entry has checked the list: never taken)
+  }
+  float* F = flds + P.patch * slot_len;
+  pm::Trajectory t;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    t.xm[d] = P.xm[d];
+    t.xp[d] = P.xp[d];
+    t.v[d] = P.v[d];
+    t.lg[d] = P.lg[d];
+    t.lf[d] = pm::fint(P.xp[d]);
+  }
+  Walker<DIM, DEPOSIT> w;
+  float val[12];
+  int ci[3];
+  bool more = w.first(G.pc, t, P.qni_wni, ci, val);
+  leaf_to_global<DIM>(G, F, ci, val);
+  while (more) {
+    more = w.next(G.pc, P.qni_wni, ci, val);
+    leaf_to_global<DIM>(G, F, ci, val);
+  }
+}
+
 // ---------------------------------------------------------------- tiled kernel
 
 // mbarrier / bulk-copy PTX (sm_90+): one thread arms the barrier with the byte count,
@@ -1304,6 +1342,32 @@ int PUSH_CAT(push_gap_, PUSH_VARIANT)(Ctx* c)
     return push_dim<pm::DIM_YZ, pm::DEPOSIT_VAR1>(c, true);
   }
   return push_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c, true);
+#endif
+}
+
+template <int DIM, int DEPOSIT>
+static int deposit_paths_dim(Ctx* c, const psc_b200_jpath* d_paths, uint32_t n)
+{
+  KernelScope ks(c, "deposit_paths");
+  PUSH_VARIANT::k_deposit_paths<DIM, DEPOSIT><<<div_up(n, 128), 128, 0, c->stream>>>(c->gd, n, d_paths, c->fld(0),
+                                                                     c->fld_slot_len(0));
+  c->n_launches++;
+  return check_launch(c, "deposit_paths");
+}
+
+// d_paths: n trajectories on the device (capi.cu psc_b200_deposit_j stages them)
+int PUSH_CAT(deposit_paths_, PUSH_VARIANT)(Ctx* c, const psc_b200_jpath* d_paths, uint32_t n)
+{
+  using namespace PUSH_VARIANT;
+#ifdef PUSH_PROBE
+  return deposit_paths_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c, d_paths, n);
+#else
+  if (c->gd.dim == pm::DIM_XYZ) {
+    return deposit_paths_dim<pm::DIM_XYZ, pm::DEPOSIT_SPLIT>(c, d_paths, n);
+  } else if (c->gd.deposit == pm::DEPOSIT_VAR1) {
+    return deposit_paths_dim<pm::DIM_YZ, pm::DEPOSIT_VAR1>(c, d_paths, n);
+  }
+  return deposit_paths_dim<pm::DIM_YZ, pm::DEPOSIT_SPLIT>(c, d_paths, n);
 #endif
 }
 

@@ -36,7 +36,7 @@ struct Kind
 // grid.hxx:265-293: dimensionless normalisation, fnqs = 1 / nicell
 struct Normalization
 {
-  double fnqs = 1., eta = 1., cori = 1.;
+  double fnqs = 1., eta = 1., cori = 1., prts_per_unit_density = 1.;
 };
 
 // grid.hxx:35-61
@@ -64,6 +64,7 @@ struct Grid
     ldims = domain.ldims;
     norm.fnqs = 1. / nicell;
     norm.cori = 1. / nicell; // grid.hxx:288
+    norm.prts_per_unit_density = nicell; // grid.hxx:287
     // "bydim" patch order (libmrc/src/mrc_domain_lib.c:21-35)
     for (int pz = 0; pz < np[2]; pz++) {
       for (int py = 0; py < np[1]; py++) {
@@ -83,6 +84,7 @@ struct Grid
 
   int n_patches() const { return (int)patches.size(); }
   bool isInvar(int d) const { return domain.gdims[d] == 1; }
+  bool atBoundaryLo(int p, int d) const { return patches[p].off[d] == 0; } // grid.hxx:114
 
   Int3 ldims;
   Domain domain;

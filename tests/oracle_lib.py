@@ -374,14 +374,45 @@ def energies(grid, flds, prts, off):
     return out
 
 
-def step(grid, flds, prts, off, sort_now=True, marder_loop=0, marder_diffusion=0.9):
-    """Psc::step ordering (psc.hxx:321-486) with the oracle's operators; periodic
-    or conducting-wall boundaries, no collisions/injection/output."""
+class PoInjectCand(C.Structure):
+    _fields_ = [("patch", C.c_int), ("idx", C.c_int * 3), ("x", C.c_double * 3), ("u", C.c_double * 3),
+                ("w", C.c_double), ("kind", C.c_int)]
+
+
+def boundary_inject(grid, flds, prts, off, cand):
+    """BoundaryInjector::inject on the generator's draws `cand` = [(patch, idx, x, u, w, kind)]:
+    returns (prts, off) with the accepted particles appended to their patches (push_back order)
+    and the current of their way in added to flds' J."""
+    L = lib()
+    L.po_boundary_inject.restype = C.c_long
+    arr = (PoInjectCand * max(len(cand), 1))()
+    for i, (p, idx, x, u, w, kind) in enumerate(cand):
+        arr[i].patch, arr[i].w, arr[i].kind = p, w, kind
+        for d in range(3):
+            arr[i].idx[d], arr[i].x[d], arr[i].u[d] = idx[d], x[d], u[d]
+    out = np.zeros(max(len(cand), 1), dtype=PRT_DTYPE)
+    out_patch = np.zeros(max(len(cand), 1), dtype=np.int32)
+    n = L.po_boundary_inject(grid.byref(), ptr(flds), arr, C.c_long(len(cand)), ptr(out), ptr(out_patch))
+    out, out_patch = out[:n], out_patch[:n]
+    parts = []
+    for p in range(grid.n_patches):
+        parts.append(prts[off[p]:off[p + 1]])
+        parts.append(out[out_patch == p])
+    new = np.concatenate(parts) if parts else prts
+    n_by = [int(off[p + 1] - off[p]) + int((out_patch == p).sum()) for p in range(grid.n_patches)]
+    return np.ascontiguousarray(new), off_from_counts(n_by)
+
+
+def step(grid, flds, prts, off, sort_now=True, marder_loop=0, marder_diffusion=0.9, inject=None):
+    """Psc::step ordering (psc.hxx:321-486) with the oracle's operators; `inject(flds, prts,
+    off) -> (prts, off)` stands for the injectors' slot between push and exchange (:391-399)."""
     L = lib()
     G = grid.byref()
     if sort_now:
         L.po_sort(G, ptr(prts), ptr(off), None)
     L.po_push_mprts(G, ptr(flds), ptr(prts), ptr(off))
+    if inject is not None:
+        prts, off = inject(flds, prts, off)
     prts, off, _ = bnd_particles(grid, prts, off)
     L.po_bndf_add_ghosts_J(G, ptr(flds))
     L.po_add_ghosts(G, ptr(flds), NR_FIELDS, JXI, JXI + 3)
