@@ -152,6 +152,18 @@ int psc_b200_mflds_zero(psc_b200_ctx* ctx, int field_id, int mb, int me);
 /* uniform value everywhere incl. ghosts (setupFields with a constant lambda) */
 int psc_b200_mflds_fill(psc_b200_ctx* ctx, int field_id, int m, float value);
 
+/* ---- OutputFieldsItem's hand-off (src/include/output_fields.hxx:150-236): what happens to an
+ * item (the state fields = Item_jeh, or a moment container) between the operator that produced
+ * it and the writer stays on the device except for the one interior copy a write needs.
+ *   mflds_add:   y[y_mb + m] += x[x_mb + m], m < n_comps   (:203  tfd = tfd + pfd, float + float)
+ *   mflds_scale: y[m] = float(a * double(y[m]))            (:221  (1. / naccum) * tfd)
+ *   mflds_download_interior: host[p][m - mb][k][j][i] over the patches' own cells
+ *                            (psc::mflds::interior, :179) -- 1 / (1 + 2 ibn / ldims)^3 of the bytes
+ *                            of mflds_download ---- */
+int psc_b200_mflds_add(psc_b200_ctx* ctx, int y_field_id, int y_mb, int x_field_id, int x_mb, int n_comps);
+int psc_b200_mflds_scale(psc_b200_ctx* ctx, int field_id, int mb, int me, double a);
+int psc_b200_mflds_download_interior(psc_b200_ctx* ctx, int field_id, int mb, int me, float* host);
+
 /* ---- PushParticles::push_mprts (push_particles_1vb.hxx:27-84) ---- */
 int psc_b200_push_mprts(psc_b200_ctx* ctx);
 /* ---- Sort::operator() = SortCountsort2 (psc_sort_impl.hxx:65-124) ---- */

@@ -38,6 +38,7 @@
 
 #include "../psc_b200.h"
 
+#include <algorithm>
 #include <array>
 #include <cassert>
 #include <cmath>
@@ -454,6 +455,28 @@ public:
     assert(h.size() == (size_t)n_patches() * (me - mb) * patch_len());
     PSC_B200_CHECK(psc_b200_mflds_upload(ctx(), id_, mb, me, h.data()));
   }
+  // what OutputFieldsItem does to an item (output_fields.hxx:179,203,221), on the device:
+  // this[mb + m] += other[other_mb + m]
+  void add(const MfieldsB200& other, int mb = 0, int other_mb = 0, int n_comps = -1)
+  {
+    if (n_comps < 0) {
+      n_comps = std::min(n_comps_ - mb, other.n_comps_ - other_mb);
+    }
+    PSC_B200_CHECK(psc_b200_mflds_add(ctx(), id_, mb, other.id_, other_mb, n_comps));
+  }
+  // this[m] = float(a * double(this[m]))
+  void scale(double a) { PSC_B200_CHECK(psc_b200_mflds_scale(ctx(), id_, 0, n_comps_, a)); }
+  // psc::mflds::interior on the host: [p][m][k][j][i] over the patches' own cells
+  std::vector<float> download_interior(int mb, int me) const
+  {
+    int ld[3], ibn[3];
+    PSC_B200_CHECK(psc_b200_get_ldims(ctx(), ld, ibn));
+    std::vector<float> h((size_t)n_patches() * (me - mb) * ld[0] * ld[1] * ld[2]);
+    PSC_B200_CHECK(psc_b200_mflds_download_interior(ctx(), id_, mb, me, h.data()));
+    return h;
+  }
+  std::vector<float> download_interior() const { return download_interior(0, n_comps_); }
+
   // offset of (m, i, j, k) of patch p inside a download(mb, me) buffer
   size_t index(int p, int m_rel, int n_m, int i, int j, int k) const
   {
@@ -639,6 +662,28 @@ public:
     : mres_(grid, psc_b200_moment_n_comps(Context<GridT>::get(grid)->ctx(), WHICH))
   {}
   int n_comps() const { return mres_.n_comps(); }
+  // addKindSuffix (fields_item.hxx:22-32) over the moment's stems (psc/moment.hxx:130-133,
+  // 158-161, 185-188, 217-220, 246-249, 281-286): kinds outermost
+  std::vector<std::string> comp_names() const
+  {
+    static const std::vector<std::string> stems[] = {
+      {"n"},
+      {"vx", "vy", "vz"},
+      {"px", "py", "pz"},
+      {"Txx", "Tyy", "Tzz", "Txy", "Txz", "Tyz"},
+      {"rho", "jx", "jy", "jz", "px", "py", "pz", "txx", "tyy", "tzz", "txy", "tyz", "tzx"}};
+    if (WHICH == PSC_B200_MOMENT_RHO_NC) {
+      return {"rho"};
+    }
+    std::vector<std::string> result;
+    const auto& kinds = mres_.grid().kinds;
+    for (size_t k = 0; k < kinds.size(); k++) {
+      for (const auto& stem : stems[WHICH]) {
+        result.emplace_back(stem + "_" + kinds[k].name);
+      }
+    }
+    return result;
+  }
   Mfields& operator()(Mparticles& mprts)
   {
     PSC_B200_CHECK(psc_b200_moment_1st(mprts.ctx(), mres_.id(), WHICH));
@@ -661,6 +706,205 @@ template <typename GridT>
 using Moments_1st_B200 = MomentB200<GridT, PSC_B200_MOMENT_ALL>;
 template <typename GridT>
 using Moment_rho_1st_nc_B200 = MomentB200<GridT, PSC_B200_MOMENT_RHO_NC>;
+
+// ----------------------------------------------------------------------
+// OutputFields / OutputMoments (src/include/output_fields.hxx).  The parameter structs are
+// the reference's, member for member; OutputFieldsItemB200 is its OutputFieldsItem with the
+// item left on the device: evaluated there (Item_jeh = the state fields themselves, no copy;
+// the moments by psc_b200_moment_1st), accumulated for the time average there, and only what
+// a writer is handed crosses to the host -- the interior of the item (pfd) or of the mean
+// (tfd).  Writer: `explicit operator bool`, `open(pfx, dir)`, `write_step(grid, rn, rx, data,
+// name, comp_names)` as WriterMRC / WriterADIOS2 have them (writer_mrc.hxx:8-123), `data`
+// being a HostItemB200 (interior, [p][m][k][j][i]) instead of a gtensor expression.
+
+struct BaseOutputFieldItemParamsB200 // output_fields.hxx:63-78
+{
+  int out_interval = 0; // difference between output timesteps (0 = disable)
+  std::string data_dir = ".";
+  std::array<int, 3> rn = {};
+  std::array<int, 3> rx = {10000000, 10000000, 10000000};
+
+  bool enabled() const { return out_interval > 0; }
+  bool do_out(int timestep) const { return enabled() && timestep % out_interval == 0; }
+};
+
+struct OutputPfieldItemParamsB200 : BaseOutputFieldItemParamsB200
+{};
+
+struct OutputTfieldItemParamsB200 : BaseOutputFieldItemParamsB200 // :83-101
+{
+  int average_length = 1000000; // max range of timesteps over which to average
+  int sample_interval = 1;      // difference between timesteps used for average
+
+  bool do_accum(int timestep) const
+  {
+    if (!enabled()) {
+      return false;
+    }
+    int n_intervals_elapsed = (timestep - 1) / out_interval;
+    int next_out = out_interval * (n_intervals_elapsed + 1); // could be this timestep
+    bool in_averaging_range = next_out - timestep < average_length;
+    bool on_averaging_step = (next_out - timestep) % sample_interval == 0;
+    return in_averaging_range && on_averaging_step;
+  }
+};
+
+struct OutputFieldsItemParamsB200 // :139-143
+{
+  OutputPfieldItemParamsB200 pfield;
+  OutputTfieldItemParamsB200 tfield;
+};
+
+struct HostItemB200
+{
+  std::vector<float> data; // [p][m][k][j][i], the patches' own cells
+  int n_patches, n_comps;
+  std::array<int, 3> ldims;
+  int timestep; // the step the item belongs to (inside PSC: grid.timestep())
+};
+
+// keeps what it was given (tests; a deck inside PSC wraps WriterMRC / WriterADIOS2 instead)
+struct WriterMemoryB200
+{
+  struct Step
+  {
+    int timestep;
+    std::string name;
+    std::vector<std::string> comp_names;
+    HostItemB200 item;
+  };
+  explicit operator bool() const { return !pfx.empty(); }
+  void open(const std::string& pfx_, const std::string& dir_ = ".")
+  {
+    assert(pfx.empty());
+    pfx = pfx_, dir = dir_;
+  }
+  template <typename GridT>
+  void write_step(const GridT& grid, const std::array<int, 3>&, const std::array<int, 3>&, HostItemB200&& item,
+                  const std::string& name, const std::vector<std::string>& comp_names)
+  {
+    const int timestep = item.timestep;
+    steps.push_back(Step{timestep, name, comp_names, std::move(item)});
+    (void)grid;
+  }
+  std::string pfx, dir;
+  std::vector<Step> steps;
+};
+
+template <typename GridT>
+struct Item_jeh_B200 // fields_item_fields.hxx:14-31
+{
+  static std::string name() { return "jeh"; }
+  static int n_comps() { return PSC_B200_NR_FIELDS; }
+  static std::vector<std::string> comp_names()
+  {
+    return {"jx_ec", "jy_ec", "jz_ec", "ex_ec", "ey_ec", "ez_ec", "hx_fc", "hy_fc", "hz_fc"};
+  }
+  MfieldsB200<GridT>& operator()(MfieldsStateB200<GridT>& mflds) const { return mflds; }
+};
+
+template <typename GridT>
+struct GetItemJehB200 // :106-117
+{
+  static std::string suffix() { return ""; }
+  explicit GetItemJehB200(const GridT&) {}
+  MfieldsB200<GridT>& get_item(MparticlesB200<GridT>&, MfieldsStateB200<GridT>& mflds) { return item_(mflds); }
+  std::string name() const { return item_.name(); }
+  std::vector<std::string> comp_names() const { return item_.comp_names(); }
+  Item_jeh_B200<GridT> item_;
+};
+
+template <typename GridT>
+struct GetItemMomentsB200 // :119-131 (Item_Moments = Moments_1st, all 13 moments per kind)
+{
+  static std::string suffix() { return "_moments"; }
+  explicit GetItemMomentsB200(const GridT& grid) : item_(grid) {}
+  MfieldsB200<GridT>& get_item(MparticlesB200<GridT>& mprts, MfieldsStateB200<GridT>&) { return item_(mprts); }
+  std::string name() const { return item_.name(); }
+  std::vector<std::string> comp_names() const { return item_.comp_names(); }
+  Moments_1st_B200<GridT> item_;
+};
+
+template <typename GridT, typename GetItem, typename Writer = WriterMemoryB200>
+class OutputFieldsItemB200 : public OutputFieldsItemParamsB200 // :150-236
+{
+public:
+  using Mparticles = MparticlesB200<GridT>;
+  using MfieldsState = MfieldsStateB200<GridT>;
+  using Mfields = MfieldsB200<GridT>;
+
+  OutputFieldsItemB200(const GridT& grid, const OutputFieldsItemParamsB200& prm = {})
+    : OutputFieldsItemParamsB200{prm}, get_item_(grid)
+  {}
+  virtual ~OutputFieldsItemB200() {}
+
+  // DiagnosticBase::perform_diagnostic; `timestep` = grid.timestep() inside PSC
+  virtual void perform_diagnostic(Mparticles& mprts, MfieldsState& mflds, int timestep)
+  {
+    const GridT& grid = mflds.grid();
+    bool do_pfield = pfield.do_out(timestep);
+    bool do_tfield = tfield.do_out(timestep);
+    bool do_tfield_accum = tfield.do_accum(timestep);
+    if (!(do_pfield || do_tfield_accum)) {
+      return;
+    }
+    Mfields& item = get_item_.get_item(mprts, mflds);
+    if (do_pfield) {
+      if (!io_pfd_) {
+        io_pfd_.open("pfd" + GetItem::suffix(), pfield.data_dir);
+      }
+      io_pfd_.write_step(grid, pfield.rn, pfield.rx, host_item(item, timestep), get_item_.name(),
+                         get_item_.comp_names());
+    }
+    if (do_tfield_accum) {
+      if (!tfd_) {
+        tfd_.reset(new Mfields{grid, item.n_comps()});
+      }
+      tfd_->add(item);
+      naccum_++;
+    }
+    if (do_tfield && naccum_ > 0) {
+      // (naccum_ == 0 happens at the initial output when average_length < out_interval; the
+      // reference dereferences its unallocated tfd_ there)
+      if (!io_tfd_) {
+        io_tfd_.open("tfd" + GetItem::suffix(), tfield.data_dir);
+      }
+      // convert accumulated values to correct temporal mean
+      tfd_->scale(1. / naccum_);
+      io_tfd_.write_step(grid, tfield.rn, tfield.rx, host_item(*tfd_, timestep), get_item_.name(),
+                         get_item_.comp_names());
+      naccum_ = 0;
+      tfd_->zero();
+    }
+  }
+
+  Writer& io_pfd() { return io_pfd_; }
+  Writer& io_tfd() { return io_tfd_; }
+
+private:
+  static HostItemB200 host_item(const Mfields& m, int timestep)
+  {
+    HostItemB200 h;
+    h.timestep = timestep;
+    h.data = m.download_interior();
+    h.n_patches = m.n_patches();
+    h.n_comps = m.n_comps();
+    auto im = m.im(), ibn = m.ibn();
+    h.ldims = {im[0] - 2 * ibn[0], im[1] - 2 * ibn[1], im[2] - 2 * ibn[2]};
+    return h;
+  }
+
+  GetItem get_item_;
+  Writer io_pfd_;
+  Writer io_tfd_;
+  std::unique_ptr<Mfields> tfd_;
+  int naccum_ = 0;
+};
+
+template <typename GridT, typename Writer = WriterMemoryB200>
+using OutputFieldsB200 = OutputFieldsItemB200<GridT, GetItemJehB200<GridT>, Writer>; // :238-243
+template <typename GridT, typename Writer = WriterMemoryB200>
+using OutputMomentsB200 = OutputFieldsItemB200<GridT, GetItemMomentsB200<GridT>, Writer>; // :245-250
 
 // Collision (psc.hxx:111,363-371; decks: `Collision collision{grid, interval, nu}`, e.g.
 // psc_bubble_yz.cxx:303-306): binary Coulomb collisions inside every cell on the device
@@ -1189,6 +1433,35 @@ public:
     injectors_.push_back([injector](Mparticles& mprts, MfieldsState& mflds) { injector->inject(mprts, mflds); });
   }
 
+  // Psc::add_diagnostic / perform_diagnostics / integrate (psc.hxx:184-198, 514-528, 243-310)
+  void add_diagnostic(std::function<void(Mparticles&, MfieldsState&, int)> diagnostic)
+  {
+    diagnostics_.push_back(std::move(diagnostic));
+  }
+  template <typename Diagnostic>
+  void add_diagnostic(Diagnostic* diagnostic)
+  {
+    assert(diagnostic);
+    diagnostics_.push_back([diagnostic](Mparticles& mprts, MfieldsState& mflds, int timestep) {
+      diagnostic->perform_diagnostic(mprts, mflds, timestep);
+    });
+  }
+  void perform_diagnostics()
+  {
+    for (auto& diagnostic : diagnostics_) {
+      diagnostic(mprts_, mflds_, timestep_);
+    }
+  }
+  void integrate(int nmax)
+  {
+    initialize();
+    perform_diagnostics(); // initial output
+    while (timestep_ < nmax) {
+      (*this)();
+      perform_diagnostics();
+    }
+  }
+
   void operator()()
   {
     const int t = ++timestep_;
@@ -1254,6 +1527,7 @@ private:
   typename Config::Marder marder_;
   typename Config::Checks checks_;
   std::vector<std::function<void(Mparticles&, MfieldsState&)>> injectors_;
+  std::vector<std::function<void(Mparticles&, MfieldsState&, int)>> diagnostics_;
   int timestep_ = 0;
 };
 

@@ -8,6 +8,7 @@ from ._lib import GridDesc, StepParams, CollisionParams, HeatingParams, JPath, P
 from .api import (Moment, MOMENT_N, MOMENT_V, MOMENT_P, MOMENT_T, MOMENT_ALL, MOMENT_RHO_NC,  # noqa: F401
                   Grid, Mparticles, Mfields, MfieldsState, energies, write_checkpoint, read_checkpoint, PushParticles, Sort, BndParticles,  # noqa: F401
                   Bnd, BndFields, PushFields, Marder, Checks, Psc, Collision, Heating, BoundaryInjector, ParticleGeneratorMaxwellian, PRT_DTYPE,
+                  ItemJeh, OutputFieldItemParams, WriterMemory, OutputFieldsItem, OutputFields, OutputMoments,
                   JXI, JYI, JZI, EX, EY, EZ, HX, HY, HZ, NR_FIELDS,
                   BND_FLD_OPEN, BND_FLD_PERIODIC, BND_FLD_CONDUCTING_WALL, BND_FLD_ABSORBING,
                   BND_PRT_REFLECTING, BND_PRT_PERIODIC, BND_PRT_ABSORBING, BND_PRT_OPEN,

@@ -130,6 +130,9 @@ def load():
         "psc_b200_collide": [CTX, C.POINTER(CollisionParams), P],
         "psc_b200_heating_spot_foil": [CTX, C.POINTER(HeatingParams), P],
         "psc_b200_deposit_j": [CTX, P, C.c_uint64],
+        "psc_b200_mflds_add": [CTX, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+        "psc_b200_mflds_scale": [CTX, C.c_int, C.c_int, C.c_int, C.c_double],
+        "psc_b200_mflds_download_interior": [CTX, C.c_int, C.c_int, C.c_int, P],
         "psc_b200_checkpoint_write": [CTX, C.c_char_p, C.c_int64],
         "psc_b200_checkpoint_read": [CTX, C.c_char_p, C.POINTER(C.c_int64)],
         "psc_b200_energies": [CTX, P],

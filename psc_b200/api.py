@@ -50,8 +50,8 @@ class Grid:
         self.corner, self.length = tuple(float(v) for v in corner), tuple(float(v) for v in length)
         assert len(kinds) <= MAX_KINDS
         d.n_kinds = len(kinds)
-        for k, (q, m) in enumerate(kinds):
-            d.q[k], d.m[k] = q, m
+        for k, kind in enumerate(kinds):
+            d.q[k], d.m[k] = kind[0], kind[1]
         d.bc_fld_lo = i3(*(bc_fld_lo or [BND_FLD_PERIODIC] * 3))
         d.bc_fld_hi = i3(*(bc_fld_hi or [BND_FLD_PERIODIC] * 3))
         d.bc_prt_lo = i3(*(bc_prt_lo or [BND_PRT_PERIODIC] * 3))
@@ -65,7 +65,9 @@ class Grid:
         d.device = device
         d.max_n_prts = max_n_prts
         self.desc = d
-        self.kinds = [tuple(k) for k in kinds]
+        self.kinds = [tuple(k[:2]) for k in kinds]
+        # Grid_t::Kind::name (grid.hxx:18-33), the suffix of per-kind output components
+        self.kind_names = [k[2] if len(k) > 2 else "k%d" % i for i, k in enumerate(kinds)]
         self.lib = load()
         self.ctx = C.c_void_p()
         check(self.lib.psc_b200_create(C.byref(d), C.byref(self.ctx)))
@@ -255,6 +257,24 @@ class Mfields:
 
     def fill(self, m, value):
         check(self.grid_.lib.psc_b200_mflds_fill(self.grid_.ctx, self.id, m, value))
+
+    def add(self, other, mb=0, other_mb=0, n_comps=None):
+        """self[mb + m] += other[other_mb + m] (output_fields.hxx:203)"""
+        n = min(self.n_comps_ - mb, other.n_comps_ - other_mb) if n_comps is None else n_comps
+        check(self.grid_.lib.psc_b200_mflds_add(self.grid_.ctx, self.id, mb, other.id, other_mb, n))
+
+    def scale(self, a, mb=0, me=None):
+        """self[m] = float32(a * float64(self[m])) (output_fields.hxx:221)"""
+        me = self.n_comps_ if me is None else me
+        check(self.grid_.lib.psc_b200_mflds_scale(self.grid_.ctx, self.id, mb, me, float(a)))
+
+    def download_interior(self, mb=0, me=None):
+        """psc::mflds::interior on the host: [p][m][k][j][i] over the patches' own cells"""
+        me = self.n_comps_ if me is None else me
+        ld = self.grid_.ldims
+        host = np.zeros((self.n_patches(), me - mb, ld[2], ld[1], ld[0]), dtype=np.float32)
+        check(self.grid_.lib.psc_b200_mflds_download_interior(self.grid_.ctx, self.id, mb, me, _ptr(host)))
+        return host
 
 
 class MfieldsState(Mfields):
@@ -503,15 +523,148 @@ class Moment:
             raise ValueError("unknown moment %r" % (which,))
         self.mres = Mfields(grid, self.n_comps_)
 
+    # per-kind component stems (psc/moment.hxx:130-133,158-161,185-188,217-220,246-249,281-286)
+    STEMS = {MOMENT_N: ["n"], MOMENT_V: ["vx", "vy", "vz"], MOMENT_P: ["px", "py", "pz"],
+             MOMENT_T: ["Txx", "Tyy", "Tzz", "Txy", "Txz", "Tyz"],
+             MOMENT_ALL: ["rho", "jx", "jy", "jz", "px", "py", "pz", "txx", "tyy", "tzz", "txy", "tyz", "tzx"]}
+
     def name(self):
         return self.NAMES[self.which]
 
     def n_comps(self):
         return self.n_comps_
 
+    def comp_names(self):
+        """addKindSuffix (fields_item.hxx:22-32): kinds outermost; rho_1st_nc is just "rho" """
+        if self.which == MOMENT_RHO_NC:
+            return ["rho"]
+        return ["%s_%s" % (stem, kn) for kn in self.grid_.kind_names for stem in self.STEMS[self.which]]
+
     def __call__(self, mprts):
         check(self.grid_.lib.psc_b200_moment_1st(self.grid_.ctx, self.mres.id, self.which))
         return self.mres
+
+
+class ItemJeh:
+    """Item_jeh (fields_item_fields.hxx:14-31): the state fields themselves, no copy"""
+
+    @staticmethod
+    def name():
+        return "jeh"
+
+    @staticmethod
+    def comp_names():
+        return ["jx_ec", "jy_ec", "jz_ec", "ex_ec", "ey_ec", "ez_ec", "hx_fc", "hy_fc", "hz_fc"]
+
+    def __call__(self, mflds):
+        return mflds
+
+
+class OutputFieldItemParams:
+    """BaseOutputFieldItemParams + OutputTfieldItemParams (output_fields.hxx:63-101)"""
+
+    def __init__(self, out_interval=0, data_dir=".", rn=(0, 0, 0), rx=(10000000,) * 3,
+                 average_length=1000000, sample_interval=1):
+        self.out_interval, self.data_dir, self.rn, self.rx = out_interval, data_dir, tuple(rn), tuple(rx)
+        self.average_length, self.sample_interval = average_length, sample_interval
+
+    def enabled(self):
+        return self.out_interval > 0
+
+    def do_out(self, timestep):
+        return self.enabled() and timestep % self.out_interval == 0
+
+    def do_accum(self, timestep):
+        """:88-100 -- on the sampling steps of the averaging window that ends at the next output"""
+        if not self.enabled():
+            return False
+        n_intervals_elapsed = int((timestep - 1) / self.out_interval)  # (C++ integer division truncates)
+        next_out = self.out_interval * (n_intervals_elapsed + 1)
+        in_averaging_range = next_out - timestep < self.average_length
+        on_averaging_step = (next_out - timestep) % self.sample_interval == 0
+        return in_averaging_range and on_averaging_step
+
+
+class WriterMemory:
+    """stands where WriterMRC / WriterADIOS2 stand (writer_mrc.hxx:8-123): open(pfx, dir) once,
+    write_step(grid, rn, rx, data, name, comp_names) per output; keeps what it was given.
+    `data` is the item's interior on the host, [p][m][k][j][i]."""
+
+    def __init__(self):
+        self.pfx = self.dir = None
+        self.steps = []
+
+    def __bool__(self):
+        return self.pfx is not None
+
+    def open(self, pfx, dir="."):
+        assert self.pfx is None
+        self.pfx, self.dir = pfx, dir
+
+    def write_step(self, grid, rn, rx, data, name, comp_names):
+        self.steps.append(dict(timestep=grid.timestep, rn=rn, rx=rx, data=data, name=name,
+                               comp_names=list(comp_names)))
+
+
+class OutputFieldsItem:
+    """OutputFieldsItem<Mfields, MfieldsState, Mparticles, GetItem, Writer>
+    (output_fields.hxx:150-236; DiagnosticBase::perform_diagnostic).  The item is evaluated on
+    the device (`get_item(mprts, mflds) -> (Mfields, name, comp_names)`), the running sum for
+    the time average lives and is updated there, and only what a writer is handed crosses to
+    the host: the interior of the item (pfd) or of the mean (tfd)."""
+
+    def __init__(self, get_item, suffix, pfield=None, tfield=None, writer=WriterMemory):
+        self.get_item, self.suffix = get_item, suffix
+        self.pfield, self.tfield = pfield or OutputFieldItemParams(), tfield or OutputFieldItemParams()
+        self.io_pfd, self.io_tfd = writer(), writer()
+        self.tfd, self.naccum = None, 0
+
+    def perform_diagnostic(self, mprts, mflds):
+        grid = mflds.grid()
+        timestep = grid.timestep
+        do_pfield = self.pfield.do_out(timestep)
+        do_tfield = self.tfield.do_out(timestep)
+        do_tfield_accum = self.tfield.do_accum(timestep)
+        if not (do_pfield or do_tfield_accum):
+            return
+        item, name, comp_names = self.get_item(mprts, mflds)
+        if do_pfield:
+            if not self.io_pfd:
+                self.io_pfd.open("pfd" + self.suffix, self.pfield.data_dir)
+            self.io_pfd.write_step(grid, self.pfield.rn, self.pfield.rx, item.download_interior(), name, comp_names)
+        if do_tfield_accum:
+            if self.tfd is None:
+                self.tfd = Mfields(grid, item.n_comps())
+            self.tfd.add(item)
+            self.naccum += 1
+        if do_tfield and self.naccum > 0:
+            # (naccum == 0 happens at the initial output when average_length < out_interval;
+            # the reference dereferences its unallocated tfd_ there)
+            if not self.io_tfd:
+                self.io_tfd.open("tfd" + self.suffix, self.tfield.data_dir)
+            # convert accumulated values to correct temporal mean
+            self.tfd.scale(1. / self.naccum)
+            self.io_tfd.write_step(grid, self.tfield.rn, self.tfield.rx, self.tfd.download_interior(), name,
+                                   comp_names)
+            self.naccum = 0
+            self.tfd.zero()
+
+    __call__ = perform_diagnostic
+
+
+def OutputFields(pfield=None, tfield=None, writer=WriterMemory):
+    """OutputFields<MfieldsState, Mparticles> = OutputFieldsItem<..., GetItemJeh> (:238-243)"""
+    item = ItemJeh()
+    return OutputFieldsItem(lambda mprts, mflds: (item(mflds), item.name(), item.comp_names()), "",
+                            pfield, tfield, writer)
+
+
+def OutputMoments(grid, pfield=None, tfield=None, writer=WriterMemory, which=MOMENT_ALL):
+    """OutputMoments<MfieldsState, Mparticles, Dim> = OutputFieldsItem<..., GetItemMoments<Dim>>
+    (:245-250): Moments_1st evaluated on the device"""
+    item = Moment(grid, which)
+    return OutputFieldsItem(lambda mprts, mflds: (item(mprts), item.name(), item.comp_names()), "_moments",
+                            pfield, tfield, writer)
 
 
 class Marder:
@@ -600,7 +753,7 @@ class Psc:
     def __init__(self, grid, mflds, mprts, sort_interval=1, marder_interval=0,
                  marder_diffusion=0.9, marder_loop=3, checks=None, fused=False, collision=None):
         self.collision = collision
-        self.injectors_ = []
+        self.injectors_, self.diagnostics_ = [], []
         self.grid_, self.mflds_, self.mprts_ = grid, mflds, mprts
         self.sort_interval, self.marder_interval = sort_interval, marder_interval
         self.marder = Marder(grid, marder_diffusion, marder_loop)
@@ -615,6 +768,25 @@ class Psc:
         injectors is issued operator by operator rather than as the single fused call."""
         assert injector is not None
         self.injectors_.append(injector)
+
+    def add_diagnostic(self, diagnostic):
+        """Psc::add_diagnostic (psc.hxx:184-198): anything with perform_diagnostic(mprts, mflds)"""
+        assert diagnostic is not None
+        self.diagnostics_.append(diagnostic)
+
+    def perform_diagnostics(self):
+        """psc.hxx:514-528"""
+        for diagnostic in self.diagnostics_:
+            diagnostic.perform_diagnostic(self.mprts_, self.mflds_)
+
+    def integrate(self, nmax):
+        """Psc::integrate (psc.hxx:243-310): ghost fills, initial diagnostics, then step +
+        diagnostics until timestep nmax"""
+        self.initialize()
+        self.perform_diagnostics()
+        while self.grid_.timestep < nmax:
+            self.step()
+            self.perform_diagnostics()
 
     def initialize(self):
         """psc.hxx:220-238 pre_first_step: fill H, J, E ghosts"""

@@ -813,6 +813,21 @@ int psc_b200_mflds_fill(psc_b200_ctx* ctx, int id, int m, float value)
   GUARD(return flds_fill(c, id, m, value);)
 }
 
+int psc_b200_mflds_add(psc_b200_ctx* ctx, int y_id, int y_mb, int x_id, int x_mb, int n_comps)
+{
+  GUARD(return flds_add(c, y_id, y_mb, x_id, x_mb, n_comps);)
+}
+
+int psc_b200_mflds_scale(psc_b200_ctx* ctx, int id, int mb, int me, double a)
+{
+  GUARD(return flds_scale(c, id, mb, me, a);)
+}
+
+int psc_b200_mflds_download_interior(psc_b200_ctx* ctx, int id, int mb, int me, float* host)
+{
+  GUARD(return flds_download_interior(c, id, mb, me, host);)
+}
+
 int psc_b200_push_mprts(psc_b200_ctx* ctx)
 {
   GUARD(PSC_TRY(store_ready(c)); return op_push(c);)

@@ -269,6 +269,9 @@ int heating_spot_foil(Ctx* c, const psc_b200_heating_params* prm, uint64_t* n_ki
 
 // ---- fields.cu
 int flds_create(Ctx* c, int n_comps, int* id);
+int flds_add(Ctx* c, int y_id, int y_mb, int x_id, int x_mb, int n_comps);
+int flds_scale(Ctx* c, int id, int mb, int me, double a);
+int flds_download_interior(Ctx* c, int id, int mb, int me, float* host);
 int flds_zero(Ctx* c, int id, int mb, int me);
 int flds_fill(Ctx* c, int id, int m, float v);
 int flds_upload(Ctx* c, int id, int mb, int me, const float* host, bool sync = true);

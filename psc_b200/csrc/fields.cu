@@ -832,6 +832,139 @@ int flds_download(Ctx* c, int id, int mb, int me, float* host, bool sync)
   return 0;
 }
 
+// ---------------------------------------------------------------- output hand-off
+// What OutputFieldsItem does to its items between the operator that produces them and the
+// writer (output_fields.hxx:170-231): take the interior, add it to the running sum, turn
+// the sum into the mean.  All three stream once through HBM.
+
+// y[p][ymb + m][r] += x[p][xmb + m][r]   (tfd_->gt() = tfd_->gt() + pfd, float + float)
+template <typename V>
+__global__ void __launch_bounds__(256)
+  k_flds_add(V* __restrict__ y, const V* __restrict__ x, long y_slot, long x_slot, long row, int n_patches)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)row * n_patches) {
+    return;
+  }
+  const size_t p = i / row, r = i - p * row;
+  V a = y[p * y_slot + r];
+  const V b = x[p * x_slot + r];
+  if constexpr (sizeof(V) == 16) {
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+  } else {
+    a += b;
+  }
+  y[p * y_slot + r] = a;
+}
+
+// y = float(a * double(y))   ((1. / naccum_) * tfd_->gt(): a double scalar times float data)
+template <typename V>
+__global__ void __launch_bounds__(256) k_flds_scale(V* __restrict__ y, long y_slot, long row, int n_patches, double a)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)row * n_patches) {
+    return;
+  }
+  const size_t p = i / row, r = i - p * row;
+  V v = y[p * y_slot + r];
+  if constexpr (sizeof(V) == 16) {
+    v.x = (float)(a * (double)v.x), v.y = (float)(a * (double)v.y);
+    v.z = (float)(a * (double)v.z), v.w = (float)(a * (double)v.w);
+  } else {
+    v = (float)(a * (double)v);
+  }
+  y[p * y_slot + r] = v;
+}
+
+// psc::mflds::interior: out[p][m][k][j][i] over the patch's own cells
+__global__ void __launch_bounds__(256)
+  k_flds_pack_interior(GridDev G, const float* __restrict__ F, long slot_len, int mb, int n_m,
+                       float* __restrict__ out, size_t n)
+{
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) {
+    return;
+  }
+  size_t r = idx;
+  const int i = (int)(r % G.ldims[0]);
+  r /= G.ldims[0];
+  const int j = (int)(r % G.ldims[1]);
+  r /= G.ldims[1];
+  const int k = (int)(r % G.ldims[2]);
+  r /= G.ldims[2];
+  const int m = (int)(r % n_m);
+  const size_t p = r / n_m;
+  out[idx] = F[p * slot_len + fld_off(G, mb + m, i, j, k)];
+}
+
+int flds_add(Ctx* c, int y_id, int y_mb, int x_id, int x_mb, int n_comps)
+{
+  PSC_TRY(check_field(c, y_id, y_mb, y_mb + n_comps));
+  PSC_TRY(check_field(c, x_id, x_mb, x_mb + n_comps));
+  if (n_comps == 0) {
+    return 0;
+  }
+  if (y_id == x_id && y_mb < x_mb + n_comps && x_mb < y_mb + n_comps) {
+    return fail("mflds_add: source and destination components overlap");
+  }
+  KernelScope ks(c, "flds_add");
+  const long fl = c->gd.fld_len, row = fl * n_comps;
+  float* y = c->fld(y_id) + (size_t)y_mb * fl;
+  const float* x = c->fld(x_id) + (size_t)x_mb * fl;
+  const long ys = c->fld_slot_len(y_id), xs = c->fld_slot_len(x_id);
+  if (fl % 4 == 0) { // every component of every slot starts on a 16-byte boundary
+    k_flds_add<float4><<<div_up((size_t)(row / 4) * c->gd.n_patches, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), ys / 4, xs / 4, row / 4, c->gd.n_patches);
+  } else {
+    k_flds_add<float><<<div_up((size_t)row * c->gd.n_patches, 256), 256, 0, c->stream>>>(y, x, ys, xs, row,
+                                                                                         c->gd.n_patches);
+  }
+  c->n_launches++;
+  return check_launch(c, "flds_add");
+}
+
+int flds_scale(Ctx* c, int id, int mb, int me, double a)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  if (me == mb) {
+    return 0;
+  }
+  KernelScope ks(c, "flds_scale");
+  const long fl = c->gd.fld_len, row = fl * (me - mb);
+  float* y = c->fld(id) + (size_t)mb * fl;
+  const long ys = c->fld_slot_len(id);
+  if (fl % 4 == 0) {
+    k_flds_scale<float4><<<div_up((size_t)(row / 4) * c->gd.n_patches, 256), 256, 0, c->stream>>>(
+      reinterpret_cast<float4*>(y), ys / 4, row / 4, c->gd.n_patches, a);
+  } else {
+    k_flds_scale<float><<<div_up((size_t)row * c->gd.n_patches, 256), 256, 0, c->stream>>>(y, ys, row,
+                                                                                           c->gd.n_patches, a);
+  }
+  c->n_launches++;
+  return check_launch(c, "flds_scale");
+}
+
+int flds_download_interior(Ctx* c, int id, int mb, int me, float* host)
+{
+  PSC_TRY(check_field(c, id, mb, me));
+  const size_t n = (size_t)c->gd.n_patches * (me - mb) * c->gd.n_cells;
+  if (n == 0) {
+    return 0;
+  }
+  PSC_TRY(c->scr[1].reserve(n * sizeof(float)));
+  float* d = c->scr[1].as<float>();
+  {
+    KernelScope ks(c, "flds_pack_interior");
+    k_flds_pack_interior<<<div_up(n, 256), 256, 0, c->stream>>>(c->gd, c->fld(id), c->fld_slot_len(id), mb,
+                                                               me - mb, d, n);
+    c->n_launches++;
+  }
+  PSC_TRY(check_launch(c, "flds_pack_interior"));
+  PSC_CUDA_TRY(cudaMemcpyAsync(host, d, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // ---------------------------------------------------------------- Bnd
 
 int bnd_fill_ghosts(Ctx* c, int id, int mb, int me)

@@ -90,10 +90,22 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
   cprm.continuity_every_step = 1;
   cprm.continuity_threshold = 1e-4;
   psc_b200::Step<Config> step(grid, mflds, mprts, prm, cprm);
+  // OutputFields / OutputMoments as a deck sets them up (psc_bubble_yz.cxx:322-337): fields
+  // every 2 steps, time averages over the last 3 steps written every 4
+  psc_b200::OutputFieldsItemParamsB200 outf_prm;
+  outf_prm.pfield.out_interval = 2;
+  outf_prm.tfield.out_interval = 4;
+  outf_prm.tfield.average_length = 3;
+  psc_b200::OutputFieldsB200<Grid> outf{grid, outf_prm};
+  psc_b200::OutputMomentsB200<Grid> outm{grid, outf_prm};
+  step.add_diagnostic(&outf);
+  step.add_diagnostic(&outm);
   step.initialize();
+  step.perform_diagnostics(); // Psc::integrate: initial output (psc.hxx:252-254)
   double max_cont = 0.;
   for (int n = 0; n < n_steps; n++) {
     step();
+    step.perform_diagnostics();
     max_cont = std::fmax(max_cont, step.checks().continuity.last_max_err);
   }
 
@@ -171,6 +183,31 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
     wr(ha.data(), ha.size() * 4);
     if (mom_n.name() != "n_1st_cc" || mom_all.name() != "all_1st_cc" || mn.n_comps() != 2 || ma.n_comps() != 26) {
       return 4;
+    }
+  }
+  // what the writers were handed: pfd at steps 0, 2, 4, one tfd (mean over steps 2..4) at step 4
+  {
+    auto& pf = outf.io_pfd().steps;
+    auto& tf = outf.io_tfd().steps;
+    auto& tm = outm.io_tfd().steps;
+    if (n_steps == 4) {
+      if (pf.size() != 3 || pf[0].item.timestep != 0 || pf[1].item.timestep != 2 || pf[2].item.timestep != 4 ||
+          tf.size() != 1 || tm.size() != 1 || tf[0].item.timestep != 4 || outf.io_pfd().pfx != "pfd" ||
+          outm.io_tfd().pfx != "tfd_moments" || tf[0].name != "jeh" || tm[0].name != "all_1st_cc" ||
+          tf[0].comp_names.size() != 9 || tf[0].comp_names[3] != "ex_ec" || tm[0].comp_names.size() != 26 ||
+          tm[0].comp_names[0] != "rho_e" || tm[0].comp_names[14] != "jx_i" || tf[0].item.n_comps != 9 ||
+          tf[0].item.ldims != grid.ldims) {
+        std::fprintf(stderr, "OutputFields: the writers were not handed what the cadence says\n");
+        return 12;
+      }
+      int no[3] = {(int)tf[0].item.data.size(), (int)tm[0].item.data.size(), (int)pf[1].item.data.size()};
+      wr(no, sizeof(no));
+      wr(tf[0].item.data.data(), tf[0].item.data.size() * 4);
+      wr(tm[0].item.data.data(), tm[0].item.data.size() * 4);
+      wr(pf[1].item.data.data(), pf[1].item.data.size() * 4);
+    } else {
+      int no[3] = {0, 0, 0};
+      wr(no, sizeof(no));
     }
   }
   std::fclose(f);
@@ -275,8 +312,48 @@ static int run(const std::string& out, bool yz, int n_steps, bool fused)
   return 0;
 }
 
+// OutputFieldsParamsTest.DoOut / Tfield_DoAccum (src/libpsc/tests/test_mfields_io.cxx:232-259)
+// on the parameter structs of the wrapper header; no device needed
+static int selftest_output_params()
+{
+#define EXPECT(cond)                                                                               \
+  if (!(cond)) {                                                                                   \
+    std::fprintf(stderr, "selftest: %s (line %d)\n", #cond, __LINE__);                             \
+    return 1;                                                                                      \
+  }
+  {
+    psc_b200::BaseOutputFieldItemParamsB200 prm;
+    EXPECT(!prm.do_out(0)); // should be disabled
+    prm.out_interval = 10;  // now enabled
+    EXPECT(prm.do_out(0));
+  }
+  {
+    psc_b200::OutputTfieldItemParamsB200 prm; // default: use every step between outs
+    EXPECT(!prm.do_accum(0));                 // should be disabled
+    prm.out_interval = 100;                   // now enabled
+    EXPECT(prm.do_accum(0));                  // accum on out step itself
+    prm.average_length = 50;
+    EXPECT(!prm.do_accum(0));
+    EXPECT(!prm.do_accum(50));
+    EXPECT(prm.do_accum(51));
+    EXPECT(prm.do_accum(52));
+    EXPECT(prm.do_accum(53));
+    prm.sample_interval = 2;
+    EXPECT(!prm.do_accum(51));
+    EXPECT(prm.do_accum(52));
+    EXPECT(!prm.do_accum(53));
+    EXPECT(prm.do_accum(100));
+  }
+#undef EXPECT
+  std::printf("selftest ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc == 2 && std::strcmp(argv[1], "selftest") == 0) {
+    return selftest_output_params();
+  }
   if (argc < 5) {
     std::fprintf(stderr, "usage: %s out.bin xyz|yz n_steps fused\n", argv[0]);
     return 1;

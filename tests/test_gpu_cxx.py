@@ -53,7 +53,15 @@ def _read_dump(path):
     nn = take(np.int32, 2)
     mom_n = take(np.float32, int(nn[0]))
     mom_all = take(np.float32, int(nn[1]))
-    return hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all
+    no = take(np.int32, 3)
+    outputs = [take(np.float32, int(k)) for k in no]  # tfd jeh, tfd moments, pfd jeh of step 2
+    return hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all, outputs
+
+
+def _interior(og, a):
+    b = og.ibn
+    sl = [slice(b[d], a.shape[4 - d] - b[d]) for d in range(3)]
+    return a[:, :, sl[2], sl[1], sl[0]]
 
 
 @pytest.mark.gpu
@@ -64,7 +72,7 @@ def test_wrappers_match_oracle(dim, fused, tmp_path):
     out = str(tmp_path / "dump.bin")
     r = subprocess.run([exe, out, dim, str(N_STEPS), str(fused)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all = _read_dump(out)
+    hdr, off0, prts0, flds0, off1, prts1, flds1, tail, mom_n, mom_all, outputs = _read_dump(out)
     if dim == "yz":
         og = ol.Grid(gdims=(1, 16, 32), length=(1., 20., 30.), np_=(1, 2, 2), dt=0.3, kinds=KINDS, nicell=6)
     else:
@@ -78,8 +86,22 @@ def test_wrappers_match_oracle(dim, fused, tmp_path):
     # Psc::initialize: ghost fills before the first step (psc.hxx:220-238)
     ol.fill_ghosts(og, f, 0, 9)
     rp, ro = prts0.copy(), off0.copy()
+    # OutputFields / OutputMoments (output_fields.hxx:150-236) with pfield every 2, tfield every 4
+    # averaging the last 3 steps: what the writers must have been handed
+    tfd_jeh = tfd_mom = pfd2 = None
     for step in range(1, N_STEPS + 1):
         rp, ro = ol.step(og, f, rp, ro, sort_now=(step % 2 == 0))
+        if step >= 2:
+            jeh, mom = _interior(og, f).copy(), _interior(og, ol.moment_1st(og, rp, ro, ol.MOM_ALL))
+            tfd_jeh = jeh if tfd_jeh is None else tfd_jeh + jeh
+            tfd_mom = mom.copy() if tfd_mom is None else tfd_mom + mom
+            if step == 2:
+                pfd2 = jeh
+    tfd_jeh = (np.float64(1. / 3) * tfd_jeh.astype(np.float64)).astype(np.float32)
+    tfd_mom = (np.float64(1. / 3) * tfd_mom.astype(np.float64)).astype(np.float32)
+    for got, ref, tol in ((outputs[0], tfd_jeh, 2e-5), (outputs[1], tfd_mom, 1e-4), (outputs[2], pfd2, 2e-5)):
+        assert got.size == ref.size
+        assert np.abs(got.reshape(ref.shape) - ref).max() <= tol * np.abs(ref).max()
     assert tail[0] < 1e-5, "continuity residual %g" % tail[0]
     if fused:
         # the fused step performs the sort of the following step early when one is due;
