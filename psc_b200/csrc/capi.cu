@@ -434,7 +434,9 @@ static int step_core(Ctx* c, const psc_b200_step_params* prm)
   const bool do_sort = prm->sort || (c->opt_keep_sorted && c->opt_fused_sort && c->opt_tiled);
   bool gap_ok = do_sort && c->opt_fused_sort && c->opt_gapped && c->opt_tiled && !c->comm &&
                 !prm->checks && prm->marder_loop <= 0 && c->n_prts > 0;
-  if (!gap_ok) {
+  // (pull mode: the push below completes the pending sort itself; the continuity check wants
+  // the store before the push)
+  if (!gap_ok && !(c->pull_pending && !prm->checks)) {
     PSC_TRY(store_ready(c));
   }
   if (do_sort && !c->sorted && !c->gapped) {
@@ -496,6 +498,7 @@ static int step_core(Ctx* c, const psc_b200_step_params* prm)
     PSC_TRY(bndf_fill_ghosts_E(c));
     PSC_TRY(bnd_fill_ghosts(c, 0, pm::EX, pm::EX + 3));
     if (prm->marder_loop > 0) {
+      PSC_TRY(store_ready(c));
       PSC_TRY(marder(c, prm->marder_diffusion, prm->marder_loop)); // :448-455
     }
     PSC_TRY(push_H(c, .5)); // :461
@@ -504,6 +507,7 @@ static int step_core(Ctx* c, const psc_b200_step_params* prm)
   }
   if (prm->checks) {
     double e;
+    PSC_TRY(store_ready(c));
     PSC_TRY(check_continuity_end(c, &e)); // :471-476
     PSC_TRY(check_gauss(c, &e));          // :479-483
   }
@@ -560,7 +564,9 @@ static int step_begin(Ctx* c, const psc_b200_step_params* prm)
   if (!split) {
     return step(c, prm); // nothing left pending: the async transfers simply follow it
   }
-  PSC_TRY(store_ready(c));
+  if (!c->pull_pending) {
+    PSC_TRY(store_ready(c));
+  }
   if (!c->sorted) {
     PSC_TRY(sort_mprts(c)); // psc.hxx:356-361
   }
@@ -604,6 +610,12 @@ static int step_begin(Ctx* c, const psc_b200_step_params* prm)
   PSC_TRY(rc);
   if (prm->energies && c->scatter_energies_done) {
     c->en_valid = true; // (the scatter reduced them on its way)
+  } else if (prm->energies && (c->fs_pull || c->pull_pending)) {
+    // pull mode: no pass over the stayers to ride on
+    PSC_TRY(fused_bnd_sort_finish(c));
+    PSC_TRY(store_ready(c));
+    PSC_TRY(prts_energies(c, c->en_host + 6, false));
+    c->en_valid = true;
   } else if (prm->energies) {
     if (c->fs_deferred) {
       // the sorted store is still the "other" buffer and its size is only on the device
@@ -717,7 +729,7 @@ int psc_b200_get_ldims(const psc_b200_ctx* ctx, int ldims[3], int ibn[3])
 
 int psc_b200_mprts_set(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
 {
-  GUARD(c->gapped = false; return prts_set(c, prts, n_by_patch);)
+  GUARD(c->gapped = false; c->pull_pending = false; return prts_set(c, prts, n_by_patch);)
 }
 
 int psc_b200_mprts_inject(psc_b200_ctx* ctx, const void* prts, const uint32_t* n_by_patch)
@@ -742,13 +754,13 @@ int psc_b200_mprts_get(psc_b200_ctx* ctx, void* prts, uint32_t* off)
 
 int psc_b200_mprts_setup_thermal(psc_b200_ctx* ctx, int ppc, const double* vth, uint64_t seed)
 {
-  GUARD(c->gapped = false; return prts_setup_thermal(c, ppc, nullptr, vth, seed);)
+  GUARD(c->gapped = false; c->pull_pending = false; return prts_setup_thermal(c, ppc, nullptr, vth, seed);)
 }
 
 int psc_b200_mprts_setup_thermal_by_patch(psc_b200_ctx* ctx, const int* ppc_by_patch, const double* vth,
                                           uint64_t seed)
 {
-  GUARD(c->gapped = false; if (!ppc_by_patch) { return fail("null ppc_by_patch"); }
+  GUARD(c->gapped = false; c->pull_pending = false; if (!ppc_by_patch) { return fail("null ppc_by_patch"); }
         return prts_setup_thermal(c, 0, ppc_by_patch, vth, seed);)
 }
 
@@ -878,7 +890,7 @@ int psc_b200_checkpoint_write(psc_b200_ctx* ctx, const char* path, int64_t times
 
 int psc_b200_checkpoint_read(psc_b200_ctx* ctx, const char* path, int64_t* timestep)
 {
-  GUARD(return checkpoint_read(c, path, timestep);)
+  GUARD(c->pull_pending = false; return checkpoint_read(c, path, timestep);)
 }
 
 int psc_b200_bnd_add_ghosts(psc_b200_ctx* ctx, int id, int mb, int me)
@@ -1016,6 +1028,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "tma") { c->opt_tma = v; }
     else if (n == "lean") { c->opt_lean = v; }
     else if (n == "push_collect") { c->opt_push_collect = v; }
+    else if (n == "pull") { c->opt_pull = v; }
     else if (n == "vec_fields") { c->opt_vec_fields = v; }
     else if (n == "threads") { c->opt_threads = v; }
     else if (n == "min_blocks") { c->opt_min_blocks = v; }
@@ -1049,6 +1062,9 @@ int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
     else if (n == "gap_redone") { *value = (double)c->n_gap_redone; }
     else if (n == "gap_movers") { *value = (double)c->g_mov_used; }
     else if (n == "fused_fallbacks") { *value = (double)c->n_fused_fallback; }
+    else if (n == "pull_steps") { *value = (double)c->n_pulled; }
+    else if (n == "pull_materialized") { *value = (double)c->n_pull_materialized; }
+    else if (n == "pull_overflows") { *value = (double)c->n_pull_overflow; }
     else { return fail("unknown stat " + n); }
     return 0;)
 }

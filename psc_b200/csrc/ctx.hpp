@@ -98,6 +98,7 @@ struct Ctx
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with TMA (tensor map / cp.async.bulk) instead of LDG/STS
+  int opt_pull = 1;         // the push of the next step completes the sort of this one (one pass less over the particles)
   int opt_push_collect = 1; // multi-rank: k_push_lean lists the remote leavers (else a pass over the boundary cells)
   int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time
   int opt_vec_fields = 1;  // Yee update with 128-bit accesses where the rows allow it (3D, im0 % 4 == 0)
@@ -133,6 +134,16 @@ struct Ctx
   uint32_t* d_cell_off = nullptr; // n_patches * n_cells + 1
   uint32_t* d_cell_off_alt = nullptr; // written by the fused boundary+sort pass
   uint64_t n_fused_fallback = 0;
+  // pull mode (push_lean.cuh PULL, fused_sort.cu): after a step the particles that changed cell
+  // sit in the OTHER buffer (laid out by d_cell_off_alt, scr[13] = per cell {arrivals in front
+  // of the stayers, stayers}), the stayers still in this one among the dead copies of the
+  // leavers; the next push pulls them across.  pull_materialize() completes the sort instead
+  // whenever something else wants the store.
+  bool pull_pending = false;
+  bool pulled = false;        // the last push was a pull push (its mover list is in scr[12])
+  bool fs_pull = false;       // the fused pass in flight placed the movers only
+  uint32_t mv_cap = 0, last_n_movers = 0;
+  uint64_t n_pulled = 0, n_pull_materialized = 0, n_pull_overflow = 0;
   // step_begin / step_end (pipelined host I/O): the exchange + sort is in flight on `stream`,
   // the field chain and the host transfers on `stream2`
   bool step_pending = false;
@@ -179,7 +190,7 @@ struct Ctx
   std::vector<FieldArr> flds;
 
   // ---- scratch
-  DevBuf scr[12];
+  DevBuf scr[14];
   DevBuf stage; // host<->device staging of AoS records
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
@@ -255,8 +266,14 @@ void gap_release(Ctx* c);
 int push_gap_exact(Ctx* c);
 int push_gap_fast(Ctx* c);
 // every operator that reads the particle store directly calls this first
+int pull_materialize(Ctx* c); // fused_sort.cu: pull mode -> contiguous cell-ordered store
+int pull_enter(Ctx* c);       // ... and into it from a cell-ordered store (no arrivals yet)
+bool pull_possible(const Ctx* c);
 inline int store_ready(Ctx* c)
 {
+  if (c->pull_pending) {
+    return pull_materialize(c);
+  }
   return c->gapped ? gap_compact(c) : 0;
 }
 

@@ -162,9 +162,11 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, cnt_t* 
 // k_fs_offsets_face appends the neighbour-patch routes for the cells on the patch faces
 // only (one thread per face cell; the face slabs are enumerated z, y, x and a cell that
 // lies in several is taken by the first).
+// STAY (pull mode): also emit, per target cell, {arrivals placed in front of its stayers, stayers}
+template <bool STAY>
 __global__ void __launch_bounds__(256, 4)
   k_fs_offsets_same(GridDev G, uint32_t nct, cnt_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt,
-                    uint32_t* __restrict__ flags)
+                    uint32_t* __restrict__ flags, uint2* __restrict__ stay)
 {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nct) {
@@ -175,7 +177,13 @@ __global__ void __launch_bounds__(256, 4)
   const int ld0 = G.ldims[0], ld1 = G.ldims[1];
   const int c0 = c % ld0, c1 = (c / ld0) % ld1, c2 = c / (ld0 * ld1);
   uint32_t total = 0;
-  fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
+  if constexpr (STAY) {
+    uint32_t nl = 0, nc = 0;
+    fs_route<true>(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total, &nl, &nc);
+    stay[g] = make_uint2(nl, nc);
+  } else {
+    fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
+  }
   new_cnt[g] = total;
   if (total > CNT_MAX) {
     atomicExch(&flags[0], 1u); // offsets inside this cell do not fit the 16-bit planes
@@ -436,6 +444,85 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   }
 }
 
+// ---- pull mode (push_lean.cuh PULL): only the particles that change cell are moved here;
+// the stayers cross over inside the next push.
+
+// one thread per entry of the push's mover list: the particle at mv_idx goes to
+// new_cell_off[target] + offset of its (source cell, class) group + its rank in the group,
+// with the boundary fix-ups -- the same place k_fs_scatter would put it
+__global__ void __launch_bounds__(256)
+  k_fs_place_movers(GridDev G, FsTables T, uint32_t nct, const uint32_t* __restrict__ flags, uint32_t cap,
+                    uint32_t n_host, const uint32_t* __restrict__ mv_idx, const uint2* __restrict__ mv_key,
+                    const cnt_t* __restrict__ pre, const uint32_t* __restrict__ new_cell_off,
+                    const float4* __restrict__ xi4, const float4* __restrict__ pxi4, float4* __restrict__ xo,
+                    float4* __restrict__ po)
+{
+  const uint32_t n = n_host != 0xffffffffu ? n_host : min(flags[3], cap);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t i = mv_idx[k];
+    const uint2 key = mv_key[k];
+    const uint32_t cls = key.x / nct, g = key.x - cls * nct;
+    const int p = g / G.n_cells;
+    const int s = g - p * G.n_cells;
+    const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+    const float4 X = xi4[i], U = pxi4[i];
+    float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
+    int q = 0, c = 0;
+    if (fs_classify(G, T, p, s0, s1, s2, x, u, q, c) != (int)cls) {
+      continue; // (cannot happen: the push classified the same record with the same arithmetic)
+    }
+    const uint32_t dst = __ldg(&new_cell_off[(size_t)q * G.n_cells + c]) + pre[key.x] + key.y;
+    xo[dst] = make_float4(x[0], x[1], x[2], X.w);
+    po[dst] = make_float4(u[0], u[1], u[2], U.w);
+  }
+}
+
+// the rest of the sort, when something other than the next push wants the store: one warp
+// per source cell copies the records that still live in the cell to their place
+__global__ void __launch_bounds__(FS_WARPS * 32)
+  k_pull_stayers(GridDev G, uint32_t nct, const uint32_t* __restrict__ cell_off,
+                 const uint32_t* __restrict__ new_cell_off, const uint2* __restrict__ stay,
+                 const float4* __restrict__ xi4, const float4* __restrict__ pxi4, float4* __restrict__ xo,
+                 float4* __restrict__ po)
+{
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t g = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
+  if (g >= nct) {
+    return;
+  }
+  const int p = g / G.n_cells;
+  const int s = g - p * G.n_cells;
+  const int s0 = s % G.ldims[0], s1 = (s / G.ldims[0]) % G.ldims[1], s2 = s / (G.ldims[0] * G.ldims[1]);
+  const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+  uint32_t dst = __ldg(&new_cell_off[g]) + stay[g].x;
+  for (uint32_t base = begin; base < end; base += 32) {
+    const uint32_t i = base + lane;
+    bool live = false;
+    float4 X, U;
+    if (i < end) {
+      X = xi4[i], U = pxi4[i];
+      live = pm::cell_position(G.pc, X.x, 0) == s0 && pm::cell_position(G.pc, X.y, 1) == s1 &&
+             pm::cell_position(G.pc, X.z, 2) == s2;
+    }
+    const unsigned lm = __ballot_sync(FULL, live);
+    if (live) {
+      xo[dst + __popc(lm & lt)] = X;
+      po[dst + __popc(lm & lt)] = U;
+    }
+    dst += __popc(lm);
+  }
+}
+
+// entering pull mode from a cell-ordered store: nothing in front of the stayers, everybody stays
+__global__ void k_stay_init(uint32_t nct, const uint32_t* __restrict__ cell_off, uint2* __restrict__ stay)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < nct) {
+    stay[g] = make_uint2(0u, cell_off[g + 1] - cell_off[g]);
+  }
+}
+
 __global__ void k_patch_offsets(const uint32_t* __restrict__ cell_off, int n_patches, int n_cells,
                                 uint32_t* __restrict__ off)
 {
@@ -591,8 +678,39 @@ static int fused_fallback(Ctx* c)
   // precondition broken for some particle: the source store is intact, take the general path
   c->n_fused_fallback++;
   c->counts_valid = false;
+  c->fs_pull = false; // (a pull push leaves a complete pushed store like any other)
   PSC_TRY(bnd_particles(c));
   return sort_mprts(c);
+}
+
+// the scatter pass of fused_bnd_sort (count planes turned into offsets, new cell offsets scanned)
+static int launch_scatter(Ctx* c, bool energies)
+{
+  const GridDev& G = c->gd;
+  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+  const cnt_t* cnt = c->scr[9].as<cnt_t>();
+  FsTables T{c->d_patch_bnd, c->d_nei_patch};
+  ScatterEnergies SE{};
+  if (energies) {
+    // step_begin asked for DiagEnergies: the particle part rides on this pass
+    for (int k = 0; k < c->g.desc.n_kinds; k++) {
+      SE.q[k] = (float)c->g.desc.q[k];
+      SE.m[k] = (float)c->g.desc.m[k];
+    }
+    SE.fnqs_fac = c->g.desc.fnqs * c->g.dx[0] * c->g.dx[1] * c->g.dx[2];
+    PSC_TRY(c->scr[0].reserve(2 * sizeof(double)));
+    SE.out2 = c->scr[0].as<double>();
+    PSC_CUDA_TRY(cudaMemsetAsync(SE.out2, 0, 2 * sizeof(double), c->stream));
+    k_fs_scatter<true><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
+      G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
+    PSC_CUDA_TRY(cudaMemcpyAsync(c->en_host + 6, SE.out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->scatter_energies_done = true;
+  } else {
+    k_fs_scatter<false><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
+      G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
+  }
+  c->n_launches++;
+  return 0;
 }
 
 // second half of fused_bnd_sort: the flags and the new patch offsets are on the host
@@ -605,8 +723,27 @@ static int fused_commit(Ctx* c, const uint32_t* h, uint32_t n_expected, bool mul
     }
     return fused_fallback(c);
   }
-  c->cur ^= 1;
-  std::swap(c->d_cell_off, c->d_cell_off_alt);
+  if (c->fs_pull && h[3] > c->mv_cap) {
+    // the push's mover list overflowed: the full scatter instead (the counters, the new cell
+    // offsets and the pushed store are all still in place)
+    c->fs_pull = false;
+    c->n_pull_overflow++;
+    c->last_n_movers = h[3];
+    PSC_TRY(launch_scatter(c, false));
+    PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    PSC_TRY(check_launch(c, "fused_bnd_sort (scatter after a mover-list overflow)"));
+  }
+  if (c->fs_pull) {
+    // the stayers cross over inside the next push (or in pull_materialize): the store is
+    // "this buffer's live records + the other buffer's arrivals" until then
+    c->fs_pull = false;
+    c->pull_pending = true;
+    c->last_n_movers = h[3];
+    c->n_pulled++;
+  } else {
+    c->cur ^= 1;
+    std::swap(c->d_cell_off, c->d_cell_off_alt);
+  }
   for (int p = 0; p <= np; p++) {
     c->h_off[p] = h[4 + p];
   }
@@ -640,6 +777,9 @@ int fused_bnd_sort(Ctx* c, bool defer)
   const GridDev& G = c->gd;
   const uint32_t rem_cap = c->rem_cap; // remote leavers listed by the push of this step (0: not)
   c->rem_cap = 0;
+  const bool pull = c->pulled && c->opt_pull; // the push listed the movers: place them, leave the stayers
+  c->pulled = false;
+  c->fs_pull = false;
   if (!c->pushed_from_sorted) {
     c->counts_valid = false;
     PSC_TRY(bnd_particles(c));
@@ -667,7 +807,13 @@ int fused_bnd_sort(Ctx* c, bool defer)
   c->counts_valid = false;
   {
     KernelScope ks(c, "fsort_offsets");
-    k_fs_offsets_same<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags);
+    if (pull) {
+      PSC_TRY(c->scr[13].reserve((size_t)nct * sizeof(uint2)));
+      k_fs_offsets_same<true><<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags,
+                                                                       c->scr[13].as<uint2>());
+    } else {
+      k_fs_offsets_same<false><<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags, nullptr);
+    }
     // faces towards a direction in which some patch has a neighbour (none along an
     // invariant direction: Grid_ / MrcDomain)
     FaceGeom FG{};
@@ -691,6 +837,7 @@ int fused_bnd_sort(Ctx* c, bool defer)
     c->n_launches += 2;
   }
   uint32_t n_expected = c->n_prts;
+  uint32_t n_movers_multi = 0;
   // ---- multi-rank: ship the leavers, merge the arrivals into the target cells' tails
   uint32_t n_recv_tot = 0;
   float4 *xr = nullptr, *pr = nullptr;
@@ -708,6 +855,7 @@ int fused_bnd_sort(Ctx* c, bool defer)
       return fused_fallback(c);
     }
     const uint32_t n_rem = h4[2];
+    n_movers_multi = h4[3];
     if (!c->rf_built) {
       PSC_TRY(build_remote_cells(c));
     }
@@ -724,6 +872,7 @@ int fused_bnd_sort(Ctx* c, bool defer)
         PSC_TRY(c->scr[7].reserve(4 * (size_t)n_rem * sizeof(uint32_t)));
         uint32_t* a = c->scr[7].as<uint32_t>();
         k0 = a, v0 = a + n_rem, k1 = a + 2 * (size_t)n_rem, v1 = a + 3 * (size_t)n_rem;
+        PSC_CUDA_TRY(cudaMemsetAsync(flags + 3, 0, sizeof(uint32_t), c->stream)); // (a pull push counted its movers there)
         k_fs_collect_remote<<<div_up(c->n_rf_cells, FS_WARPS), FS_WARPS * 32, 0, c->stream>>>(
           G, T, c->n_rf_cells, c->rf_cells.as<uint32_t>(), c->d_cell_off, c->xi(), v0, k0, flags + 3,
           n_rem);
@@ -777,26 +926,22 @@ int fused_bnd_sort(Ctx* c, bool defer)
     KernelScope ks(c, "fsort_scan");
     PSC_TRY(scan_exclusive<uint32_t>(c, LoadArr<uint32_t>{new_cnt}, nct, c->d_cell_off_alt, c->scr[2]));
   }
+  uint32_t n_movers_host = 0xffffffffu; // (multi-rank: known on the host already)
+  if (multi) {
+    n_movers_host = std::min(n_movers_multi, c->mv_cap);
+  }
   {
-    KernelScope ks(c, "fsort_scatter");
-    ScatterEnergies SE{};
-    if (c->want_scatter_energies && !multi) {
-      // step_begin asked for DiagEnergies: the particle part rides on this pass
-      for (int k = 0; k < c->g.desc.n_kinds; k++) {
-        SE.q[k] = (float)c->g.desc.q[k];
-        SE.m[k] = (float)c->g.desc.m[k];
-      }
-      SE.fnqs_fac = c->g.desc.fnqs * c->g.dx[0] * c->g.dx[1] * c->g.dx[2];
-      PSC_TRY(c->scr[0].reserve(2 * sizeof(double)));
-      SE.out2 = c->scr[0].as<double>();
-      PSC_CUDA_TRY(cudaMemsetAsync(SE.out2, 0, 2 * sizeof(double), c->stream));
-      k_fs_scatter<true><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
-        G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
-      PSC_CUDA_TRY(cudaMemcpyAsync(c->en_host + 6, SE.out2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      c->scatter_energies_done = true;
+    KernelScope ks(c, pull ? "fsort_place_movers" : "fsort_scatter");
+    if (pull) {
+      const uint2* mv_key = c->scr[12].as<uint2>();
+      const uint32_t* mv_idx = reinterpret_cast<const uint32_t*>(mv_key + c->mv_cap);
+      k_fs_place_movers<<<148 * 8, 256, 0, c->stream>>>(G, T, nct, flags, c->mv_cap, n_movers_host, mv_idx, mv_key,
+                                                       cnt, c->d_cell_off_alt, c->xi(), c->pxi(), c->xi_alt(),
+                                                       c->pxi_alt());
+      c->n_launches++;
+      c->fs_pull = true;
     } else {
-      k_fs_scatter<false><<<div_up(nct, SC_CELLS), SC_WARPS * 32, 0, c->stream>>>(
-        G, T, nct, c->d_cell_off, c->d_cell_off_alt, cnt, c->xi(), c->pxi(), c->xi_alt(), c->pxi_alt(), SE);
+      PSC_TRY(launch_scatter(c, c->want_scatter_energies && !multi));
     }
     if (n_recv_tot) {
       k_fs_place_remote<<<div_up(n_recv_tot, 256), 256, 0, c->stream>>>(
@@ -806,7 +951,7 @@ int fused_bnd_sort(Ctx* c, bool defer)
     k_patch_offsets<<<div_up(np + 1, 128), 128, 0, c->stream>>>(c->d_cell_off_alt, np, G.n_cells,
                                                                d_new_off);
   }
-  c->n_launches += 2;
+  c->n_launches += 1;
   if (defer && !multi) {
     const size_t need = (size_t)(np + 1 + 4) * sizeof(uint32_t);
     if (c->fs_host_bytes < need) {
@@ -829,6 +974,60 @@ int fused_bnd_sort(Ctx* c, bool defer)
   return fused_commit(c, h.data(), n_expected, multi);
 }
 
+
+// ====================================================================== pull mode
+
+// pull mode needs: the lean push with its class counts and SAME cell arithmetic (push.cu checks
+// those when it launches), no reflecting particle walls (a reflected particle that stays in its
+// cell would have to be re-ranked among the stayers), plane entries that fit the mover key
+bool pull_possible(const Ctx* c)
+{
+  if (!c->opt_pull || !c->opt_fused_sort || c->opt_gapped) {
+    return false;
+  }
+  for (int d = 0; d < 3; d++) {
+    if (!c->g.invar[d] && (c->g.desc.bc_prt_lo[d] == PSC_B200_BND_PRT_REFLECTING ||
+                           c->g.desc.bc_prt_hi[d] == PSC_B200_BND_PRT_REFLECTING)) {
+      return false;
+    }
+  }
+  return (size_t)FS_PLANES * c->gd.n_cells * c->gd.n_patches < (size_t(1) << 32);
+}
+
+// from a cell-ordered store: the output layout is this one, nothing lies in front of the
+// stayers, everybody stays
+int pull_enter(Ctx* c)
+{
+  const uint32_t nct = (uint32_t)c->gd.n_cells * c->gd.n_patches;
+  PSC_TRY(c->scr[13].reserve((size_t)nct * sizeof(uint2)));
+  PSC_CUDA_TRY(cudaMemcpyAsync(c->d_cell_off_alt, c->d_cell_off, ((size_t)nct + 1) * sizeof(uint32_t),
+                               cudaMemcpyDeviceToDevice, c->stream));
+  k_stay_init<<<div_up(nct, 256), 256, 0, c->stream>>>(nct, c->d_cell_off, c->scr[13].as<uint2>());
+  c->n_launches++;
+  c->pull_pending = true;
+  return check_launch(c, "pull_enter");
+}
+
+int pull_materialize(Ctx* c)
+{
+  if (!c->pull_pending) {
+    return 0;
+  }
+  const GridDev& G = c->gd;
+  const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+  {
+    KernelScope ks(c, "pull_materialize");
+    k_pull_stayers<<<div_up(nct, FS_WARPS), FS_WARPS * 32, 0, c->stream>>>(
+      G, nct, c->d_cell_off, c->d_cell_off_alt, c->scr[13].as<uint2>(), c->xi(), c->pxi(), c->xi_alt(),
+      c->pxi_alt());
+    c->n_launches++;
+  }
+  c->cur ^= 1;
+  std::swap(c->d_cell_off, c->d_cell_off_alt);
+  c->pull_pending = false;
+  c->n_pull_materialized++;
+  return check_launch(c, "pull_materialize");
+}
 
 // ====================================================================== gapped store
 

@@ -439,6 +439,18 @@ struct PushArgs
   uint32_t* rem_key;
   uint32_t* rem_idx;
   uint32_t rem_cap;
+  // lean kernel, PULL (push_lean.cuh): the store the stayers are pulled from (cell_off describes
+  // it; xi4 / pxi4 are the output store then), the output store's cell offsets, per cell
+  // {arrivals in front of the stayers, stayers}, and the list of the particles that change
+  // cell in this push: index in the output store, (plane entry = class * nct + source cell, rank
+  // inside that group); flags[3] is the list's fill count
+  const float4* xin4;
+  const float4* pin4;
+  const uint32_t* out_off;
+  const uint2* stay;
+  uint32_t* mv_idx;
+  uint2* mv_key;
+  uint32_t mv_cap;
   GapPush gap; // GAP variant only (gap.cuh)
 };
 
@@ -1092,6 +1104,36 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, PushArgs A
   CUtensorMap tm;
   static_assert(sizeof(tm) == sizeof(tm128), "");
   memcpy(&tm, &tm128, sizeof(tm));
+  if (c->pull_pending) {
+    // the mover list: room for a quarter of the store, and at least
+    // twice what moved last step; a step that overflows it takes the full scatter instead
+    const size_t cap = std::min<size_t>(0xffffffffu, std::max<size_t>({size_t(1) << 16, (size_t)c->n_prts / 4,
+                                                                       2 * (size_t)c->last_n_movers}));
+    PSC_TRY(c->scr[12].reserve(cap * (sizeof(uint32_t) + sizeof(uint2))));
+    A.mv_key = c->scr[12].as<uint2>();
+    A.mv_idx = reinterpret_cast<uint32_t*>(A.mv_key + cap);
+    A.mv_cap = (uint32_t)cap;
+    c->mv_cap = A.mv_cap;
+  }
+  if (c->pull_pending) {
+    // (push_dim has checked that this launch is possible: count, same_dxi, W = 1)
+    A.xin4 = c->xi();
+    A.pin4 = c->pxi();
+    A.xi4 = c->xi_alt();
+    A.pxi4 = c->pxi_alt();
+    A.out_off = c->d_cell_off_alt;
+    A.stay = c->scr[13].as<uint2>();
+    PSC_CUDA_TRY(cudaMemsetAsync(A.cnt, 0, (size_t)A.nct * FS_PLANES * sizeof(cnt_t), c->stream));
+    auto kern = lean::k_push_lean<DIM, DEPOSIT, true, true, 1, true>;
+    PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    kern<<<tiles, lean::n_warps<1>() * 32, smem_bytes, c->stream>>>(tm, G, geo, A);
+    // the output store is the store now
+    c->cur ^= 1;
+    std::swap(c->d_cell_off, c->d_cell_off_alt);
+    c->pull_pending = false;
+    c->pulled = true;
+    return 0;
+  }
 #define PSC_LEAN_W(CN, SM, WW)                                                                    \
   do {                                                                                            \
     auto kern = lean::k_push_lean<DIM, DEPOSIT, CN, SM, WW>;                                      \
@@ -1220,6 +1262,9 @@ static int push_dim(Ctx* c, bool gap)
 {
   const GridDev& G = c->gd;
   c->counts_valid = false;
+  if (c->pull_pending && !(c->sorted && c->opt_tiled && !gap)) {
+    PSC_TRY(pull_materialize(c)); // (options changed under a pending pull)
+  }
   if (c->n_prts == 0) {
     return gap ? fail("gapped push: empty store") : 0;
   }
@@ -1272,8 +1317,22 @@ static int push_dim(Ctx* c, bool gap)
       stat = stat && (inv || (G.ibn[d] == 2 && G.ldims[d] % gs.t(d) == 0));
     }
     int rc = -1;
-    if (stat && !gap && c->opt_lean && c->opt_tma && G.im[xyz ? 0 : 1] % 4 == 0) {
-      // (tensor-map strides are multiples of 16 bytes)
+    // (tensor-map strides are multiples of 16 bytes)
+    const bool lean_ok = stat && !gap && c->opt_lean && c->opt_tma && G.im[xyz ? 0 : 1] % 4 == 0;
+    // pull mode (push_lean.cuh PULL): this push completes the previous step's sort on its way
+    bool pull_now = lean_ok && count && A.same_dxi && c->opt_lean < 2 && pull_possible(c);
+#ifdef PM_FAST_MATH
+    pull_now = lean_ok && count && A.same_dxi && pull_possible(c);
+#endif
+    if (c->pull_pending && !pull_now) {
+      PSC_TRY(pull_materialize(c));
+      A.cell_off = c->d_cell_off;
+      A.xi4 = c->xi();
+      A.pxi4 = c->pxi();
+    } else if (pull_now && !c->pull_pending) {
+      PSC_TRY(pull_enter(c));
+    }
+    if (lean_ok) {
       KernelScope ks(c, "push_lean");
       rc = launch_lean<DIM, DEPOSIT>(c, gs, count, A);
     }
