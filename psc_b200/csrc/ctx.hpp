@@ -98,7 +98,10 @@ struct Ctx
   int opt_tiled = 1;       // use the tiled shared-memory push when the store is sorted
   int opt_fma = 0;         // 0: -fmad=false build of the push (bit-exact vs CPU), 1: FMA build
   int opt_tma = 1;         // stage the E/B tile with TMA (tensor map / cp.async.bulk) instead of LDG/STS
-  int opt_pull = 1;         // the push of the next step completes the sort of this one (one pass less over the particles)
+  int opt_pull = 0;         // the push of the next step completes the sort of this one (one pass less over the
+                            // particles; byte-identical stores, but 40.6 ms against 33.1 ms per S3D step as it
+                            // stands -- DESIGN.md 3.2d): opt-in
+  int opt_pull_cap = 0;     // > 0: capacity of the pull push's mover list (tests: force the overflow route)
   int opt_push_collect = 1; // multi-rank: k_push_lean lists the remote leavers (else a pass over the boundary cells)
   int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time
   int opt_vec_fields = 1;  // Yee update with 128-bit accesses where the rows allow it (3D, im0 % 4 == 0)

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, SC_MINB)
   }
 }
 
-// ---- pull mode (push_lean.cuh PULL): only the particles that change cell are moved here;
+// ---- pull mode (push_lean_pull.cuh): only the particles that change cell are moved here;
 // the stayers cross over inside the next push.
 
 // one thread per entry of the push's mover list: the particle at mv_idx goes to
@@ -982,8 +982,8 @@ int fused_bnd_sort(Ctx* c, bool defer)
 // cell would have to be re-ranked among the stayers), plane entries that fit the mover key
 bool pull_possible(const Ctx* c)
 {
-  if (!c->opt_pull || !c->opt_fused_sort || c->opt_gapped) {
-    return false;
+  if (!c->opt_pull || !c->opt_fused_sort || c->opt_gapped || c->comm) {
+    return false; // (multi-rank: the remote arrivals' placement has not been exercised in pull mode)
   }
   for (int d = 0; d < 3; d++) {
     if (!c->g.invar[d] && (c->g.desc.bc_prt_lo[d] == PSC_B200_BND_PRT_REFLECTING ||

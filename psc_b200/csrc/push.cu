@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_push_tiled(GridDev G, GEO geo, P
 }
 
 #include "push_lean.cuh"
+#include "push_lean_pull.cuh"
 
 // ---------------------------------------------------------------- host side
 
@@ -1107,8 +1108,11 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, PushArgs A
   if (c->pull_pending) {
     // the mover list: room for a quarter of the store, and at least
     // twice what moved last step; a step that overflows it takes the full scatter instead
-    const size_t cap = std::min<size_t>(0xffffffffu, std::max<size_t>({size_t(1) << 16, (size_t)c->n_prts / 4,
-                                                                       2 * (size_t)c->last_n_movers}));
+    size_t cap = std::min<size_t>(0xffffffffu, std::max<size_t>({size_t(1) << 16, (size_t)c->n_prts / 4,
+                                                                 2 * (size_t)c->last_n_movers}));
+    if (c->opt_pull_cap > 0) {
+      cap = (size_t)c->opt_pull_cap;
+    }
     PSC_TRY(c->scr[12].reserve(cap * (sizeof(uint32_t) + sizeof(uint2))));
     A.mv_key = c->scr[12].as<uint2>();
     A.mv_idx = reinterpret_cast<uint32_t*>(A.mv_key + cap);
@@ -1124,7 +1128,7 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, PushArgs A
     A.out_off = c->d_cell_off_alt;
     A.stay = c->scr[13].as<uint2>();
     PSC_CUDA_TRY(cudaMemsetAsync(A.cnt, 0, (size_t)A.nct * FS_PLANES * sizeof(cnt_t), c->stream));
-    auto kern = lean::k_push_lean<DIM, DEPOSIT, true, true, 1, true>;
+    auto kern = lean::k_push_lean_pull<DIM, DEPOSIT>;
     PSC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     kern<<<tiles, lean::n_warps<1>() * 32, smem_bytes, c->stream>>>(tm, G, geo, A);
     // the output store is the store now
@@ -1319,7 +1323,7 @@ static int push_dim(Ctx* c, bool gap)
     int rc = -1;
     // (tensor-map strides are multiples of 16 bytes)
     const bool lean_ok = stat && !gap && c->opt_lean && c->opt_tma && G.im[xyz ? 0 : 1] % 4 == 0;
-    // pull mode (push_lean.cuh PULL): this push completes the previous step's sort on its way
+    // pull mode (push_lean_pull.cuh): this push completes the previous step's sort on its way
     bool pull_now = lean_ok && count && A.same_dxi && c->opt_lean < 2 && pull_possible(c);
 #ifdef PM_FAST_MATH
     pull_now = lean_ok && count && A.same_dxi && pull_possible(c);

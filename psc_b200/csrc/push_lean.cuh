@@ -117,25 +117,10 @@ __device__ __forceinline__ float moments_to_leaf(float v, int lane)
 }
 
 // W = particles per lane: 1, or 2 with the update on the packed FP32 pipe (pic_math.cuh f2)
-//
-// PULL (COUNT, SAME, W = 1): the push of step n + 1 doubles as the sort of step n.  The input
-// store (A.xin4 / A.pin4, cell runs A.cell_off) is the previous push's output: ordered by the
-// cells the particles were in BEFORE that push, so a run holds the particles that stayed in
-// the cell ("live": their cell index still is the run's) and, dead, those that left it.  The
-// output store (A.xi4 / A.pxi4, cell runs A.out_off) already holds every particle that changed
-// cell, at its place in the reference's order (k_fs_place_movers): inside a cell
-// [arrivals from lower cells | stayers | arrivals from higher cells and other patches].  For
-// each row the kernel pushes the arrivals in front of the stayers where they lie, pulls the
-// live particles of the input run through the push to out_off + n_before + rank, then pushes
-// the arrivals behind them -- in this order, and the queue is walked first-in first-out, so
-// that the particles leaving a cell in one direction are ranked in index order (the rank goes
-// into the mover list for the next k_fs_place_movers).  One read and one write of every
-// particle per step instead of two.
-template <int DIM, int DEPOSIT, bool COUNT, bool SAME, int W, bool PULL = false>
+template <int DIM, int DEPOSIT, bool COUNT, bool SAME, int W>
 __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
   k_push_lean(const __grid_constant__ CUtensorMap tm, GridDev G, GeoStatic<DIM> geo, PushArgs A)
 {
-  static_assert(!PULL || (COUNT && SAME && W == 1), "PULL needs the class counts and the index in the queue");
   constexpr int QC = qcap<W>();
   constexpr int NW = n_warps<W>();
   constexpr bool XYZ = DIM == pm::DIM_XYZ;
@@ -206,18 +191,13 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
   // add each one to the plane of its destination class
   auto drain = [&](int cnt) {
     const bool a2 = lane < cnt;
-    // PULL walks the queue from its head (first in, first out: ranks in index order)
-    const int q0 = PULL ? 0 : qn - cnt;
     Walker<DIM, DEPOSIT> w;
     float val[NM];
     int ci[3] = {0, 0, 0};
     bool more = false;
     float qw = 0.f;
-    [[maybe_unused]] bool mover = false;     // PULL: changes cell inside this rank's patches
-    [[maybe_unused]] uint32_t mv_e = 0;      // ... its counter: plane entry (class, source cell)
-    [[maybe_unused]] uint32_t mv_i = 0;      // ... its index in the store
     if (a2) {
-      const float4 A0 = myQ[2 * (q0 + lane)], A1 = myQ[2 * (q0 + lane) + 1];
+      const float4 A0 = myQ[2 * (qn - cnt + lane)], A1 = myQ[2 * (qn - cnt + lane) + 1];
       pm::Trajectory t;
       int sc[3], dc[3]; // the indexer's source and destination cells
       float xn[3];      // pushed position (SAME: read back when needed)
@@ -262,26 +242,11 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           }
           float uu[3] = {0.f, 0.f, 0.f};
           cls = fs_classify(G, A.tab, p, sc[0], sc[1], sc[2], xn, uu, rq, rc);
-          if constexpr (PULL) {
-            if (cls == CLS_CENTER) {
-              // wrapped around a periodic direction and landed on the far edge, which the
-              // exchange folds back to 0 (bnd_particles_impl.hxx:131-140): it stays in its cell
-              // with the folded position.  Nobody rewrites a stayer in pull mode but us.
-              const uint32_t i = (uint32_t)__float_as_int(XYZ ? A1.w : A0.x);
-              A.xi4[i] = make_float4(xn[0], xn[1], xn[2], A.xi4[i].w);
-            }
-          }
         }
         if (cls < FS_PLANES) {
           const size_t e = (size_t)cls * A.nct + (size_t)p * G.n_cells +
                            (size_t)((sc[2] * G.ldims[1] + sc[1]) * G.ldims[0] + sc[0]);
-          if (PULL && cls != CLS_CENTER) {
-            mover = true; // (counted below, together with the others of its group)
-            mv_e = (uint32_t)e;
-            mv_i = (uint32_t)__float_as_int(XYZ ? A1.w : A0.x);
-          } else {
-            atomicAdd(cnt32 + (e >> 1), 1u << (16 * (e & 1)));
-          }
+          atomicAdd(cnt32 + (e >> 1), 1u << (16 * (e & 1)));
         } else if (cls == CLS_BAD) {
           atomicExch(&A.flags[0], 1u);
         } else if (cls == CLS_DROP) {
@@ -299,50 +264,10 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
       more = w.first(G.pc, t, qw, ci, val);
       leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
     }
-    if constexpr (PULL) {
-      // rank of every mover inside its (source cell, class) group -- the lanes are in index
-      // order, so are the walks of a cell's entries -- and its record in the mover list
-      const unsigned mm = __ballot_sync(FULL, mover);
-      if (mm) {
-        uint32_t sb = 0;
-        if (lane == __ffs(mm) - 1) {
-          sb = atomicAdd(&A.flags[3], (uint32_t)__popc(mm));
-        }
-        sb = __shfl_sync(FULL, sb, __ffs(mm) - 1);
-        if (mover) {
-          const unsigned grp = __match_any_sync(mm, mv_e);
-          const int leader = __ffs(grp) - 1;
-          const int sh = 16 * (mv_e & 1);
-          uint32_t old = 0;
-          if (lane == leader) {
-            old = atomicAdd(cnt32 + (mv_e >> 1), (uint32_t)__popc(grp) << sh);
-          }
-          old = __shfl_sync(grp, old, leader);
-          const uint32_t rank = ((old >> sh) & 0xffffu) + __popc(grp & lt);
-          const uint32_t slot = sb + __popc(mm & lt);
-          if (slot < A.mv_cap) {
-            A.mv_idx[slot] = mv_i;
-            A.mv_key[slot] = make_uint2(mv_e, rank);
-          }
-        }
-      }
-    }
     while (__any_sync(FULL, more)) {
       if (more) {
         more = w.next(G.pc, qw, ci, val);
         leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
-      }
-    }
-    if constexpr (PULL) {
-      // close the gap at the head (at most QC - 32 < 32 entries remain)
-      const int rem = qn - cnt;
-      float4 m0, m1;
-      if (lane < rem) {
-        m0 = myQ[2 * (cnt + lane)], m1 = myQ[2 * (cnt + lane) + 1];
-      }
-      __syncwarp();
-      if (lane < rem) {
-        myQ[2 * lane] = m0, myQ[2 * lane + 1] = m1;
       }
     }
     qn -= cnt;
@@ -368,77 +293,11 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
     const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, RUN);
     // shared J of the row's first cell, as seen by this lane's leaf slot
     const int jrow = myJ + (rs2 - n2) * SZ + (XYZ ? (rs1 - n1) * SY + (o0 - n0) : (o1 - n1) * SY);
-    // PULL: lane j < RUN holds, for the row's j-th cell, where its stayers go in the output store
-    // and how many arrivals lie in front of / behind them
-    [[maybe_unused]] uint32_t my_sbase = 0, my_nbefore = 0, my_abase = 0, my_nafter = 0;
-    if constexpr (PULL) {
-      const uint32_t* const ooff = A.out_off + (size_t)p * G.n_cells;
-      const uint32_t o_lo = __ldg(&ooff[c0 + min(lane, RUN)]);
-      const uint32_t o_hi = __shfl_down_sync(FULL, o_lo, 1);
-      if (lane < RUN) {
-        const uint2 st = __ldg(&A.stay[(size_t)p * G.n_cells + c0 + lane]); // {n_before, n_stay}
-        my_nbefore = st.x;
-        my_sbase = o_lo + my_nbefore;
-        my_abase = my_sbase + st.y;
-        my_nafter = o_hi - my_abase;
-      }
-    }
-    // PULL: push the arrivals of the row's cells where they lie (they were put there in sorted
-    // order) and park every one of them: the walk deposits it, counts it, and lists it if it
-    // moves on
-    [[maybe_unused]] auto arrivals = [&](uint32_t my_first, uint32_t my_n) {
-      uint32_t incl = my_n; // inclusive scan over the row's cells (lanes >= RUN hold 0)
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) {
-          incl += v;
-        }
-      }
-      const uint32_t total = __shfl_sync(FULL, incl, 31);
-      for (uint32_t vb = 0; vb < total; vb += 32) {
-        if (qn > QC - 32) {
-          drain(min(qn, 32));
-        }
-        const uint32_t v = vb + lane;
-        const bool act = v < total;
-        int j = 0;
-#pragma unroll
-        for (int k = 0; k < RUN - 1; k++) {
-          j += v >= __shfl_sync(FULL, incl, k);
-        }
-        const uint32_t ex = __shfl_sync(FULL, incl - my_n, j), fi0 = __shfl_sync(FULL, my_first, j);
-        const uint32_t i = fi0 + (v - ex);
-        pm::Trajectory t;
-        float qw = 0.f;
-        if (act) {
-          const float4 X = A.xi4[i], U = A.pxi4[i];
-          float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
-          pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
-          qw = U.w;
-        }
-        const unsigned am = __ballot_sync(FULL, act);
-        if (act) {
-          const int slot = qn + __popc(am & lt);
-          const float fi = __int_as_float((int)i);
-          myQ[2 * slot] = make_float4(XYZ ? t.xm[0] : fi, t.xm[1], t.xm[2], qw);
-          myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], XYZ ? fi : t.v[0]);
-        }
-        qn += __popc(am);
-        __syncwarp();
-      }
-    };
-    if constexpr (PULL) {
-      arrivals(my_sbase - my_nbefore, my_nbefore);
-    }
     if constexpr (W == 1) {
     if (begin < end) {
       int cur = 0;                                           // cell of the row the passes are at
       uint32_t cb = begin, ce = __shfl_sync(FULL, myoff, 1); // its particle range
       uint32_t n_left = 0;                                   // ... and whether this lane's particles left it (summed at the flush)
-      [[maybe_unused]] uint32_t srun = 0;                    // PULL: live particles of the cell so far (= their rank base)
       float acc[NM];                                         // this lane's share of the cell's moments
 #pragma unroll
       for (int n = 0; n < NM; n++) {
@@ -462,11 +321,9 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         }
       };
       // the next chunk travels global -> shared with cp.async while this one is computed
-      const float4* const xsrc = PULL ? A.xin4 : A.xi4;
-      const float4* const psrc = PULL ? A.pin4 : A.pxi4;
       if (begin + lane < end) {
-        cp_async16(myP, xsrc + begin + lane);
-        cp_async16(myP + 32 * sizeof(float4), psrc + begin + lane);
+        cp_async16(myP, A.xi4 + begin + lane);
+        cp_async16(myP + 32 * sizeof(float4), A.pxi4 + begin + lane);
       }
       cp_async_commit();
       uint32_t base = begin;
@@ -483,8 +340,8 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         cp_async_wait_all();
         const float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
         if (i + 32 < end) {
-          cp_async16(myP, xsrc + i + 32);
-          cp_async16(myP + 32 * sizeof(float4), psrc + i + 32);
+          cp_async16(myP, A.xi4 + i + 32);
+          cp_async16(myP + 32 * sizeof(float4), A.pxi4 + i + 32);
         }
         cp_async_commit();
         // ---- gather, Boris, move (the reference's arithmetic, pic_math.cuh)
@@ -492,14 +349,12 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         float dx[3] = {0.f, 0.f, 0.f}, xa[3] = {0.f, 0.f, 0.f}; // displacement, centred offset
         float q = 0.f;                                         // q w of a particle that stayed in its cell
         pm::Trajectory t;
-        float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
-        uint32_t di = i; // where the pushed record goes (PULL: its place in the output store)
+        float x[3] = {X.x, X.y, X.z};
         if (act) {
+          float u[3] = {U.x, U.y, U.z};
           pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-          if constexpr (!PULL) {
-            A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-            A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
-          }
+          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
           cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
           if constexpr (!SAME) {
             // 1/float(dx) and float(dx_inv) may disagree at a cell edge: such a particle is
@@ -520,47 +375,12 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           }
           q = cross ? 0.f : U.w;
         }
-        [[maybe_unused]] bool live = false; // PULL: the record still belongs to the cell of its run
-        if constexpr (PULL) {
-          // destination of the live records: the stayers' base of the lane's cell + the rank among
-          // the cell's live records.  The loop visits the cells this chunk touches exactly like the
-          // pass loop below, on copies of its state.
-          const bool in_row = act && (XYZ ? (t.lg[1] == rs1 && t.lg[2] == rs2) : t.lg[2] == rs2);
-          int cu = cur;
-          uint32_t b2 = cb, e2 = ce, sr = srun;
-          for (;;) {
-            const uint32_t hi = min(e2 - base, 32u), lo = b2 > base ? b2 - base : 0u;
-            const bool lv = ((uint32_t)lane - lo < hi - lo) && in_row && t.lg[RD] == (XYZ ? o0 : o1) + cu;
-            const unsigned lm = __ballot_sync(FULL, lv);
-            const uint32_t sb = __shfl_sync(FULL, my_sbase, cu);
-            if (lv) {
-              live = true;
-              di = sb + sr + __popc(lm & lt);
-            }
-            if (e2 > base + 32 || ++cu == RUN) {
-              break;
-            }
-            sr = 0;
-            b2 = e2;
-            e2 = __shfl_sync(FULL, myoff, cu + 1);
-            if (b2 >= base + 32) {
-              break;
-            }
-          }
-          if (live) {
-            A.xi4[di] = make_float4(x[0], x[1], x[2], X.w);
-            A.pxi4[di] = make_float4(u[0], u[1], u[2], U.w);
-          } else {
-            cross = false; // a record that left its cell a step ago: its copy among the arrivals is the particle
-            q = 0.f;
-          }
-        }
         // park cell-crossing particles for the split/deposit walk
         const unsigned cm = __ballot_sync(FULL, cross);
         if (cm) {
           if (cross) {
             const int slot = qn + __popc(cm & lt);
-            const float fi = __int_as_float((int)di);
+            const float fi = __int_as_float((int)i);
             if constexpr (SAME) {
               // (xm | i, qw), (xp, i | vx)
               myQ[2 * slot] = make_float4(XYZ ? t.xm[0] : fi, t.xm[1], t.xm[2], U.w);
@@ -583,9 +403,6 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           const float qe = mine ? q : 0.f;
           if (COUNT) {
             n_left += mine && cross;
-          }
-          if constexpr (PULL) {
-            srun += __popc(__ballot_sync(FULL, mine && live));
           }
           {
             const float qh = qe * h12;
@@ -620,19 +437,16 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           if (ce > cb) {
             flush_moments(jrow + cur * ROW_STRIDE);
             if (COUNT) {
-              const uint32_t pop = PULL ? srun : ce - cb, left = __reduce_add_sync(FULL, n_left);
+              const uint32_t pop = ce - cb, left = __reduce_add_sync(FULL, n_left);
               if (lane == 0) {
                 const size_t e = cen0 + (size_t)(c0 + cur);
                 atomicAdd(cnt32 + (e >> 1), (pop - left) << (16 * (e & 1)));
-                if (ce - cb > CNT_MAX) {
+                if (pop > CNT_MAX) {
                   atomicExch(&A.flags[0], 1u);
                 }
               }
               n_left = 0;
             }
-          }
-          if constexpr (PULL) {
-            srun = 0;
           }
           if (++cur == RUN) {
             break;
@@ -842,9 +656,6 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         }
         base += 64;
       } while (base < end);
-    }
-    if constexpr (PULL) {
-      arrivals(my_abase, my_nafter);
     }
     if (lane == 0) {
       row = atomicAdd(&row_ctr, 1);
