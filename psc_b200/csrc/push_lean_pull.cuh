@@ -298,27 +298,38 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? (PULL ? LEAN_PULL_
     const uint32_t begin = __shfl_sync(FULL, myoff, 0), end = __shfl_sync(FULL, myoff, RUN);
     // shared J of the row's first cell, as seen by this lane's leaf slot
     const int jrow = myJ + (rs2 - n2) * SZ + (XYZ ? (rs1 - n1) * SY + (o0 - n0) : (o1 - n1) * SY);
-    // PULL: lane j < RUN holds where the stayers of the row's j-th cell go in the output store
-    [[maybe_unused]] uint32_t my_sbase = 0;
-    // ... and its arrivals in front of (behind) the stayers: first index, count.  Loaded when
-    // needed rather than kept across the chunk loop (registers)
-    [[maybe_unused]] auto arrival_range = [&](bool behind, uint32_t& first, uint32_t& n) {
-      const uint32_t* const ooff = A.out_off + (size_t)p * G.n_cells;
-      const uint32_t o_lo = __ldg(&ooff[c0 + min(lane, RUN)]);
-      const uint32_t o_hi = __shfl_down_sync(FULL, o_lo, 1);
-      first = 0, n = 0;
-      if (lane < RUN) {
-        const uint2 st = __ldg(&A.stay[(size_t)p * G.n_cells + c0 + lane]); // {n_before, n_stay}
-        my_sbase = o_lo + st.x;
-        first = behind ? my_sbase + st.y : o_lo;
-        n = behind ? o_hi - first : st.x;
+    // lane j < RUN holds where the stayers of the row's j-th cell go in the output store
+    uint32_t my_sbase = 0;
+    // Arrivals of the row.  Segments: lane j < RUN = the arrivals in front of cell j's stayers,
+    // lane RUN + j = those behind them; a virtual index runs over the 2 RUN segments.  They are
+    // pushed where they lie.  One that stays in its cell deposits its single leaf directly (the
+    // moment formulas of the chunk loop for one particle) and is counted in the CENTER plane;
+    // one that moves on is parked for the ordered walk: in front of the row's stayers if it lies
+    // in front of them.  One that lies BEHIND them must be parked after them: the early pass
+    // (row start) leaves such a record untouched and remembers its lane (late_mask), the late
+    // pass (row end) pushes it again and parks it.  Rows with more than 32 arrivals push the
+    // ones behind the stayers in the late pass altogether.
+    static_assert(2 * RUN <= 32, "one lane per arrival segment of a row");
+    uint32_t late_mask = 0;
+    bool one_shot = true;
+    auto arrival_pass = [&](const bool late) {
+      if (late && one_shot && late_mask == 0) {
+        return;
       }
-    };
-    // PULL: push the arrivals of the row's cells where they lie (they were put there in sorted
-    // order) and park every one of them: the walk deposits it, counts it, and lists it if it
-    // moves on
-    [[maybe_unused]] auto arrivals = [&](uint32_t my_first, uint32_t my_n) {
-      uint32_t incl = my_n; // inclusive scan over the row's cells (lanes >= RUN hold 0)
+      const int jj = lane < RUN ? lane : lane - RUN; // (lanes >= 2 RUN: empty segments)
+      uint32_t seg_first = 0, seg_n = 0;
+      if (lane < 2 * RUN) {
+        const uint32_t* const ooff = A.out_off + (size_t)p * G.n_cells + c0 + jj;
+        const uint32_t o_lo = __ldg(ooff), o_hi = __ldg(ooff + 1);
+        const uint2 st = __ldg(&A.stay[(size_t)p * G.n_cells + c0 + jj]); // {n_before, n_stay}
+        if (lane < RUN) {
+          my_sbase = o_lo + st.x;
+          seg_first = o_lo, seg_n = st.x;
+        } else {
+          seg_first = o_lo + st.x + st.y, seg_n = o_hi - seg_first;
+        }
+      }
+      uint32_t incl = seg_n; // inclusive scan over the segments
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(FULL, incl, o);
@@ -327,51 +338,110 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? (PULL ? LEAN_PULL_
         }
       }
       const uint32_t total = __shfl_sync(FULL, incl, 31);
-      for (uint32_t vb = 0; vb < total; vb += 32) {
+      if (!late) {
+        one_shot = total <= 32;
+      }
+      const uint32_t vb0 = (late && !one_shot) ? __shfl_sync(FULL, incl, RUN - 1) & ~31u : 0u;
+      for (uint32_t vb = vb0; vb < total; vb += 32) {
         if (qn > QC - 32) {
           drain(min(qn, 32));
         }
         const uint32_t v = vb + lane;
-        const bool act = v < total;
-        int j = 0;
+        int sg = 0; // segment of this lane's virtual index
 #pragma unroll
-        for (int k = 0; k < RUN - 1; k++) {
-          j += v >= __shfl_sync(FULL, incl, k);
+        for (int k = 0; k < 2 * RUN - 1; k++) {
+          sg += v >= __shfl_sync(FULL, incl, k);
         }
-        const uint32_t ex = __shfl_sync(FULL, incl - my_n, j), fi0 = __shfl_sync(FULL, my_first, j);
-        const uint32_t i = fi0 + (v - ex);
+        const uint32_t ex = __shfl_sync(FULL, incl - seg_n, sg), f0 = __shfl_sync(FULL, seg_first, sg);
+        const uint32_t i = f0 + (v - ex);
+        const bool behind = sg >= RUN;
+        const int j = behind ? sg - RUN : sg; // cell of the row
+        bool doit = v < total;
+        if (late) {
+          doit = doit && behind && (one_shot ? ((late_mask >> lane) & 1u) != 0u : true);
+        } else {
+          doit = doit && (!behind || one_shot);
+        }
         pm::Trajectory t;
         float qw = 0.f;
-        if (act) {
+        bool park = false, defer = false;
+        if (doit) {
           const float4 X = A.xi4[i], U = A.pxi4[i];
           float x[3] = {X.x, X.y, X.z}, u[3] = {U.x, U.y, U.z};
           pm::advance<DIM>(G.pc, EM, x, u, __float_as_int(X.w), t);
-          A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
-          A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+          const bool cross = (XYZ && t.lf[0] != t.lg[0]) || t.lf[1] != t.lg[1] || t.lf[2] != t.lg[2];
           qw = U.w;
+          defer = !late && behind && cross; // (left as it is: the late pass pushes it again)
+          if (!defer) {
+            A.xi4[i] = make_float4(x[0], x[1], x[2], X.w);
+            A.pxi4[i] = make_float4(u[0], u[1], u[2], U.w);
+            park = cross;
+            if (!cross) {
+              // its leaf, from its moments (header comment of push_lean.cuh)
+              float dx[3], xa[3];
+#pragma unroll
+              for (int d = 0; d < 3; d++) {
+                dx[d] = t.xp[d] - t.xm[d];
+                xa[d] = __fmaf_rn(.5f, t.xp[d] + t.xm[d], -(float)t.lg[d]);
+              }
+              if (!XYZ) {
+                dx[0] = t.v[0] * G.pc.dt * G.pc.dxi_idx[0];
+              }
+              const float qh = qw * ((1.f / 12.f) * dx[0] * dx[1] * dx[2]);
+              float* const b = sJ + (rs2 - n2) * SZ + (XYZ ? (rs1 - n1) * SY + (o0 - n0) : (o1 - n1) * SY) +
+                               j * ROW_STRIDE;
+              const float* const fnq = DEPOSIT == pm::DEPOSIT_SPLIT ? G.pc.fnqs_split : G.pc.fnq_var1;
+              if (XYZ) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                  const float m = qw * dx[d];
+                  const float sa = m * xa[(d + 1) % 3], sb = m * xa[(d + 2) % 3];
+                  const float sab = __fmaf_rn(sa, xa[(d + 2) % 3], qh);
+                  atomicAdd(b + leaf_lin<DIM>(4 * d + 0, SY, SZ, NODES), (((m - sa) - sb) + sab) * fnq[d]);
+                  atomicAdd(b + leaf_lin<DIM>(4 * d + 1, SY, SZ, NODES), (sa - sab) * fnq[d]);
+                  atomicAdd(b + leaf_lin<DIM>(4 * d + 2, SY, SZ, NODES), (sb - sab) * fnq[d]);
+                  atomicAdd(b + leaf_lin<DIM>(4 * d + 3, SY, SZ, NODES), sab * fnq[d]);
+                }
+              } else {
+                const float m0 = qw * dx[0], m1 = qw * dx[1], m2 = qw * dx[2];
+                const float sa = m0 * xa[1], sb = m0 * xa[2];
+                const float sab = __fmaf_rn(sa, xa[2], qh);
+                atomicAdd(b + leaf_lin<DIM>(0, SY, SZ, NODES), (((m0 - sa) - sb) + sab) * fnq[0]);
+                atomicAdd(b + leaf_lin<DIM>(1, SY, SZ, NODES), (sa - sab) * fnq[0]);
+                atomicAdd(b + leaf_lin<DIM>(2, SY, SZ, NODES), (sb - sab) * fnq[0]);
+                atomicAdd(b + leaf_lin<DIM>(3, SY, SZ, NODES), sab * fnq[0]);
+                const float s1b = m1 * xa[2], s2a = m2 * xa[1];
+                atomicAdd(b + leaf_lin<DIM>(4, SY, SZ, NODES), (m1 - s1b) * fnq[1]);
+                atomicAdd(b + leaf_lin<DIM>(5, SY, SZ, NODES), s1b * fnq[1]);
+                atomicAdd(b + leaf_lin<DIM>(6, SY, SZ, NODES), (m2 - s2a) * fnq[2]);
+                atomicAdd(b + leaf_lin<DIM>(7, SY, SZ, NODES), s2a * fnq[2]);
+              }
+              const size_t e = cen0 + (size_t)(c0 + j);
+              atomicAdd(cnt32 + (e >> 1), 1u << (16 * (e & 1)));
+            }
+          }
         }
-        const unsigned am = __ballot_sync(FULL, act);
-        if (act) {
-          const int slot = qn + __popc(am & lt);
-          const float fi = __int_as_float((int)i);
-          myQ[2 * slot] = make_float4(XYZ ? t.xm[0] : fi, t.xm[1], t.xm[2], qw);
-          myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], XYZ ? fi : t.v[0]);
+        late_mask |= __ballot_sync(FULL, defer); // (warp-uniform)
+        const unsigned pm_ = __ballot_sync(FULL, park);
+        if (pm_) {
+          if (park) {
+            const int slot = qn + __popc(pm_ & lt);
+            const float fi = __int_as_float((int)i);
+            myQ[2 * slot] = make_float4(XYZ ? t.xm[0] : fi, t.xm[1], t.xm[2], qw);
+            myQ[2 * slot + 1] = make_float4(t.xp[0], t.xp[1], t.xp[2], XYZ ? fi : t.v[0]);
+          }
+          qn += __popc(pm_);
+          __syncwarp();
         }
-        qn += __popc(am);
-        __syncwarp();
       }
     };
 #pragma unroll 1
-    for (int ph = 0; ph < (PULL ? 2 : 1); ph++) {
-    if constexpr (PULL) {
-      // ph 0: the arrivals in front of the stayers, then the stayers; ph 1: the arrivals behind
-      // them (one copy of the arrival code: the kernel has to stay inside the instruction cache)
-      uint32_t first, n;
-      arrival_range(ph == 1, first, n);
-      arrivals(first, n);
-      if (ph == 1) {
-        break;
-      }
+    for (int ph = 0; ph < 2; ph++) {
+    // ph 0: the arrivals (early pass), then the stayers; ph 1: the late pass (one copy of the
+    // arrival code: the kernel has to stay inside the instruction cache)
+    arrival_pass(ph == 1);
+    if (ph == 1) {
+      break;
     }
     if constexpr (W == 1) {
     if (begin < end) {
