@@ -64,6 +64,14 @@ struct FldTile2
   }
 };
 
+// float add to shared memory through a 32-bit shared-space address: same CAS loop as
+// atomicAdd(float*), but no generic -> shared conversion (an S2UR on the critical path of
+// every cell flush: 9 % of the stall samples, profiles/README.md)
+__device__ __forceinline__ void red_shared_f32(uint32_t addr, float v)
+{
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
                                               uint64_t* bar, bool four_d)
 {
@@ -133,6 +141,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
   extern __shared__ __align__(128) float smem[];
   float* sEM = smem;             // [6][f2][f1][f0]
   float* sJ = smem + 6 * NODES;  // [3][f2][f1][f0]
+  const uint32_t sJ32 = smem_u32(sJ);
   float4* sQ = reinterpret_cast<float4*>(smem + ((9 * NODES + 3) & ~3)); // [NW][QC][2]
   float4* sP = sQ + NW * QC * 2;                                         // [NW][2][32 W] next chunk
   __shared__ uint64_t bar;
@@ -313,7 +322,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         warp_transpose_reduce<NVP>(v, lane);
         const float leaf = moments_to_leaf<DIM>(v[0], lane) * my_fnq;
         if (writer) {
-          atomicAdd(&sJ[at], leaf);
+          red_shared_f32(sJ32 + 4u * (uint32_t)at, leaf);
         }
 #pragma unroll
         for (int n = 0; n < NM; n++) {
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         warp_transpose_reduce<NVP>(v, lane);
         const float leaf = moments_to_leaf<DIM>(v[0], lane) * my_fnq;
         if (writer) {
-          atomicAdd(&sJ[at], leaf);
+          red_shared_f32(sJ32 + 4u * (uint32_t)at, leaf);
         }
 #pragma unroll
         for (int n = 0; n < NM; n++) {
