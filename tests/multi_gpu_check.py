@@ -60,8 +60,15 @@ def gather_obj(obj, rank, world):
     return out
 
 
+# one rank takes the general exchange + sort while its peers stay on the fused pass (a particle
+# that moves two cells breaks the fused pass's precondition on the rank that owns it): dz = 0.25 <
+# v dt.  Both paths issue exactly one particle exchange per call over the same neighbour tables,
+# which is what keeps the ranks in step (fused_sort.cu, fused_bnd_sort).
+FALLBACK_CASE = dict(gdims=(16, 16, 32), length=(16., 16., 8.), np_=(2, 2, 4))
+
+
 def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None, balance_step=None,
-             want_info=False):
+             want_info=False, vth=(0.5, 0.05), hot_particle=False):
     og = ol.Grid(dt=0.35, kinds=KINDS, nicell=8, **gkw)
     npg = og.n_patches
     if n_by_rank is None:
@@ -71,7 +78,11 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
     rank_of_patch = np.repeat(np.arange(world), n_by_rank).astype(np.int32)
     flds = random_fields(og, seed=3, amp_e=0.02, amp_b=0.05)
     ol.fill_ghosts(og, flds, 3, 9)
-    prts, off = thermal_plasma(og, ppc=6, seed=4, vth=(0.5, 0.05), margin=0.02)
+    prts, off = thermal_plasma(og, ppc=6, seed=4, vth=vth, margin=0.02)
+    if hot_particle:
+        # patch 0 (rank 0): from cell z = 2 to cell z = 4 in one step
+        prts["x"][off[0] + 5] = (3.5, 3.5, 0.74)
+        prts["u"][off[0] + 5] = (0., 0., 10.)
 
     g = og.g
     grid = pb.Grid(gdims=tuple(g.gdims), length=tuple(g.length), np=tuple(g.np), dt=g.dt, kinds=og.kinds,
@@ -156,6 +167,8 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
         bytes_equal = bool(same_counts and all_p.tobytes() == rp.tobytes())
         if n_steps == 1:
             ok = ok and bytes_equal
+        if hot_particle and fused:
+            ok = ok and res[0][3]["fallbacks"] >= 1 and all(r[3]["fallbacks"] == 0 for r in res[1:])
         info = dict(name=name, fused=int(fused), steps=n_steps, ranks=world, counts_equal=bool(same_counts),
                     particles_byte_exact=bytes_equal, fld_rel=float(ferr), x_abs=perr, u_abs=uerr,
                     energies_rel=eerr, balanced=balance_step is not None, ok=bool(ok))
@@ -185,6 +198,9 @@ def main():
     uneven = [npg - small * (world - 1)] + [small] * (world - 1)
     ok = run_case("xyz_uneven_ranks", cases["xyz_periodic_slabs"], rank, world, local_rank, True,
                   n_by_rank=uneven) and ok
+    # one rank on the general path, the others on the fused pass
+    ok = run_case("xyz_one_rank_falls_back", FALLBACK_CASE, rank, world, local_rank, True, n_steps=2,
+                  vth=(0.05, 0.005), hot_particle=True) and ok
     # load balancing: start uneven, rebalance after the first step, keep stepping
     for fused in (False, True):
         ok = run_case("xyz_balance_after_step1", cases["xyz_periodic_slabs"], rank, world, local_rank,
