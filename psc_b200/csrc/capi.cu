@@ -1030,6 +1030,7 @@ int psc_b200_set_option(psc_b200_ctx* ctx, const char* name, double value)
     else if (n == "push_collect") { c->opt_push_collect = v; }
     else if (n == "pull") { c->opt_pull = v; }
     else if (n == "pull_cap") { c->opt_pull_cap = v; }
+    else if (n == "cell_moments") { c->opt_cell_moments = v; }
     else if (n == "vec_fields") { c->opt_vec_fields = v; }
     else if (n == "threads") { c->opt_threads = v; }
     else if (n == "min_blocks") { c->opt_min_blocks = v; }

@@ -101,6 +101,7 @@ struct Ctx
   int opt_pull = 0;         // the push of the next step completes the sort of this one (one pass less over the
                             // particles; byte-identical stores, but 40.6 ms against 33.1 ms per S3D step as it
                             // stands -- DESIGN.md 3.2d): opt-in
+  int opt_cell_moments = 1; // moments of a cell-ordered store: summed per cell in registers, one add per cell and node
   int opt_pull_cap = 0;     // > 0: capacity of the pull push's mover list (tests: force the overflow route)
   int opt_push_collect = 1; // multi-rank: k_push_lean lists the remote leavers (else a pass over the boundary cells)
   int opt_lean = 1;        // k_push_lean (push_lean.cuh) whenever the tile geometry is compile-time

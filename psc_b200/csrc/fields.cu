@@ -475,6 +475,80 @@ __global__ void k_rho_1st_nc(GridDev G, uint32_t n, const uint32_t* __restrict__
   }
 }
 
+// The same deposit for a cell-ordered store: one warp per cell sums its particles' eight
+// (four) node weights in registers and adds them once per cell -- 64 x fewer global atomics at
+// 64 particles per cell (S3D: 150 ms -> the time of reading the particles).  A particle whose
+// node index is not the run's cell (1/float(dx) vs float(dx_inv) at a cell edge) adds on its own.
+constexpr int RHO_WARPS = 8;
+__global__ void __launch_bounds__(RHO_WARPS * 32)
+  k_rho_1st_nc_cells(GridDev G, uint32_t nct, const uint32_t* __restrict__ cell_off,
+                     const float4* __restrict__ xi4, const float4* __restrict__ pxi4, float* __restrict__ R,
+                     long slot_len, float fnqs, const float* __restrict__ qk)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * RHO_WARPS + (threadIdx.x >> 5);
+  if (g >= nct) {
+    return;
+  }
+  const int p = g / G.n_cells;
+  const int s = g - p * G.n_cells;
+  const int c[3] = {s % G.ldims[0], (s / G.ldims[0]) % G.ldims[1], s / (G.ldims[0] * G.ldims[1])};
+  const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+  if (begin == end) {
+    return;
+  }
+  const bool yz = G.dim == pm::DIM_YZ;
+  float* Rp = R + p * slot_len;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (uint32_t i = begin + lane; i < end; i += 32) {
+    const float4 X = xi4[i];
+    const float qw = pxi4[i].w;
+    const float q = qk[__float_as_int(X.w)];
+    const float value = fnqs * ((qw / q) * q); // (moment.hxx:77 val = w * q, w = qni_wni / q)
+    const float x[3] = {X.x, X.y, X.z};
+    int l[3];
+    float h[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const float xn = x[d] * G.pc.dxi[d];
+      l[d] = pm::fint(xn);
+      h[d] = xn - (float)l[d];
+    }
+    const bool here = (yz || l[0] == c[0]) && l[1] == c[1] && l[2] == c[2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int ox = k & 1, oy = (k >> 1) & 1, oz = k >> 2;
+      if (yz && ox) {
+        continue;
+      }
+      const float wgt = yz ? value * (oy ? h[1] : 1.f - h[1]) * (oz ? h[2] : 1.f - h[2])
+                           : value * (ox ? h[0] : 1.f - h[0]) * (oy ? h[1] : 1.f - h[1]) * (oz ? h[2] : 1.f - h[2]);
+      if (here) {
+        acc[k] += wgt;
+      } else {
+        atomicAdd(Rp + fld_off(G, 0, yz ? 0 : l[0] + ox, l[1] + oy, l[2] + oz), wgt);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+  }
+  // lane k adds node k
+  float mine = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    mine = lane == k ? acc[k] : mine;
+  }
+  if (lane < 8 && !(yz && (lane & 1))) {
+    const int ox = lane & 1, oy = (lane >> 1) & 1, oz = lane >> 2;
+    atomicAdd(Rp + fld_off(G, 0, yz ? 0 : c[0] + ox, c[1] + oy, c[2] + oz), mine);
+  }
+}
+
 // add_ghosts_reflecting.hxx:77-154, node-centred, one (d, hi) at a time
 __global__ void k_reflect_nc(GridDev G, float* __restrict__ R, long slot_len, int d, int hi,
                              const pm::PatchBnd* __restrict__ pbs)
@@ -1328,6 +1402,167 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The cell-centred moments of a cell-ordered store: one warp per cell.  A particle of cell c
+// deposits to the cells l .. l + 1 with l in {c - 1, c} per direction (which half of the cell
+// it sits in), i.e. to the 27 cells around c with three weights per direction, one of them 0:
+//   l = c - 1: {1 - h, h, 0}      l = c: {0, 1 - h, h}
+// -- the reference's factors, multiplied in its order (value * wx * wy * wz).  For one component
+// at a time every lane sums its particles' 27 contributions in registers, a transposing
+// butterfly leaves the warp total of target t on lane t, and lane t adds it once: 27 global
+// atomics per cell and component instead of 8 per particle and value (S3D, Moments_1st:
+// 648 ms before).  A particle whose l is not c - 1 or c (1/float(dx) against float(dx_inv) at
+// an edge) adds on its own.
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane)
+{
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = lane & h;
+#pragma unroll
+    for (int j = 0; j < h; j++) {
+      const float send = up ? v[j] : v[j + h];
+      const float keep = up ? v[j + h] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+}
+
+constexpr int MOM_WARPS = 4;
+// (WHICH at compile time: Moment_n needs neither the momenta nor the 1/gamma of the others)
+template <int WHICH>
+__global__ void __launch_bounds__(MOM_WARPS * 32)
+  k_moment_1st_cells(GridDev G, MomentPrm M, int n_kinds, uint32_t nct, const uint32_t* __restrict__ cell_off,
+                     const float4* __restrict__ xi4, const float4* __restrict__ pxi4, float* __restrict__ R,
+                     long slot_len)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = blockIdx.x * MOM_WARPS + (threadIdx.x >> 5);
+  if (g >= nct) {
+    return;
+  }
+  const int p = g / G.n_cells;
+  const int s = g - p * G.n_cells;
+  const int c[3] = {s % G.ldims[0], (s / G.ldims[0]) % G.ldims[1], s / (G.ldims[0] * G.ldims[1])};
+  const uint32_t begin = __ldg(&cell_off[g]), end = __ldg(&cell_off[g + 1]);
+  if (begin == end) {
+    return;
+  }
+  const bool yz = G.dim == pm::DIM_YZ;
+  float* Rp = R + p * slot_len;
+  constexpr int nv = WHICH == PSC_B200_MOMENT_N ? 1 : (WHICH == PSC_B200_MOMENT_V || WHICH == PSC_B200_MOMENT_P) ? 3
+                     : WHICH == PSC_B200_MOMENT_T ? 6 : 13;
+  for (int comp = 0; comp < nv * n_kinds; comp++) {
+    const int ck = comp / nv, kk = comp - ck * nv; // kind, value of that kind
+    float acc[32];
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+      acc[t] = 0.f;
+    }
+    for (uint32_t i = begin + lane; i < end; i += 32) {
+      const float4 X = xi4[i];
+      const int kind = __float_as_int(X.w);
+      if (kind != ck) {
+        continue;
+      }
+      const float4 U = pxi4[i];
+      const float q = M.q[kind], ms = M.m[kind];
+      const float w = U.w / q; // const_accessor_simple.hxx:60-63
+      const float u[3] = {U.x, U.y, U.z};
+      const float x[3] = {X.x, X.y, X.z};
+      int l[3];
+      float h[3];
+      bool near = true;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const float xn = x[d] * G.pc.dxi[d];
+        l[d] = pm::fint(xn - .5f);
+        h[d] = xn - .5f - (float)l[d];
+        near = near && ((yz && d == 0) || l[d] == c[d] - 1 || l[d] == c[d]);
+      }
+      float vxi[3];
+      {
+        const float root = pm::rsqrt_ref(1.f + u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          vxi[d] = u[d] * root;
+        }
+      }
+      float val;
+      switch (WHICH) {
+        case PSC_B200_MOMENT_N: val = w; break;
+        case PSC_B200_MOMENT_V: val = w * (kk == 0 ? vxi[0] : kk == 1 ? vxi[1] : vxi[2]); break;
+        case PSC_B200_MOMENT_P: val = w * ms * (kk == 0 ? u[0] : kk == 1 ? u[1] : u[2]); break;
+        case PSC_B200_MOMENT_T: {
+          // (a, b) = (0,0) (1,1) (2,2) (0,1) (0,2) (1,2)
+          const float ua = kk == 0 || kk == 3 || kk == 4 ? u[0] : (kk == 1 || kk == 5 ? u[1] : u[2]);
+          const float vb = kk == 0 ? vxi[0] : (kk == 1 || kk == 3 ? vxi[1] : vxi[2]);
+          val = w * ms * ua * vb;
+          break;
+        }
+        default: { // PSC_B200_MOMENT_ALL: rho, j (3), p (3), t: (0,0) (1,1) (2,2) (0,1) (1,2) (2,0)
+          if (kk == 0) {
+            val = w * q;
+          } else if (kk < 4) {
+            val = w * q * (kk == 1 ? vxi[0] : kk == 2 ? vxi[1] : vxi[2]);
+          } else if (kk < 7) {
+            val = w * ms * (kk == 4 ? u[0] : kk == 5 ? u[1] : u[2]);
+          } else {
+            const int k6 = kk - 7;
+            const float ua = k6 == 0 || k6 == 3 ? u[0] : (k6 == 1 || k6 == 4 ? u[1] : u[2]);
+            const float vb = k6 == 0 || k6 == 5 ? vxi[0] : (k6 == 1 || k6 == 3 ? vxi[1] : vxi[2]);
+            val = w * ms * ua * vb;
+          }
+        }
+      }
+      const float value = M.fnqs * val;
+      if (!near) {
+        for (int cn = 0; cn < 8; cn++) {
+          const int ox = cn & 1, oy = (cn >> 1) & 1, oz = cn >> 2;
+          if (yz && ox) {
+            continue;
+          }
+          float wgt = value;
+          if (!yz) {
+            wgt = wgt * (ox ? h[0] : 1.f - h[0]);
+          }
+          wgt = wgt * (oy ? h[1] : 1.f - h[1]) * (oz ? h[2] : 1.f - h[2]);
+          atomicAdd(Rp + fld_off(G, comp, yz ? 0 : l[0] + ox, l[1] + oy, l[2] + oz), wgt);
+        }
+        continue;
+      }
+      // three weights per direction (the factor of a target the particle does not reach is never used)
+      float w3[3][3];
+      bool hit[3][3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const bool low = l[d] == c[d] - 1;
+        w3[d][0] = 1.f - h[d];
+        w3[d][1] = low ? h[d] : 1.f - h[d];
+        w3[d][2] = h[d];
+        hit[d][0] = low, hit[d][1] = true, hit[d][2] = !low;
+      }
+#pragma unroll
+      for (int t = 0; t < 27; t++) {
+        const int tx = t % 3, ty = (t / 3) % 3, tz = t / 9;
+        if (yz && tx != 1) {
+          continue;
+        }
+        const bool on = (yz || hit[0][tx]) && hit[1][ty] && hit[2][tz];
+        float wgt = value;
+        if (!yz) {
+          wgt = wgt * w3[0][tx];
+        }
+        wgt = wgt * w3[1][ty] * w3[2][tz];
+        acc[t] += on ? wgt : 0.f;
+      }
+    }
+    warp_transpose_reduce32(acc, lane);
+    if (lane < 27 && acc[0] != 0.f) {
+      const int tx = lane % 3, ty = (lane / 3) % 3, tz = lane / 9;
+      atomicAdd(Rp + fld_off(G, comp, yz ? 0 : c[0] + tx - 1, c[1] + ty - 1, c[2] + tz - 1), acc[0]);
+    }
+  }
+}
+
 // add_ghosts_reflecting.hxx:7-70, cell-centred, one (d, hi) at a time, all components
 __global__ void k_reflect_cc(GridDev G, float* __restrict__ R, long slot_len, int n_comps, int d, int hi,
                              const pm::PatchBnd* __restrict__ pbs)
@@ -1411,8 +1646,23 @@ int moment_1st(Ctx* c, int id, int which)
   }
   if (c->n_prts) {
     KernelScope ks(c, "moment_1st");
-    k_moment_1st<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(G, M, c->n_prts, c->d_off, c->xi(), c->pxi(),
-                                                                c->fld(id), c->fld_slot_len(id));
+    if (c->sorted && c->opt_cell_moments && which != PSC_B200_MOMENT_RHO_NC) {
+      const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+#define PSC_MOM_CELLS(W)                                                                           \
+  k_moment_1st_cells<W><<<div_up(nct, MOM_WARPS), MOM_WARPS * 32, 0, c->stream>>>(                 \
+    G, M, c->g.desc.n_kinds, nct, c->d_cell_off, c->xi(), c->pxi(), c->fld(id), c->fld_slot_len(id))
+      switch (which) {
+        case PSC_B200_MOMENT_N: PSC_MOM_CELLS(PSC_B200_MOMENT_N); break;
+        case PSC_B200_MOMENT_V: PSC_MOM_CELLS(PSC_B200_MOMENT_V); break;
+        case PSC_B200_MOMENT_P: PSC_MOM_CELLS(PSC_B200_MOMENT_P); break;
+        case PSC_B200_MOMENT_T: PSC_MOM_CELLS(PSC_B200_MOMENT_T); break;
+        default: PSC_MOM_CELLS(PSC_B200_MOMENT_ALL); break;
+      }
+#undef PSC_MOM_CELLS
+    } else {
+      k_moment_1st<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(G, M, c->n_prts, c->d_off, c->xi(), c->pxi(),
+                                                                  c->fld(id), c->fld_slot_len(id));
+    }
     c->n_launches++;
   }
   for (int hi = 0; hi < 2; hi++) {
@@ -1457,9 +1707,16 @@ int moment_rho_1st_nc(Ctx* c, int id)
   PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (c->n_prts) {
     KernelScope ks(c, "rho_1st_nc");
-    k_rho_1st_nc<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(
-      G, c->n_prts, c->d_off, c->xi(), c->pxi(), c->fld(id), c->fld_slot_len(id),
-      (float)c->g.desc.fnqs, c->scr[8].as<float>());
+    if (c->sorted && c->opt_cell_moments) {
+      const uint32_t nct = (uint32_t)G.n_cells * G.n_patches;
+      k_rho_1st_nc_cells<<<div_up(nct, RHO_WARPS), RHO_WARPS * 32, 0, c->stream>>>(
+        G, nct, c->d_cell_off, c->xi(), c->pxi(), c->fld(id), c->fld_slot_len(id), (float)c->g.desc.fnqs,
+        c->scr[8].as<float>());
+    } else {
+      k_rho_1st_nc<<<div_up(c->n_prts, 256), 256, 0, c->stream>>>(
+        G, c->n_prts, c->d_off, c->xi(), c->pxi(), c->fld(id), c->fld_slot_len(id),
+        (float)c->g.desc.fnqs, c->scr[8].as<float>());
+    }
     c->n_launches++;
   }
   // ItemMomentBnd::add_ghosts, fields_item.hxx:36-90

@@ -26,15 +26,21 @@ GRIDS = {
 MOMENTS = {"n": ol.MOM_N, "v": ol.MOM_V, "p": ol.MOM_P, "T": ol.MOM_T, "all": ol.MOM_ALL, "rho_nc": ol.MOM_RHO_NC}
 
 
+@pytest.mark.parametrize("store", ["unordered", "cell_ordered"])
 @pytest.mark.parametrize("mom", list(MOMENTS))
 @pytest.mark.parametrize("name", list(GRIDS))
-def test_moment_matches_oracle(name, mom):
+def test_moment_matches_oracle(name, mom, store):
+    """unordered store: one thread per particle, global atomics per value and corner; cell-ordered
+    store: one warp per cell, the sums of a cell in registers, one add per cell, target and component"""
     import psc_b200 as pb
     og = ol.Grid(dt=0.4, kinds=KINDS, nicell=6, **GRIDS[name])
     prts, off = thermal_plasma(og, ppc=5, seed=21, vth=(0.4, 0.03, 0.2))
     prts["qni_wni"] *= (0.5 + np.random.default_rng(3).random(len(prts))).astype(np.float32)  # weights != 1
     ref = ol.moment_1st(og, prts, off, MOMENTS[mom])
     grid, mprts, _ = gpu_state(og, None, prts, off)
+    if store == "cell_ordered":
+        pb.Sort()(mprts)
+    assert grid.get_stat("sorted") == (store == "cell_ordered")
     item = pb.Moment(grid, MOMENTS[mom])
     assert item.n_comps() == ref.shape[1]
     got = item(mprts).download()
@@ -48,13 +54,16 @@ def test_moment_matches_oracle(name, mom):
     grid.close()
 
 
+@pytest.mark.parametrize("store", ["unordered", "cell_ordered"])
 @pytest.mark.parametrize("dim", ["xyz", "yz"])
 @pytest.mark.parametrize("case", MOMENT_CASES, ids=[c["name"] for c in MOMENT_CASES])
-def test_moment_known_answers(case, dim):
+def test_moment_known_answers(case, dim, store):
     """test_moments.cxx: one particle of weight .4, nicell 200, dx 10"""
     import psc_b200 as pb
     og, prts, off = moment_case_grid(case, dim)
     grid, mprts, _ = gpu_state(og, None, prts, off)
+    if store == "cell_ordered":
+        pb.Sort()(mprts)
     got = moment_interior_comp0(og, pb.Moment(grid, case["which"])(mprts).download())
     exp = moment_case_expected(case, dim, og)
     assert np.abs(got - exp).max() < 1e-6
