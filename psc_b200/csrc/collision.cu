@@ -48,9 +48,16 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z)
   return z ^ (z >> 31);
 }
 
-__device__ __forceinline__ uint64_t coll_hash(uint64_t seed, uint64_t step, uint64_t cell, uint64_t k, uint64_t stream)
+// counter-based streams: one key per (seed, step, cell), then one mix per draw (k, stream)
+// (a splitmix64 sequence seeded by the cell key; 64-bit multiplies are 4 IMADs each, and a
+// four-deep hash per draw was 17 % of the kernel's instructions)
+__device__ __forceinline__ uint64_t coll_cell_key(uint64_t seed, uint64_t step, uint64_t cell)
 {
-  return mix64(seed ^ mix64(step ^ mix64(cell ^ mix64(2 * k + stream))));
+  return mix64(seed ^ mix64(step ^ mix64(cell)));
+}
+__device__ __forceinline__ uint64_t coll_hash(uint64_t cell_key, uint64_t k, uint64_t stream)
+{
+  return mix64(cell_key ^ (2 * k + stream));
 }
 
 // ]0, 1] with 24 random bits (RngC::uniform's range, binary_collision.hxx:13-28)
@@ -211,13 +218,13 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
   const int my_nn = g0 + lane < nct ? (int)(__ldg(&cell_off[my_g + 1]) - my_cb) : 0;
   unsigned long long my_coll = 0;
 
-  // one binary collision between records a and b (indices into the store) of global cell gcell
+  // one binary collision between records a and b (indices into the store); gcell: the cell's stream key
   auto do_bc = [&](uint32_t a, uint32_t b, float nudt1, uint64_t gcell, uint64_t s0, uint64_t j) {
     float4 ua = pxi4[a], ub = pxi4[b];
     const int ka = __float_as_int(xi4[a].w), kb = __float_as_int(xi4[b].w);
     float u1[3] = {ua.x, ua.y, ua.z}, u2[3] = {ub.x, ub.y, ub.z};
-    const float r1 = P.rng ? coll_u01(coll_hash(P.seed, P.step, gcell, s0 + j, 1)) : .5f;
-    const float r2 = P.rng ? coll_u01(coll_hash(P.seed, P.step, gcell, s0 + j, 2)) : .5f;
+    const float r1 = P.rng ? coll_u01(coll_hash(gcell, s0 + j, 1)) : .5f;
+    const float r2 = P.rng ? coll_u01(coll_hash(gcell, s0 + j, 2)) : .5f;
     binary_collision(u1, u2, P.q[ka], P.m[ka], P.q[kb], P.m[kb], nudt1, r1, r2);
     pxi4[a] = make_float4(u1[0], u1[1], u1[2], ua.w);
     pxi4[b] = make_float4(u2[0], u2[1], u2[2], ub.w);
@@ -232,11 +239,11 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
 
   // ---- small cells: one cell per lane
   if (my_nn >= 2 && my_nn <= COLL_SMALL) {
-    const uint64_t gcell = P.cell0 + my_g;
+    const uint64_t gcell = coll_cell_key(P.seed, P.step, P.cell0 + my_g);
     uint64_t* const k8 = sk + lane * COLL_SMALL; // this lane's keys
     for (int i = 0; i < my_nn; i++) {
       // insertion sort of the composite keys (random 40 bits, index)
-      const uint64_t key = P.rng ? (((coll_hash(P.seed, P.step, gcell, (uint64_t)i, 0) >> 24) << 24) | (uint64_t)i)
+      const uint64_t key = P.rng ? (((coll_hash(gcell, (uint64_t)i, 0) >> 24) << 24) | (uint64_t)i)
                                  : (uint64_t)i;
       int j = i;
       while (j > 0 && k8[j - 1] > key) {
@@ -264,14 +271,110 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
   }
   __syncwarp();
 
-  // ---- the other cells, one after the other, by the whole warp
+  // ---- the other cells, by the whole warp.  Two at a time when both fit half the key buffer:
+  // the three collisions of an odd population's triangle depend on each other and hold their
+  // lane for three rounds, and a cell alone has nothing for the other 31 lanes to do meanwhile
+  // (profile: 11.8 of 32 lanes active in the collision proper); with two cells in flight every
+  // round is "one binary collision per lane" -- triangle lanes do their next step, the free
+  // lanes take the next pairs of either cell from one pool.
+  auto sort_keys = [&](uint64_t* k_, int m, uint64_t gcell, int& m2) {
+    m2 = 2;
+    while (m2 < m) {
+      m2 <<= 1;
+    }
+    for (int i = lane; i < m2; i += 32) {
+      uint64_t key = ~0ull; // padding sorts to the end
+      if (i < m) {
+        key = P.rng ? (((coll_hash(gcell, (uint64_t)i, 0) >> 24) << 24) | (uint64_t)i) : (uint64_t)i;
+      }
+      k_[i] = key;
+    }
+    __syncwarp();
+    if (P.rng) {
+      for (int k = 2; k <= m2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < (m2 >> 1); t += 32) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int l = i | j;
+            const bool up = (i & k) == 0;
+            const uint64_t a = k_[i], b = k_[l];
+            if ((a > b) == up) {
+              k_[i] = b;
+              k_[l] = a;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  };
   unsigned big = __ballot_sync(FULL, my_nn > COLL_SMALL);
   while (big) {
     const int src = __ffs(big) - 1;
     big &= big - 1;
     const uint32_t cb = __shfl_sync(FULL, my_cb, src);
     const int nn = __shfl_sync(FULL, my_nn, src);
-    const uint64_t gcell = P.cell0 + g0 + (uint32_t)src;
+    const uint64_t gcell = coll_cell_key(P.seed, P.step, P.cell0 + g0 + (uint32_t)src);
+    if (big && nn <= COLL_CAP / 2 && __shfl_sync(FULL, my_nn, __ffs(big) - 1) <= COLL_CAP / 2) {
+      const int srcB = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t cbB = __shfl_sync(FULL, my_cb, srcB);
+      const int nnB = __shfl_sync(FULL, my_nn, srcB);
+      const uint64_t gcellB = coll_cell_key(P.seed, P.step, P.cell0 + g0 + (uint32_t)srcB);
+      uint64_t* const skB = sk + COLL_CAP / 2;
+      int m2;
+      sort_keys(sk, nn, gcell, m2);
+      sort_keys(skB, nnB, gcellB, m2);
+      const float nudtA = nudt1_of(cb + (uint32_t)(sk[0] & 0xffffffu), nn);
+      const float nudtB = nudt1_of(cbB + (uint32_t)(skB[0] & 0xffffffu), nnB);
+      const int firstA = (nn & 1) ? 3 : 0, firstB = (nnB & 1) ? 3 : 0;
+      const int pairsA = (nn - firstA) >> 1, pairsB = (nnB - firstB) >> 1;
+      // lane 0 / lane 1 own the triangles (steps 0..2), everybody else (and they, afterwards) the pool
+      int tri = (lane == 0 && firstA) || (lane == 1 && firstB) ? 0 : 3;
+      int next = 0;
+      const int total = pairsA + pairsB;
+      for (;;) {
+        const bool busy = tri < 3;
+        const unsigned fm = __ballot_sync(FULL, !busy);
+        if (!__any_sync(FULL, busy) && next >= total) {
+          break;
+        }
+        // (one call site for both kinds of work: the lanes run the collision together)
+        bool act = busy, isA = lane == 0;
+        int n = 0, j = tri;
+        if (!busy) {
+          const int idx = next + __popc(fm & ((1u << lane) - 1u));
+          act = idx < total;
+          isA = idx < pairsA;
+          const int tp = isA ? idx : idx - pairsA;
+          const int first = isA ? firstA : firstB;
+          n = first + 2 * tp;
+          j = first + tp;
+        }
+        if (act) {
+          const uint64_t* const k_ = isA ? sk : skB;
+          const uint32_t b0 = isA ? cb : cbB;
+          uint32_t pa, pb;
+          float nudt = isA ? nudtA : nudtB;
+          if (busy) {
+            // triangle step tri: (p0, p1), (p0, p2), (p1, p2) at half the frequency (:235-240)
+            const uint32_t p0 = b0 + (uint32_t)(k_[0] & 0xffffffu), p1 = b0 + (uint32_t)(k_[1] & 0xffffffu),
+                           p2 = b0 + (uint32_t)(k_[2] & 0xffffffu);
+            pa = tri == 2 ? p1 : p0, pb = tri == 0 ? p1 : p2;
+            nudt = (float)(.5 * (double)nudt);
+          } else {
+            pa = b0 + (uint32_t)(k_[n] & 0xffffffu), pb = b0 + (uint32_t)(k_[n + 1] & 0xffffffu);
+          }
+          do_bc(pa, pb, nudt, isA ? gcell : gcellB, 0, (uint64_t)j);
+        }
+        if (busy) {
+          tri++;
+        }
+        next += __popc(fm);
+      }
+      __syncwarp();
+      continue;
+    }
     for (int s0 = 0; s0 < nn; s0 += COLL_CAP) {
       const int m = min(COLL_CAP, nn - s0);
       if (m < 2) {
@@ -285,7 +388,7 @@ __global__ void __launch_bounds__(COLL_WARPS * 32)
       for (int i = lane; i < m2; i += 32) {
         uint64_t key = ~0ull; // padding sorts to the end
         if (i < m) {
-          key = P.rng ? (((coll_hash(P.seed, P.step, gcell, (uint64_t)(s0 + i), 0) >> 24) << 24) | (uint64_t)i)
+          key = P.rng ? (((coll_hash(gcell, (uint64_t)(s0 + i), 0) >> 24) << 24) | (uint64_t)i)
                       : (uint64_t)i;
         }
         sk[i] = key;
@@ -468,10 +571,11 @@ __global__ void k_heating(HeatPrm P, int n_patches, uint32_t n, const uint32_t* 
     const double Hd = heating_H(P, xx, kind);
     if (Hd > 0.f) {
       const float H = (float)Hd;
+      const uint64_t pkey = mix64(P.seed ^ mix64(P.step ^ mix64((uint64_t)gp))); // one key per (seed, step, patch)
       float ran[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) {
-        const uint64_t h = mix64(P.seed ^ mix64(P.step ^ mix64((uint64_t)gp ^ mix64(((uint64_t)(i - off[p]) << 3) | (uint64_t)k))));
+        const uint64_t h = mix64(pkey ^ (((uint64_t)(i - off[p]) << 3) | (uint64_t)k));
         ran[k] = (float)(h >> 40) * (1.f / 16777216.f);
       }
       const float ranx = sqrtf(-2.f * logf((float)(1.0 - ran[0]))) * cosf((float)(2.f * M_PI * ran[1]));
