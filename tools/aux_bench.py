@@ -49,7 +49,7 @@ def main():
     peak = None
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak = float(peak.get("hbm_gbps_burst") or peak.get("hbm_gbps") or 0) or None
+        peak = float(peak.get("hbm_gbs") or peak.get("hbm_gb_s") or 0) or None
     except Exception:
         pass
     peak = peak or 6445.3
