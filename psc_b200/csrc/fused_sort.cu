@@ -152,6 +152,64 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, cnt_t* 
   }
 }
 
+// fs_route for the same-patch route (t = 0) of k_fs_offsets_same: every thread runs it, so
+// it is written for registers -- one base pointer, validity from six per-direction tests,
+// and the 27 loaded counts kept two per register (they are 16-bit): the general routine
+// above spilled 176 bytes per thread at the kernel's 64 registers
+template <bool CENTER_INFO, typename IDX>
+__device__ __forceinline__ void fs_route_same(const GridDev& G, uint32_t nct, cnt_t* __restrict__ cnt, int q,
+                                              int c0, int c1, int c2, uint32_t& total, uint32_t* n_lower,
+                                              uint32_t* n_center)
+{
+  static_assert(sizeof(cnt_t) == 2, "two counts per register");
+  const int ld0 = G.ldims[0], ld1 = G.ldims[1], ld2 = G.ldims[2];
+  // element index of the target cell + a warp-uniform offset per plane (IDX: 32 bits while
+  // 27 nct < 2^32, chosen by the host), so that no 64-bit address is kept
+  const IDX s1 = ld0, s2 = (IDX)ld0 * ld1;
+  IDX b = (IDX)q * G.n_cells + (IDX)((c2 * ld1 + c1) * ld0 + c0);
+  // source coordinate c_d - e_d inside the patch, for e_d = +1 (lo) and -1 (hi)
+  const bool lo0 = c0 >= 1, hi0 = c0 + 1 < ld0, lo1 = c1 >= 1, hi1 = c1 + 1 < ld1, lo2 = c2 >= 1, hi2 = c2 + 1 < ld2;
+  auto valid = [&](int e0, int e1, int e2) {
+    return (e0 == 1 ? lo0 : (e0 == -1 ? hi0 : true)) && (e1 == 1 ? lo1 : (e1 == -1 ? hi1 : true)) &&
+           (e2 == 1 ? lo2 : (e2 == -1 ? hi2 : true));
+  };
+  uint32_t np[14];
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    // k ascending = delta descending
+    const int e2 = 1 - k / 9, e1 = 1 - (k / 3) % 3, e0 = 1 - k % 3;
+    uint32_t v = 0;
+    if (valid(e0, e1, e2)) {
+      v = cnt[b + ((IDX)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct - (e2 * s2 + e1 * s1 + e0))];
+    }
+    if (k & 1) {
+      np[k >> 1] |= v << 16;
+    } else {
+      np[k >> 1] = v;
+    }
+  }
+  // (the store addresses are re-derived from b: kept from the loads they would be 54 registers)
+  if constexpr (sizeof(IDX) == 4) {
+    asm volatile("" : "+r"(b));
+  } else {
+    asm volatile("" : "+l"(b));
+  }
+#pragma unroll
+  for (int k = 0; k < 27; k++) {
+    const int e2 = 1 - k / 9, e1 = 1 - (k / 3) % 3, e0 = 1 - k % 3;
+    if (valid(e0, e1, e2)) {
+      const uint32_t n = (k & 1) ? np[k >> 1] >> 16 : np[k >> 1] & 0xffffu;
+      // (a target cell beyond CNT_MAX is flagged by the caller)
+      cnt[b + ((IDX)(((e2 + 1) * 3 + e1 + 1) * 3 + e0 + 1) * nct - (e2 * s2 + e1 * s1 + e0))] = (cnt_t)total;
+      if (CENTER_INFO && k == 13) {
+        *n_lower = total;
+        *n_center = n;
+      }
+      total += n;
+    }
+  }
+}
+
 // per target cell: offsets of its contributions in the reference's order; cnt is
 // rewritten in place (every (source cell, delta) entry has exactly one target).
 // Class order: stayers first, then the receiver's direction loop dir' ascending; the
@@ -163,8 +221,11 @@ __device__ __forceinline__ void fs_route(const GridDev& G, uint32_t nct, cnt_t* 
 // only (one thread per face cell; the face slabs are enumerated z, y, x and a cell that
 // lies in several is taken by the first).
 // STAY (pull mode): also emit, per target cell, {arrivals placed in front of its stayers, stayers}
-template <bool STAY>
-__global__ void __launch_bounds__(256, 4)
+#ifndef OFFS_MINB
+#define OFFS_MINB 4 // CTAs per SM (56 registers, none spilled)
+#endif
+template <bool STAY, typename IDX>
+__global__ void __launch_bounds__(256, OFFS_MINB)
   k_fs_offsets_same(GridDev G, uint32_t nct, cnt_t* __restrict__ cnt, uint32_t* __restrict__ new_cnt,
                     uint32_t* __restrict__ flags, uint2* __restrict__ stay)
 {
@@ -179,10 +240,10 @@ __global__ void __launch_bounds__(256, 4)
   uint32_t total = 0;
   if constexpr (STAY) {
     uint32_t nl = 0, nc = 0;
-    fs_route<true>(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total, &nl, &nc);
+    fs_route_same<true, IDX>(G, nct, cnt, q, c0, c1, c2, total, &nl, &nc);
     stay[g] = make_uint2(nl, nc);
   } else {
-    fs_route(G, nct, cnt, q, c0, c1, c2, 0, 0, 0, total);
+    fs_route_same<false, IDX>(G, nct, cnt, q, c0, c1, c2, total, nullptr, nullptr);
   }
   new_cnt[g] = total;
   if (total > CNT_MAX) {
@@ -807,12 +868,14 @@ int fused_bnd_sort(Ctx* c, bool defer)
   c->counts_valid = false;
   {
     KernelScope ks(c, "fsort_offsets");
+    const bool idx32 = 27ull * nct < (1ull << 32);
     if (pull) {
       PSC_TRY(c->scr[13].reserve((size_t)nct * sizeof(uint2)));
-      k_fs_offsets_same<true><<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags,
-                                                                       c->scr[13].as<uint2>());
+      auto k = idx32 ? k_fs_offsets_same<true, uint32_t> : k_fs_offsets_same<true, unsigned long long>;
+      k<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags, c->scr[13].as<uint2>());
     } else {
-      k_fs_offsets_same<false><<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags, nullptr);
+      auto k = idx32 ? k_fs_offsets_same<false, uint32_t> : k_fs_offsets_same<false, unsigned long long>;
+      k<<<div_up(nct, 256), 256, 0, c->stream>>>(G, nct, cnt, new_cnt, flags, nullptr);
     }
     // faces towards a direction in which some patch has a neighbour (none along an
     // invariant direction: Grid_ / MrcDomain)
