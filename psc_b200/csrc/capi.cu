@@ -600,12 +600,13 @@ static int step_begin(Ctx* c, const psc_b200_step_params* prm)
   }
   std::swap(c->stream, c->stream2);
   PSC_TRY(rc);
-  // ... particles on stream (:412 + :356 of the next step); single rank: enqueued only
+  // ... particles on stream (:412 + :356 of the next step): enqueued only (multi-rank: up to
+  // and including the exchange of the leavers on the host's clock, the scatter enqueued)
   c->step_pending = true;
   const uint32_t nct = (uint32_t)c->gd.n_cells * c->gd.n_patches;
   c->want_scatter_energies = prm->energies != 0;
   c->scatter_energies_done = false;
-  rc = fused_bnd_sort(c, /*defer=*/c->comm == nullptr);
+  rc = fused_bnd_sort(c, /*defer=*/true);
   c->want_scatter_energies = false;
   PSC_TRY(rc);
   if (prm->energies && c->scatter_energies_done) {

@@ -154,6 +154,8 @@ struct Ctx
   bool fs_deferred = false;      // ... and its flags / new offsets have not been read back yet
   uint32_t* fs_host = nullptr;   // pinned landing zone of that read-back
   size_t fs_host_bytes = 0;
+  uint32_t fs_n_expected = 0;    // particle count the deferred commit must find (multi-rank: after the exchange)
+  bool fs_multi = false;
   double* en_host = nullptr;     // pinned: DiagEnergies of the last step that asked for them
   bool en_valid = false;
   bool want_scatter_energies = false;  // ask the next fused scatter to reduce the particle energies ...

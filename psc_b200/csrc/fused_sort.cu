@@ -828,11 +828,13 @@ int fused_bnd_sort_finish(Ctx* c)
   c->fs_deferred = false;
   PSC_CUDA_TRY(cudaStreamSynchronize(c->stream));
   PSC_TRY(check_launch(c, "fused_bnd_sort"));
-  return fused_commit(c, c->fs_host, c->n_prts, false);
+  return fused_commit(c, c->fs_host, c->fs_n_expected, c->fs_multi);
 }
 
-// defer: single rank only -- enqueue everything, leave the read-back of the flags / new patch
-// offsets (and with it the host's wait for the scatter) to fused_bnd_sort_finish()
+// defer: enqueue everything, leave the read-back of the flags / new patch offsets (and with it
+// the host's wait for the scatter) to fused_bnd_sort_finish().  Multi-rank: the host still waits
+// for the push and the exchange of the leavers in here (their counts size the transfers); what is
+// deferred is the scatter behind them
 int fused_bnd_sort(Ctx* c, bool defer)
 {
   const GridDev& G = c->gd;
@@ -1015,7 +1017,7 @@ int fused_bnd_sort(Ctx* c, bool defer)
                                                                d_new_off);
   }
   c->n_launches += 1;
-  if (defer && !multi) {
+  if (defer) {
     const size_t need = (size_t)(np + 1 + 4) * sizeof(uint32_t);
     if (c->fs_host_bytes < need) {
       if (c->fs_host) {
@@ -1027,6 +1029,8 @@ int fused_bnd_sort(Ctx* c, bool defer)
     }
     PSC_CUDA_TRY(cudaMemcpyAsync(c->fs_host, flags, need, cudaMemcpyDeviceToHost, c->stream));
     c->fs_deferred = true;
+    c->fs_n_expected = n_expected;
+    c->fs_multi = multi;
     return 0;
   }
   std::vector<uint32_t> h(np + 1 + 4);

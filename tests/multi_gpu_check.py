@@ -8,6 +8,7 @@ ranks' particles and fields and compares them with the CPU oracle run on the who
 domain with the same rank map (remote arrivals are appended behind local ones:
 ddc_particles.hxx:456-468).  Run by tests/test_gpu_multi.py when >= 2 GPUs are visible
 and by hand under `gpurun --gpus 2`."""
+import ctypes as C
 import os
 import sys
 
@@ -42,6 +43,7 @@ def bench_parity_cases(rank, world, local_rank):
     uneven = [npg - small * (world - 1)] + [small] * (world - 1)
     todo = [("xyz_periodic_slabs", dict(fused=True, n_steps=1)), ("xyz_periodic_slabs", dict(fused=True)),
             ("xyz_wall_z", dict(fused=True)), ("yz_periodic", dict(fused=True, n_steps=1))]
+    todo.append(("xyz_periodic_slabs", dict(fused=True, pipelined=True)))
     if uneven:
         todo.append(("xyz_periodic_slabs", dict(fused=True, n_steps=4, n_by_rank=uneven, balance_step=0)))
     for name, kw in todo:
@@ -68,7 +70,7 @@ FALLBACK_CASE = dict(gdims=(16, 16, 32), length=(16., 16., 8.), np_=(2, 2, 4))
 
 
 def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None, balance_step=None,
-             want_info=False, vth=(0.5, 0.05), hot_particle=False):
+             want_info=False, vth=(0.5, 0.05), hot_particle=False, pipelined=False):
     og = ol.Grid(dt=0.35, kinds=KINDS, nicell=8, **gkw)
     npg = og.n_patches
     if n_by_rank is None:
@@ -120,7 +122,20 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
         L.po_push_H(G, ol.ptr(rf), .5)
         L.po_bndf_fill_ghosts_H(G, ol.ptr(rf))
         L.po_fill_ghosts(G, ol.ptr(rf), 9, 6, 9)
-        psc.step()
+        if pipelined:
+            # the step through psc_b200_step_begin / _step_end (pipelined host I/O): J comes down
+            # while the exchange's scatter is still running, DiagEnergies are reduced inside
+            prm = pb.StepParams(sort=1, marder_loop=0, marder_diffusion=0., push_fields=1, checks=0, energies=1)
+            h_j = np.zeros(mflds.shape(3), dtype=np.float32)
+            pb.check(grid.lib.psc_b200_step_begin(grid.ctx, C.byref(prm)))
+            pb.check(grid.lib.psc_b200_mflds_download_async(grid.ctx, 0, pb.JXI, pb.JXI + 3,
+                                                           h_j.ctypes.data_as(C.c_void_p)))
+            pb.check(grid.lib.psc_b200_io_wait(grid.ctx))
+            pb.check(grid.lib.psc_b200_step_end(grid.ctx))
+            en_in_step = np.zeros(8)
+            pb.check(grid.lib.psc_b200_last_energies(grid.ctx, en_in_step.ctypes.data_as(C.c_void_p)))
+        else:
+            psc.step()
         if balance_step is not None and _ == balance_step:
             # Balance::operator(): loads -> best_mapping -> whole patches move between GPUs
             loads = (np.diff(ro) + 1.0 * og.n_cells).astype(np.float64)
@@ -143,10 +158,19 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
     gp, go = mprts.get()
     gf = mflds.download()
     en = pb.energies(grid)
+    if pipelined:
+        # J as it came down (interior + ghosts of this rank's patches) against the device's copy,
+        # and the energies of the last step as reduced inside it
+        j_dev = mflds.download(pb.JXI, pb.JXI + 3)
+        assert np.array_equal(h_j, j_dev), "J downloaded inside the step differs from the device's"
     stats = dict(fused=grid.get_stat("fused_steps"), fallbacks=grid.get_stat("fused_fallbacks"))
-    res = gather_obj((gp, go, gf, stats), rank, world)
+    res = gather_obj((gp, go, gf, stats, en_in_step if pipelined else None), rank, world)
     ok = True
     info = None
+    if rank == 0 and pipelined:
+        # (psc_b200_last_energies is this rank's share; psc_b200_energies reduces over the ranks)
+        en_sum = np.sum([r[4] for r in res], axis=0)
+        ok = ok and bool(np.allclose(en_sum, en, rtol=1e-5, atol=1e-30))
     if rank == 0:
         counts = np.concatenate([np.diff(r[1]) for r in res])
         ref_counts = np.diff(ro)
@@ -160,7 +184,7 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
             uerr = float(np.abs(all_p["u"] - rp["u"]).max())
         ref_e = ol.energies(og, rf, rp, ro)
         eerr = float(np.abs(en - ref_e).max() / np.abs(ref_e).max())
-        ok = same_counts and ferr < 3e-5 and perr < 1e-4 and uerr < 1e-5 and eerr < 1e-4
+        ok = ok and same_counts and ferr < 3e-5 and perr < 1e-4 and uerr < 1e-5 and eerr < 1e-4
         # per-cell counts and the migration order are exact.  After ONE step the particle records
         # are byte-identical to the oracle's (same fields in, same arithmetic, same order); over
         # several steps x/u carry the round-off of J's summation order through E
@@ -171,7 +195,7 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
             ok = ok and res[0][3]["fallbacks"] >= 1 and all(r[3]["fallbacks"] == 0 for r in res[1:])
         info = dict(name=name, fused=int(fused), steps=n_steps, ranks=world, counts_equal=bool(same_counts),
                     particles_byte_exact=bytes_equal, fld_rel=float(ferr), x_abs=perr, u_abs=uerr,
-                    energies_rel=eerr, balanced=balance_step is not None, ok=bool(ok))
+                    energies_rel=eerr, balanced=balance_step is not None, pipelined=bool(pipelined), ok=bool(ok))
         print("%-28s fused=%d  counts %s  fld rel %.2e  x abs %.2e  u abs %.2e  energies rel %.2e  %s  %s" % (
             name, fused, "same" if same_counts else "DIFFER", ferr, perr, uerr, eerr,
             [r[3] for r in res], "ok" if ok else "FAIL"), flush=True)
@@ -192,6 +216,11 @@ def main():
         for fused in (False, True):
             ok = run_case(name, kw, rank, world, local_rank, fused) and ok
             ok = run_case(name + "_1step", kw, rank, world, local_rank, fused, n_steps=1) and ok
+    # the pipelined step (step_begin / step_end: the scatter behind the exchange is deferred)
+    for name in ("xyz_periodic_slabs", "xyz_wall_z", "yz_periodic"):
+        ok = run_case(name + "_pipelined", cases[name], rank, world, local_rank, True, pipelined=True) and ok
+        ok = run_case(name + "_pipelined_1step", cases[name], rank, world, local_rank, True, n_steps=1,
+                      pipelined=True) and ok
     # uneven patch distribution (what the balancer produces)
     npg = 16
     small = 3 if world <= 4 else 1
