@@ -270,13 +270,19 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           }
         }
       }
+      // The leaves of a cell-crossing trajectory go to the global J directly (red.global.add,
+      // fire and forget).  Into the shared tile they are float compare-and-swap loops
+      // (ATOMS.CAST.SPIN), twelve per leaf one after the other, and the 32 trajectories of a walk
+      // come from neighbouring cells, so the loops also retry: those loops were the largest
+      // single source of stall samples in the kernel (profiles/r02_push_lean_ncu.txt) for 3 % of
+      // the particles.  The J tile of the CTA is in L2 while the CTA runs; S3D push 17.58 -> 17.08 ms
       more = w.first(G.pc, t, qw, ci, val);
-      leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+      leaf_to_global<DIM>(G, F, ci, val);
     }
     while (__any_sync(FULL, more)) {
       if (more) {
         more = w.next(G.pc, qw, ci, val);
-        leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+        leaf_to_global<DIM>(G, F, ci, val);
       }
     }
     qn -= cnt;

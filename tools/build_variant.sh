@@ -9,5 +9,5 @@ FL="-gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler 
 nvcc $FL -fmad=false -DPUSH_VARIANT=exact $EXTRA -Xptxas -v -c push.cu -o $B/push_exact.o 2> $B/exact.log &
 nvcc $FL -fmad=true -DPUSH_VARIANT=fast $EXTRA -c push.cu -o $B/push_fast.o 2> $B/fast.log &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpsc_b200_$NAME.so build/capi.o build/particles.o $B/push_exact.o $B/push_fast.o build/sort.o build/bndp.o build/fields.o build/comm.o build/fused_sort.o -ldl
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libpsc_b200_$NAME.so build/capi.o build/particles.o $B/push_exact.o $B/push_fast.o build/sort.o build/bndp.o build/fields.o build/comm.o build/fused_sort.o build/collision.o build/checkpoint.o -ldl
 grep -A2 "Function properties for _ZN8psc_b2005exact12k_push_tiledILi0ELi1ENS0_9GeoStaticILi0EEELb1ELb1ELi256ELi3" $B/exact.log | tail -2
