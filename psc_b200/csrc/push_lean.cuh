@@ -277,12 +277,20 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
       // single source of stall samples in the kernel (profiles/r02_push_lean_ncu.txt) for 3 % of
       // the particles.  The J tile of the CTA is in L2 while the CTA runs; S3D push 17.58 -> 17.08 ms
       more = w.first(G.pc, t, qw, ci, val);
+#ifdef LEAN_DRAIN_SHARED // (A/B: tools/build_variant.sh)
+      leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+#else
       leaf_to_global<DIM>(G, F, ci, val);
+#endif
     }
     while (__any_sync(FULL, more)) {
       if (more) {
         more = w.next(G.pc, qw, ci, val);
+#ifdef LEAN_DRAIN_SHARED
+        leaf_deposit<DIM>(G, geo, sJ, F, n0, n1, n2, ci, val);
+#else
         leaf_to_global<DIM>(G, F, ci, val);
+#endif
       }
     }
     qn -= cnt;
