@@ -1060,6 +1060,7 @@ int psc_b200_get_stat(psc_b200_ctx* ctx, const char* name, double* value)
     else if (n == "capacity") { *value = (double)c->cap; }
     else if (n == "n_slots") { *value = c->n_slots; }
     else if (n == "fused_steps") { *value = (double)c->n_fused; }
+    else if (n == "lean_pushes") { *value = (double)c->n_lean; }
     else if (n == "gap_steps") { *value = (double)c->n_gap_steps; }
     else if (n == "gap_relayouts") { *value = (double)c->n_gap_relayouts; }
     else if (n == "gap_redone") { *value = (double)c->n_gap_redone; }

@@ -156,6 +156,7 @@ struct Ctx
   size_t fs_host_bytes = 0;
   uint32_t fs_n_expected = 0;    // particle count the deferred commit must find (multi-rank: after the exchange)
   bool fs_multi = false;
+  uint64_t n_lean = 0;           // pushes that ran k_push_lean (stat "lean_pushes")
   double* en_host = nullptr;     // pinned: DiagEnergies of the last step that asked for them
   bool en_valid = false;
   bool want_scatter_energies = false;  // ask the next fused scatter to reduce the particle energies ...

@@ -92,9 +92,9 @@ struct GeoStatic
   int nt_[3];
   static constexpr bool XYZ = DIM == pm::DIM_XYZ;
 #ifndef PUSH_TILE_X
-#define PUSH_TILE_X 8
-#define PUSH_TILE_Y 8
-#define PUSH_TILE_Z 8
+#define PUSH_TILE_X 16
+#define PUSH_TILE_Y 4
+#define PUSH_TILE_Z 4
 #endif
   __host__ __device__ static constexpr int t(int d)
   {
@@ -1096,9 +1096,12 @@ static int launch_lean(Ctx* c, const GeoStatic<DIM>& geo, bool count, PushArgs A
 #else
   const int W = c->opt_lean >= 2 ? 2 : 1;
 #endif
-  const size_t smem_bytes = (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
-                            (size_t)(W == 1 ? lean::n_warps<1>() : lean::n_warps<2>()) *
-                              ((W == 1 ? lean::qcap<1>() : lean::qcap<2>()) * 2 + 64 * W) * sizeof(float4);
+  // tiles + per-warp queue + staging (W = 1: the ring of n_stages chunks and its alignment slack)
+  const size_t ring = (size_t)lean::n_stages<DIM>() * lean::STAGE_BYTES;
+  const size_t smem_bytes =
+    (size_t)((9 * geo.sm() + 3) & ~3) * sizeof(float) +
+    (W == 1 ? (size_t)lean::n_warps<1>() * (lean::qcap<1>() * 2 * sizeof(float4) + ring) + ring
+            : (size_t)lean::n_warps<2>() * (lean::qcap<2>() * 2 + 64 * W) * sizeof(float4));
   TensorMap128 tm128;
   const int box[4] = {XYZ ? geo.f(0) : geo.f(1), XYZ ? geo.f(1) : geo.f(2), XYZ ? geo.f(2) : 6, 6};
   PSC_TRY(field_tile_tensor_map(c, 0, XYZ ? 4 : 3, box, &tm128));
@@ -1339,6 +1342,7 @@ static int push_dim(Ctx* c, bool gap)
     if (lean_ok) {
       KernelScope ks(c, "push_lean");
       rc = launch_lean<DIM, DEPOSIT>(c, gs, count, A);
+      c->n_lean += rc == 0;
     }
     if (rc == -1 && stat) {
       // bulk copies: contiguous rows (x in 3D, y in yz) must be 16-byte aligned

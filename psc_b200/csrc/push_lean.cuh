@@ -43,6 +43,19 @@ __host__ __device__ constexpr int n_warps()
   return W == 1 ? 8 : 8;
 #endif
 }
+// chunks in flight per warp (W = 1): the records travel global -> shared with cp.async that many
+// chunks ahead of the one being computed.  One ahead left every chunk waiting for its records
+// (the cp.async wait was the largest stall site of the kernel: a chunk takes a warp ~3600 cycles,
+// about the loaded memory latency); the yz kernel has fewer instructions per chunk and more
+// shared memory to spare, so it runs further ahead.  S3D push 17.1 -> 16.4 ms, yz 24.6 -> 20.6 ms
+template <int DIM>
+__host__ __device__ constexpr int n_stages()
+{
+  return DIM == pm::DIM_XYZ ? 2 : 4;
+}
+// bytes of staging per warp and stage: 32 x (xi4, pxi4)
+constexpr uint32_t STAGE_BYTES = 1024;
+
 // queue entries per warp: a chunk (32 W particles) must always fit behind what a walk leaves
 template <int W>
 __host__ __device__ constexpr int qcap()
@@ -184,7 +197,13 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
 
   FldTile<GeoStatic<DIM>> EM{sEM, geo, n0, n1, n2};
   float4* const myQ = sQ + warp * QC * 2;
-  const uint32_t myP = smem_u32(sP + warp * 64 * W + lane);
+  // W = 1: NST stages of 1 KB per warp, the block aligned to its size so that the stage is a
+  // bit field of the address (W = 2 keeps one stage of two chunks)
+  constexpr int NST = n_stages<DIM>();
+  constexpr uint32_t RING = NST * STAGE_BYTES;
+  uint32_t myP = W == 1 ? ((smem_u32(sP) + (RING - 1)) & ~(RING - 1)) + (uint32_t)warp * RING + (uint32_t)lane * 16u
+                        : smem_u32(sP + warp * 64 * W + lane);
+  constexpr uint32_t PSTRIDE = 32 * sizeof(float4); // xi4 -> pxi4 inside a stage
   int qn = 0; // queued trajectories of this warp (warp-uniform)
 
   // what this lane deposits when a cell is flushed: its slot of the leaf, scaled
@@ -344,11 +363,16 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
         }
       };
       // the next chunk travels global -> shared with cp.async while this one is computed
-      if (begin + lane < end) {
-        cp_async16(myP, A.xi4 + begin + lane);
-        cp_async16(myP + 32 * sizeof(float4), A.pxi4 + begin + lane);
+#pragma unroll
+      for (int k = 0; k < NST; k++) {
+        // chunk k of the row into stage (current + k) of the ring, one commit group per chunk
+        const uint32_t dst = (myP & ~(RING - 1)) | ((myP + k * STAGE_BYTES) & (RING - 1));
+        if (begin + 32 * k + lane < end) {
+          cp_async16(dst, A.xi4 + begin + 32 * k + lane);
+          cp_async16(dst + PSTRIDE, A.pxi4 + begin + 32 * k + lane);
+        }
+        cp_async_commit();
       }
-      cp_async_commit();
       uint32_t base = begin;
       do {
         const uint32_t i = base + lane;
@@ -360,13 +384,15 @@ __global__ void __launch_bounds__(n_warps<W>() * 32, W == 1 ? 3 : 2)
           flush_moments(jrow + cur * ROW_STRIDE);
           drain(min(qn, 32));
         }
-        cp_async_wait_all();
-        const float4 X = lds128(myP), U = lds128(myP + 32 * sizeof(float4));
-        if (i + 32 < end) {
-          cp_async16(myP, A.xi4 + i + 32);
-          cp_async16(myP + 32 * sizeof(float4), A.pxi4 + i + 32);
+        // all but the NST - 1 youngest groups have landed: this chunk's stage is complete
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
+        const float4 X = lds128(myP), U = lds128(myP + PSTRIDE);
+        if (i + 32 * NST < end) {
+          cp_async16(myP, A.xi4 + i + 32 * NST);
+          cp_async16(myP + PSTRIDE, A.pxi4 + i + 32 * NST);
         }
         cp_async_commit();
+        myP = (myP & ~(RING - 1)) | ((myP + STAGE_BYTES) & (RING - 1));
         // ---- gather, Boris, move (the reference's arithmetic, pic_math.cuh)
         bool cross = false;
         float dx[3] = {0.f, 0.f, 0.f}, xa[3] = {0.f, 0.f, 0.f}; // displacement, centred offset

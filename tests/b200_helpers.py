@@ -90,8 +90,9 @@ def gpu_state(og, flds, prts, off, options=None):
     return grid, mprts, mflds
 
 
-def gpu_push(options=None, sort_first=False):
-    """push(grid, flds, prts, off) backend running the CUDA path through the C ABI"""
+def gpu_push(options=None, sort_first=False, expect_lean=None):
+    """push(grid, flds, prts, off) backend running the CUDA path through the C ABI;
+    expect_lean: assert that k_push_lean did (True) / did not (False) take the push"""
     import psc_b200 as pb
 
     def push(og, flds, prts, off):
@@ -99,6 +100,9 @@ def gpu_push(options=None, sort_first=False):
         if sort_first:
             pb.Sort()(mprts)
         pb.PushParticles().push_mprts(mprts, mflds)
+        if expect_lean is not None:
+            assert (grid.get_stat("lean_pushes") >= 1) == expect_lean, "k_push_lean %s" % (
+                "did not run" if expect_lean else "ran")
         got, got_off = mprts.get()
         assert np.array_equal(got_off, off)
         prts[:] = got

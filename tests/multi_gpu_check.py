@@ -25,10 +25,12 @@ import psc_b200 as pb  # noqa: E402
 from gen import random_fields, thermal_plasma  # noqa: E402
 
 KINDS = ((-1., 1.), (1., 100.))
+# (xyz patches are 16 x 8 x 8 cells: multiples of k_push_lean's 16 x 4 x 4 tile, so that the multi-rank
+# cases run the headline kernel and its listing of the remote leavers)
 CASES = {
-    "xyz_periodic_slabs": dict(gdims=(16, 16, 32), length=(16., 16., 32.), np_=(2, 2, 4)),
+    "xyz_periodic_slabs": dict(gdims=(32, 16, 32), length=(32., 16., 32.), np_=(2, 2, 4)),
     "yz_periodic": dict(gdims=(1, 32, 64), length=(1., 32., 64.), np_=(1, 2, 4)),
-    "xyz_wall_z": dict(gdims=(16, 16, 32), length=(16., 16., 32.), np_=(2, 2, 4),
+    "xyz_wall_z": dict(gdims=(32, 16, 32), length=(32., 16., 32.), np_=(2, 2, 4),
                        bc_fld_lo=[1, 1, 2], bc_fld_hi=[1, 1, 2], bc_prt_lo=[1, 1, 0], bc_prt_hi=[1, 1, 0]),
 }
 
@@ -66,7 +68,7 @@ def gather_obj(obj, rank, world):
 # that moves two cells breaks the fused pass's precondition on the rank that owns it): dz = 0.25 <
 # v dt.  Both paths issue exactly one particle exchange per call over the same neighbour tables,
 # which is what keeps the ranks in step (fused_sort.cu, fused_bnd_sort).
-FALLBACK_CASE = dict(gdims=(16, 16, 32), length=(16., 16., 8.), np_=(2, 2, 4))
+FALLBACK_CASE = dict(gdims=(32, 16, 32), length=(32., 16., 8.), np_=(2, 2, 4))
 
 
 def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=None, balance_step=None,
@@ -163,7 +165,8 @@ def run_case(name, gkw, rank, world, local_rank, fused, n_steps=3, n_by_rank=Non
         # and the energies of the last step as reduced inside it
         j_dev = mflds.download(pb.JXI, pb.JXI + 3)
         assert np.array_equal(h_j, j_dev), "J downloaded inside the step differs from the device's"
-    stats = dict(fused=grid.get_stat("fused_steps"), fallbacks=grid.get_stat("fused_fallbacks"))
+    stats = dict(fused=grid.get_stat("fused_steps"), fallbacks=grid.get_stat("fused_fallbacks"),
+                 lean=grid.get_stat("lean_pushes"))
     res = gather_obj((gp, go, gf, stats, en_in_step if pipelined else None), rank, world)
     ok = True
     info = None

@@ -22,7 +22,19 @@ from test_gpu_gapped import CASES, KINDS, _run_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _steps_vs_oracle(og, flds, prts, off, k, opts, jtol=1e-5):
+def _lean_grid(gkw):
+    """the same case with patches 16 cells wide in x (k_push_lean's tile is 16 x 4 x 4 cells;
+    narrower patches take k_push_tiled's run-time geometry), cell size unchanged"""
+    gkw = dict(gkw)
+    g, n, l = list(gkw["gdims"]), gkw["np_"], list(gkw["length"])
+    if g[0] > 1 and (g[0] // n[0]) % 16:
+        f = 16 * n[0] / g[0]
+        g[0], l[0] = 16 * n[0], l[0] * f
+    gkw["gdims"], gkw["length"] = tuple(g), tuple(l)
+    return gkw
+
+
+def _steps_vs_oracle(og, flds, prts, off, k, opts, jtol=1e-5, expect_lean=None):
     import psc_b200 as pb
     rf, rp, ro, n_drop = _run_oracle(og, flds, prts, off, k)
     grid, mprts, mflds = gpu_state(og, flds, prts, off, dict(opts, gapped=0))
@@ -30,6 +42,8 @@ def _steps_vs_oracle(og, flds, prts, off, k, opts, jtol=1e-5):
     for _ in range(k):
         pb.check(grid.lib.psc_b200_step(grid.ctx, C.byref(prm)))
     assert grid.get_stat("fused_steps") == k and grid.get_stat("fused_fallbacks") == 0
+    if expect_lean is not None:
+        assert grid.get_stat("lean_pushes") == (k if expect_lean else 0)
     j = mflds.download(0, 3)
     got, got_off = mprts.get()
     assert np.array_equal(got_off, ro)
@@ -48,12 +62,15 @@ def _steps_vs_oracle(og, flds, prts, off, k, opts, jtol=1e-5):
 @pytest.mark.parametrize("name", list(CASES))
 def test_default_path_steps_bit_exact(name, vth, k, lean):
     gkw, opts = CASES[name]
+    takes_lean = bool(lean) and "tile" not in opts
+    if takes_lean:
+        gkw = _lean_grid(gkw)
     dx = [l / g for l, g in zip(gkw["length"], gkw["gdims"])]
     dt = 0.45 * min(d for d, g in zip(dx, gkw["gdims"]) if g > 1)
     og = ol.Grid(dt=dt, kinds=KINDS, nicell=6, **gkw)
     flds = random_fields(og, seed=11)
     prts, off = thermal_plasma(og, ppc=6, seed=12, vth=(vth, vth / 10))
-    n_drop = _steps_vs_oracle(og, flds, prts, off, k, dict(opts, lean=lean))
+    n_drop = _steps_vs_oracle(og, flds, prts, off, k, dict(opts, lean=lean), expect_lean=takes_lean)
     if "absorbing" in name and vth > 0.1:
         assert n_drop > 0
 
@@ -69,4 +86,4 @@ def test_baseline_shape_two_steps_bit_exact(lean):
     ol.fill_ghosts(og, flds, 3, 9)
     prts, off = thermal_plasma(og, ppc=32, seed=22, vth=(0.05, 0.005))
     assert len(prts) == 64 ** 3 * 64
-    _steps_vs_oracle(og, flds, prts, off, 2, dict(lean=lean))
+    _steps_vs_oracle(og, flds, prts, off, 2, dict(lean=lean), expect_lean=True)
